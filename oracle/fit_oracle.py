@@ -1,0 +1,202 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU (numpy, float64) restatement of the per-SNP fit.
+
+PARITY UNPINNED.  The arithmetic below is what the reference delegates to OpenMx
+(`DESCRIPTION:49-51`, Depends: OpenMx >= 2.19.8), an un-vendored CRAN dependency that is
+absent from /root/reference and from this image (no R either).  It is restated from
+the published algorithms that OpenMx's WLS path implements, anchored on the reference's
+own call sites:
+  * R/model.R:5      mxFitFunctionWLS(allContinuousMethod="marginals"), full weight
+  * R/model.R:497-503  continuousType <- 'cumulants', mean structure dropped
+  * R/model.R:435-436  mxData(type='raw', minVariance=2*minMAF*(1-minMAF), naAction='omit')
+  * R/model.R:427-434  gxe: data column snp_<E> = data.snp * data.<E>
+  * R/model.R:166-168  mxComputeGradientDescent(nudgeZeroStarts=FALSE) + mxComputeStandardError()
+  * R/model.R:188      mxComputeSetOriginalStarts: every SNP starts from the builder's starts
+  * R/model.R:191-192  checkpoint row: estimates, vcov, statusCode, catch1
+Published algorithms restated here:
+  * cumulants summary statistics + ADF weight: Browne (1984); sample covariance s (N-1
+    denominator) and Gamma[(ij),(kl)] = m_ijkl - s~_ij s~_kl with N-denominator moments
+    (same construction as lavaan's lav_samplestats_Gamma, which OpenMx's
+    omxData::wlsAllContinuousCumulants states it follows); W = N * Gamma^{-1}
+  * RAM expectation: McArdle & McDonald (1984): Sigma = F (I-A)^-1 S (I-A)^-T F'
+  * WLS discrepancy F = (s - sigma)' W (s - sigma); vcov = (J' W J)^-1
+The only reference-side numeric pins for this part need R's RNG; what is
+checked instead (tests/test_oracle_fit.py): the closed form of the saturated buildItem
+model, agreement with scipy's generic optimiser on the same objective, finite-difference
+Jacobians, and recovery of simulated parameters within their standard errors.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this.
+"""
+import numpy as np
+
+
+# ------------------------------------------------------------------ summary statistics
+
+def vech_pairs(p):
+    """(i, j) with i >= j, column-major lower triangle (OpenMx vech order)."""
+    return [(i, j) for j in range(p) for i in range(j, p)]
+
+
+def cumulants_stats(X):
+    """X[n, p] complete rows.  Returns (s = vech(cov), Gamma, n)."""
+    n, p = X.shape
+    d = X - X.mean(0)
+    cov = d.T @ d / (n - 1)
+    pairs = vech_pairs(p)
+    Z = np.stack([d[:, i] * d[:, j] for i, j in pairs], 1)
+    Zc = Z - Z.mean(0)
+    gamma = Zc.T @ Zc / n
+    s = np.array([cov[i, j] for i, j in pairs])
+    return s, gamma, n
+
+
+# --------------------------------------------------------------------- RAM expectation
+
+class FlatRAM:
+    def __init__(self, flat):
+        self.f = flat
+        self.nv, self.nm = flat["nv"], flat["nm"]
+        self.cells = [(int(m), int(r), int(c), int(p), v) for m, r, c, p, v in flat["cells"]]
+        self.P = len(flat["par_names"])
+
+    def matrices(self, theta):
+        nv = self.nv
+        A = np.zeros((nv, nv)); S = np.zeros((nv, nv)); M = np.zeros(nv)
+        for m, r, c, p, v in self.cells:
+            val = theta[p] if p >= 0 else v
+            if m == 0: A[r, c] = val
+            elif m == 1: S[r, c] = val
+            else: M[c] = val
+        return A, S, M
+
+    def implied(self, theta):
+        """(Sigma[nm,nm], mu[nm]) of the manifest variables."""
+        A, S, M = self.matrices(theta)
+        Z = np.linalg.inv(np.eye(self.nv) - A)
+        C = Z @ S @ Z.T
+        return C[:self.nm, :self.nm], (Z @ M)[:self.nm]
+
+    def implied_jac(self, theta):
+        """d Sigma / d theta_k and d mu / d theta_k (analytic)."""
+        A, S, M = self.matrices(theta)
+        nv, nm = self.nv, self.nm
+        Z = np.linalg.inv(np.eye(nv) - A)
+        C = Z @ S @ Z.T
+        zm = Z @ M
+        dS = np.zeros((self.P, nm, nm)); dmu = np.zeros((self.P, nm))
+        for m, r, c, p, v in self.cells:
+            if p < 0:
+                continue
+            if m == 0:      # A[r,c]: dZ = Z E_rc Z
+                t = np.outer(Z[:, r], C[c, :])
+                dS[p] += (t + t.T)[:nm, :nm]
+                dmu[p] += Z[:nm, r] * zm[c]
+            elif m == 1:    # S[r,c] (each symmetric cell listed separately)
+                dS[p] += np.outer(Z[:, r], Z[:, c])[:nm, :nm]
+            else:
+                dmu[p] += Z[:nm, c]
+        return dS, dmu
+
+
+def sigma_cumulants(ram, theta):
+    Sig, _ = ram.implied(theta)
+    return np.array([Sig[i, j] for i, j in vech_pairs(ram.nm)])
+
+
+def jac_cumulants(ram, theta):
+    dS, _ = ram.implied_jac(theta)
+    pairs = vech_pairs(ram.nm)
+    return np.stack([[dS[k][i, j] for i, j in pairs] for k in range(ram.P)], 1)  # [q, P]
+
+
+# ------------------------------------------------------------------------- optimiser
+
+def wls_fit(s, W, sigma_fn, jac_fn, theta0, lbound, max_iter=200, tol=1e-10):
+    """Damped Gauss-Newton (Levenberg-Marquardt) on F = r'Wr with box lower bounds.
+    Returns (theta, F, iterations, status) -- status in OpenMx's statusCode vocabulary."""
+    theta = np.array(theta0, float)
+    lb = np.where(np.isnan(lbound), -np.inf, lbound)
+    r = s - sigma_fn(theta)
+    F = r @ W @ r
+    lam = 1e-4
+    status = "iteration limit/blue"
+    it = 0
+    for it in range(1, max_iter + 1):
+        J = jac_fn(theta)
+        g = J.T @ W @ r
+        H = J.T @ W @ J
+        improved = False
+        for _ in range(30):
+            try:
+                delta = np.linalg.solve(H + lam * np.diag(np.maximum(np.diag(H), 1e-12)), g)
+            except np.linalg.LinAlgError:
+                lam *= 10
+                continue
+            cand = np.maximum(theta + delta, lb)
+            rc = s - sigma_fn(cand)
+            Fc = rc @ W @ rc
+            if np.isfinite(Fc) and Fc <= F:
+                improved = True
+                break
+            lam *= 10
+        if not improved:
+            status = "OK" if np.max(np.abs(g)) < 1e-6 * (1 + F) else "nonzero gradient/red"
+            break
+        step = np.max(np.abs(cand - theta) / (np.abs(theta) + 1e-3))
+        dF = F - Fc
+        theta, r, F = cand, rc, Fc
+        lam = max(lam / 10, 1e-12)
+        if step < tol or dF <= 1e-14 * (1 + F):
+            status = "OK"
+            break
+    return theta, F, it, status
+
+
+# --------------------------------------------------------------- one SNP, cumulants WLS
+
+def snp_columns(flat, pheno_cols, snp):
+    """Manifest data matrix for one SNP (OpenMx data refresh: snp column, gxe products,
+    naAction='omit').  pheno_cols: {name: float array over people}."""
+    cols = []
+    for name in flat["manifest"]:
+        if name == "snp":
+            cols.append(snp)
+        elif name.startswith("snp_") and name[4:] in flat["gxe"]:
+            cols.append(snp * pheno_cols[name[4:]])
+        else:
+            cols.append(pheno_cols[name])
+    X = np.stack(cols, 1)
+    keep = np.isfinite(X).all(1)
+    return X[keep]
+
+
+def fit_snp_cumulants(flat, pheno_cols, snp):
+    """One row of the GWAS loop for a WLS/cumulants model.  Returns dict(est, vcov, status,
+    catch1, fit, n, iterations)."""
+    ram = FlatRAM(flat)
+    names = flat["par_names"]
+    out = dict(est=np.array(flat["par_start"], float), vcov=np.full((ram.P, ram.P), np.nan), status="NA",
+               catch1="", fit=np.nan, n=0, iterations=0)
+    X = snp_columns(flat, pheno_cols, snp)
+    out["n"] = len(X)
+    var = X.var(0, ddof=1) if len(X) > 1 else np.zeros(X.shape[1])
+    for j, name in enumerate(flat["manifest"]):
+        if not (var[j] >= flat["min_variance"]):
+            out["catch1"] = (f"{flat['name']}.data: '{name}' has observed variance less than "
+                             f"{flat['min_variance']:g}")
+            return out
+    s, gamma, n = cumulants_stats(X)
+    try:
+        W = n * np.linalg.inv(gamma)
+        np.linalg.cholesky(gamma)
+    except np.linalg.LinAlgError:
+        out["catch1"] = f"{flat['name']}.data: asymptotic covariance matrix is not positive definite"
+        return out
+    theta, F, it, status = wls_fit(s, W, lambda t: sigma_cumulants(ram, t), lambda t: jac_cumulants(ram, t),
+                                   flat["par_start"], flat["par_lbound"])
+    J = jac_cumulants(ram, theta)
+    try:
+        vcov = np.linalg.inv(J.T @ W @ J)
+    except np.linalg.LinAlgError:
+        vcov = np.full((ram.P, ram.P), np.nan)
+    out.update(est=theta, vcov=vcov, status=status, fit=F, iterations=it)
+    return out
