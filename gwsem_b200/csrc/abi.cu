@@ -1,0 +1,187 @@
+// extern "C" surface of libgwsem_b200.so (include/gwsem_b200.h).
+#include <cstring>
+#include <mutex>
+
+#include "common.h"
+#include "kernels.h"
+#include "model.h"
+
+namespace gwsem {
+
+static thread_local std::string g_error;
+
+void set_error(const char* fmt, ...) {
+  char buf[2048];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+}
+
+std::string format(const char* fmt, ...) {
+  char buf[2048];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  return buf;
+}
+
+void fail(const char* fmt, ...) {
+  char buf[2048];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  throw Error(buf);
+}
+
+}  // namespace gwsem
+
+using namespace gwsem;
+
+extern "C" {
+
+int gwsem_abi_version(void) { return GWSEM_ABI_VERSION; }
+const char* gwsem_last_error(void) { return g_error.c_str(); }
+
+int gwsem_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int gwsem_engine_create(int device, gwsem_engine** out) {
+  return guarded([&] {
+    int n = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess || n == 0)
+      fail("no usable CUDA device (%s): gwsem_b200 has no CPU fallback", err == cudaSuccess ? "device count is 0" : cudaGetErrorString(err));
+    if (device < 0 || device >= n) fail("device %d out of range (0..%d)", device, n - 1);
+    GW_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GW_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) fail("device %d is sm_%d%d; this build targets sm_100a (B200)", device, prop.major, prop.minor);
+    auto* e = new gwsem_engine;
+    e->device = device;
+    e->sm_count = prop.multiProcessorCount;
+    GW_CUDA(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    e->stream = e->own_stream;
+    *out = e;
+  });
+}
+
+void gwsem_engine_destroy(gwsem_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  delete e;
+}
+
+int gwsem_engine_set_stream(gwsem_engine* e, void* cuda_stream) {
+  return guarded([&] { e->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->own_stream; });
+}
+
+int gwsem_engine_synchronize(gwsem_engine* e) {
+  return guarded([&] {
+    GW_CUDA(cudaSetDevice(e->device));
+    GW_CUDA(cudaStreamSynchronize(e->stream));
+  });
+}
+
+int64_t gwsem_engine_launch_count(const gwsem_engine* e) { return e->launches; }
+
+int gwsem_decode_2bit_device(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int n_samples,
+                             int plink1, const int32_t* d_dest_of, int dest_rows, double* d_out, double* d_maf) {
+  return guarded([&] {
+    GW_CUDA(cudaSetDevice(e->device));
+    launch_decode_2bit(e, d_packed, pitch, n_snps, n_samples, plink1, d_dest_of, dest_rows, d_out, d_maf);
+  });
+}
+
+int gwsem_decode_2bit(gwsem_engine* e, const uint8_t* packed, int64_t pitch, int n_snps, int n_samples, int plink1,
+                      const int32_t* row_filter, double* out, double* maf) {
+  return guarded([&] {
+    GW_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    const int64_t row_bytes = (n_samples + 3) / 4;
+    if (pitch < row_bytes) fail("pitch %lld smaller than record (%lld bytes)", (long long)pitch, (long long)row_bytes);
+    int dest_rows = n_samples;
+    const int32_t* d_dest = nullptr;
+    if (row_filter) {
+      std::vector<int32_t> dest_of(n_samples);
+      dest_rows = 0;
+      for (int s = 0; s < n_samples; ++s) dest_of[s] = row_filter[s] ? -1 : dest_rows++;
+      e->d_dest_of.upload(dest_of.data(), n_samples, st);
+      GW_CUDA(cudaStreamSynchronize(st));  // dest_of is a local
+      d_dest = e->d_dest_of.p;
+    }
+    // bound the double matrix held on the device
+    const int batch = (int)std::max<int64_t>(1, std::min<int64_t>(n_snps, (int64_t)(1u << 28) / std::max(dest_rows, 1)));
+    for (int s0 = 0; s0 < n_snps; s0 += batch) {
+      const int n = std::min(batch, n_snps - s0);
+      e->d_packed.ensure((size_t)n * row_bytes);
+      e->d_rows.ensure((size_t)n * dest_rows);
+      e->d_maf.ensure(n);
+      GW_CUDA(cudaMemcpy2DAsync(e->d_packed.p, row_bytes, packed + (int64_t)s0 * pitch, pitch, row_bytes, n,
+                                cudaMemcpyHostToDevice, st));
+      launch_decode_2bit(e, e->d_packed.p, row_bytes, n, n_samples, plink1, d_dest, dest_rows, e->d_rows.p, e->d_maf.p);
+      GW_CUDA(cudaMemcpyAsync(out + (size_t)s0 * dest_rows, e->d_rows.p, sizeof(double) * (size_t)n * dest_rows,
+                              cudaMemcpyDeviceToHost, st));
+      if (maf) GW_CUDA(cudaMemcpyAsync(maf + s0, e->d_maf.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+      GW_CUDA(cudaStreamSynchronize(st));
+    }
+  });
+}
+
+int gwsem_model_create(gwsem_engine* e, const gwsem_model_spec* spec, gwsem_model** out) {
+  return guarded([&] {
+    GW_CUDA(cudaSetDevice(e->device));
+    *out = new gwsem_model(e, spec);
+  });
+}
+
+void gwsem_model_destroy(gwsem_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->engine->device);
+  cudaStreamSynchronize(m->engine->stream);
+  delete m;
+}
+
+int gwsem_model_set_row_filter(gwsem_model* m, const int32_t* row_filter, int src_rows) {
+  return guarded([&] { m->prepare(row_filter, src_rows); });
+}
+
+int gwsem_fit_2bit_device(gwsem_model* m, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
+                          const gwsem_result* d_res) {
+  return guarded([&] { m->fit_2bit_device(d_packed, pitch, n_snps, plink1, *d_res); });
+}
+
+int gwsem_fit_2bit(gwsem_model* m, const uint8_t* packed, int64_t pitch, int n_snps, int plink1,
+                   const gwsem_result* res) {
+  return guarded([&] { m->fit_2bit_host(packed, pitch, n_snps, plink1, *res); });
+}
+
+}  // extern "C"
+
+// ---- not yet implemented entry points (declared in the header; fail loudly)
+extern "C" {
+#define GW_TODO(name) return guarded([&] { fail(name ": not implemented yet"); })
+int gwsem_source_open(const char*, const char*, int, gwsem_source**) { GW_TODO("gwsem_source_open"); }
+void gwsem_source_close(gwsem_source*) {}
+int gwsem_source_num_variants(const gwsem_source*) { return -1; }
+int gwsem_source_num_samples(const gwsem_source*) { return -1; }
+int gwsem_source_load_counter(const gwsem_source*) { return 0; }
+const char* gwsem_source_checkpoint_columns(const gwsem_source*) { return ""; }
+int gwsem_source_context(gwsem_source*, int, char*, size_t) { GW_TODO("gwsem_source_context"); }
+int gwsem_source_load_rows(gwsem_engine*, gwsem_source*, const int32_t*, int, const int32_t*, double*, double*) {
+  GW_TODO("gwsem_source_load_rows");
+}
+int gwsem_fit_rows_device(gwsem_model*, const double*, int, const gwsem_result*) { GW_TODO("gwsem_fit_rows_device"); }
+int gwsem_gwas_run(gwsem_model*, gwsem_source*, const gwsem_job*, int64_t*) { GW_TODO("gwsem_gwas_run"); }
+}

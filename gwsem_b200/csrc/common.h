@@ -1,0 +1,86 @@
+// Shared declarations of the gwsem_b200 engine (internal; the public surface is
+// include/gwsem_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/gwsem_b200.h"
+
+namespace gwsem {
+
+void set_error(const char* fmt, ...);
+std::string format(const char* fmt, ...);
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+[[noreturn]] void fail(const char* fmt, ...);
+
+#define GW_CUDA(call)                                                                   \
+  do {                                                                                  \
+    cudaError_t err__ = (call);                                                         \
+    if (err__ != cudaSuccess)                                                           \
+      ::gwsem::fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+  } while (0)
+
+// Wraps an extern "C" entry point body: exceptions never cross the ABI.
+template <typename F>
+int guarded(F&& body) {
+  try {
+    body();
+    return 0;
+  } catch (const std::exception& e) {
+    set_error("%s", e.what());
+    return 1;
+  } catch (...) {
+    set_error("unknown error");
+    return 1;
+  }
+}
+
+template <typename T>
+struct DeviceBuffer {
+  T* p = nullptr;
+  size_t n = 0;
+  DeviceBuffer() = default;
+  DeviceBuffer(const DeviceBuffer&) = delete;
+  DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+  DeviceBuffer(DeviceBuffer&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  ~DeviceBuffer() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void ensure(size_t count) {
+    if (count <= n) return;
+    release();
+    GW_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    n = count;
+  }
+  void upload(const T* host, size_t count, cudaStream_t st) {
+    ensure(count);
+    GW_CUDA(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, st));
+  }
+};
+
+}  // namespace gwsem
+
+struct gwsem_engine {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+  // scratch reused by the host-pointer entry points
+  gwsem::DeviceBuffer<uint8_t> d_packed;
+  gwsem::DeviceBuffer<double> d_rows, d_maf;
+  gwsem::DeviceBuffer<int32_t> d_dest_of;
+  gwsem::DeviceBuffer<unsigned long long> d_maf_acc;
+};

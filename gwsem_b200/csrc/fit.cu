@@ -1,0 +1,432 @@
+// Per-SNP WLS fit (cumulants summary statistics), one warp per SNP.
+//
+// What OpenMx does per loop iteration of the plan built by prepareComputePlan
+// (reference R/model.R:187-194), restated for the GPU:
+//   O1  naAction='omit' (people with a missing call leave every statistic), minVariance check
+//   O2  sample covariance s (N-1) and ADF weight: Gamma[(ij),(kl)] = m_ijkl - s~_ij s~_kl (N)
+//   O5  RAM expectation  Sigma = F (I-A)^-1 S (I-A)^-T F'
+//   O6  F(theta) = (s - sigma)' W (s - sigma),  W = N Gamma^-1
+//   O7  optimisation from the original start values (damped Gauss-Newton, analytic Jacobian,
+//       lower bounds by projection)
+//   O8  vcov = (J' W J)^-1
+// The arithmetic mirrors oracle/fit_oracle.py step for step (same damping schedule), so the
+// parity tests compare like with like.  All FP64.
+#include "common.h"
+#include "fit_program.h"
+#include "kernels.h"
+
+namespace gwsem {
+
+struct WarpScratch {
+  // offsets in doubles into the per-warp shared-memory slab
+  int R, mu, c2, sobs, L, theta, cand, A, S, Z, C, T, sig, r, rc, J, g, H, Hc, delta, total;
+};
+
+__host__ __device__ inline WarpScratch scratch_layout(int p, int q, int nv, int P, int nf) {
+  WarpScratch w;
+  int o = 0;
+  auto take = [&](int n) { int at = o; o += n; return at; };
+  w.R = take(5 * nf);
+  w.mu = take(p);
+  w.c2 = take(q);
+  w.sobs = take(q);
+  w.L = take(q * q);
+  w.theta = take(P);
+  w.cand = take(P);
+  w.A = take(nv * nv);
+  w.S = take(nv * nv);
+  w.Z = take(nv * nv);
+  w.C = take(nv * nv);
+  w.T = take(nv * nv);
+  w.sig = take(q);
+  w.r = take(q);
+  w.rc = take(q);
+  w.J = take(q * P);
+  w.g = take(P);
+  w.H = take(P * P);
+  w.Hc = take(P * P);
+  w.delta = take(P);
+  w.total = o;
+  return w;
+}
+
+size_t fit_scratch_doubles(int p, int q, int nv, int P, int nf) { return scratch_layout(p, q, nv, P, nf).total; }
+
+__device__ __forceinline__ int vech_index(int i, int j, int p) {  // i >= j, column-major lower triangle
+  return j * p - j * (j - 1) / 2 + (i - j);
+}
+
+// In-place Cholesky (lower) of the n x n row-major matrix a; returns false if not positive definite.
+__device__ bool warp_cholesky(double* a, int n, int lane) {
+  for (int j = 0; j < n; ++j) {
+    double d = 0.0;
+    if (lane == 0) {
+      d = a[j * n + j];
+      for (int k = 0; k < j; ++k) d -= a[j * n + k] * a[j * n + k];
+    }
+    d = __shfl_sync(0xffffffffu, d, 0);
+    if (!(d > 0.0) || !isfinite(d)) return false;
+    const double dj = sqrt(d);
+    if (lane == 0) a[j * n + j] = dj;
+    for (int i = j + 1 + lane; i < n; i += 32) {
+      double v = a[i * n + j];
+      for (int k = 0; k < j; ++k) v -= a[i * n + k] * a[j * n + k];
+      a[i * n + j] = v / dj;
+    }
+    __syncwarp();
+  }
+  return true;
+}
+
+// Solve L y = b in place for `ncol` right-hand sides stored as columns of b (row-major n x ld).
+__device__ void warp_forward_solve(const double* L, int n, double* b, int ld, int ncol, int lane) {
+  for (int c = lane; c < ncol; c += 32) {
+    for (int i = 0; i < n; ++i) {
+      double v = b[i * ld + c];
+      for (int k = 0; k < i; ++k) v -= L[i * n + k] * b[k * ld + c];
+      b[i * ld + c] = v / L[i * n + i];
+    }
+  }
+  __syncwarp();
+}
+
+struct ModelEval {
+  const FitProgram& fp;
+  const WarpScratch& ws;
+  double* sm;
+  int lane;
+
+  // A, S <- theta;  Z = (I-A)^-1;  C = Z S Z';  sig = vech(C[:p,:p])
+  __device__ void implied(const double* theta, double* sig) {
+    const int nv = fp.nv, p = fp.p;
+    double *A = sm + ws.A, *S = sm + ws.S, *Z = sm + ws.Z, *C = sm + ws.C, *T = sm + ws.T;
+    for (int e = lane; e < nv * nv; e += 32) { A[e] = 0.0; S[e] = 0.0; Z[e] = (e / nv == e % nv) ? 1.0 : 0.0; }
+    __syncwarp();
+    for (int e = lane; e < fp.n_cells; e += 32) {
+      const int m = fp.cell_mat[e], r = fp.cell_row[e], c = fp.cell_col[e], k = fp.cell_par[e];
+      const double v = k >= 0 ? theta[k] : fp.cell_val[e];
+      if (m == 0) A[r * nv + c] = v;
+      else if (m == 1) S[r * nv + c] = v;
+    }
+    __syncwarp();
+    // Z = I + A + A^2 + ...   (A is nilpotent for recursive path models; nv terms suffice)
+    for (int e = lane; e < nv * nv; e += 32) T[e] = A[e];
+    __syncwarp();
+    for (int it = 0; it < nv; ++it) {
+      bool nz = false;
+      for (int e = lane; e < nv * nv; e += 32) { Z[e] += T[e]; nz |= (T[e] != 0.0); }
+      if (!__any_sync(0xffffffffu, nz)) break;
+      __syncwarp();
+      // C (temp) = T * A
+      for (int e = lane; e < nv * nv; e += 32) {
+        const int i = e / nv, j = e % nv;
+        double v = 0.0;
+        for (int k = 0; k < nv; ++k) v += T[i * nv + k] * A[k * nv + j];
+        C[e] = v;
+      }
+      __syncwarp();
+      for (int e = lane; e < nv * nv; e += 32) T[e] = C[e];
+      __syncwarp();
+    }
+    __syncwarp();
+    // T = Z S ; C = T Z'
+    for (int e = lane; e < nv * nv; e += 32) {
+      const int i = e / nv, j = e % nv;
+      double v = 0.0;
+      for (int k = 0; k < nv; ++k) v += Z[i * nv + k] * S[k * nv + j];
+      T[e] = v;
+    }
+    __syncwarp();
+    for (int e = lane; e < nv * nv; e += 32) {
+      const int i = e / nv, j = e % nv;
+      double v = 0.0;
+      for (int k = 0; k < nv; ++k) v += T[i * nv + k] * Z[j * nv + k];
+      C[e] = v;
+    }
+    __syncwarp();
+    for (int e = lane; e < fp.q; e += 32) sig[e] = C[fp.stat_i[e] * nv + fp.stat_j[e]];
+    __syncwarp();
+  }
+
+  // J[e][k] = d sig_e / d theta_k (uses Z, C left by implied())
+  __device__ void jacobian(double* J) {
+    const int nv = fp.nv, P = fp.P;
+    const double *Z = sm + ws.Z, *C = sm + ws.C;
+    for (int idx = lane; idx < fp.q * P; idx += 32) {
+      const int e = idx / P, k = idx % P;
+      const int i = fp.stat_i[e], j = fp.stat_j[e];
+      double v = 0.0;
+      for (int ce = fp.par_cell_ptr[k]; ce < fp.par_cell_ptr[k + 1]; ++ce) {
+        const int c_id = fp.par_cells[ce];
+        const int m = fp.cell_mat[c_id], r = fp.cell_row[c_id], c = fp.cell_col[c_id];
+        if (m == 0) v += Z[i * nv + r] * C[c * nv + j] + Z[j * nv + r] * C[c * nv + i];
+        else if (m == 1) v += Z[i * nv + r] * Z[j * nv + c];
+      }
+      J[idx] = v;
+    }
+    __syncwarp();
+  }
+};
+
+__device__ double central_moment(const FitProgram& fp, const int* vars, int k, const double* mu, const double* R,
+                                 double inv_n) {
+  const int p = fp.p, p1 = p + 1;
+  double sum = 0.0;
+  for (int mask = 0; mask < (1 << k); ++mask) {
+    int sel[4] = {p, p, p, p};
+    int c = 0;
+    double coef = 1.0;
+    for (int b = 0; b < k; ++b) {
+      if ((mask >> b) & 1) sel[c++] = vars[b];
+      else coef *= -mu[vars[b]];
+    }
+    double ev = 1.0;
+    if (c) ev = R[fp.idx4[((sel[0] * p1 + sel[1]) * p1 + sel[2]) * p1 + sel[3]]] * inv_n;
+    sum += coef * ev;
+  }
+  return sum;
+}
+
+__global__ void __launch_bounds__(128)
+    fit_cumulants_kernel(FitProgram fp, int n_snps, const int32_t* __restrict__ counts,
+                         const double* __restrict__ sums, const double* __restrict__ miss, gwsem_result res) {
+  extern __shared__ double smem_d[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int snp = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (snp >= n_snps) return;
+  const int p = fp.p, q = fp.q, nv = fp.nv, P = fp.P, nf = fp.nf;
+  const WarpScratch ws = scratch_layout(p, q, nv, P, nf);
+  double* sm = smem_d + (size_t)warp * ws.total;
+
+  const int n1 = counts[4 * snp], n2 = counts[4 * snp + 1], n3 = counts[4 * snp + 2];
+  const int n = fp.n_incl - n3;
+  const double inv_n = 1.0 / (double)n;
+  double* R = sm + ws.R;
+  // raw moment table R[a][f] = sum over complete rows of g^a * h_f
+  for (int e = lane; e < 5 * nf; e += 32) {
+    const int a = e / nf, f = e % nf;
+    double v;
+    if (a == 0) {
+      v = f == 0 ? (double)n : fp.tot[f] - miss[(int64_t)snp * fp.nfm + (f - 1)];
+    } else {
+      const double w2 = (double)(1 << a);
+      if (f == 0) v = (double)n1 + w2 * (double)n2;
+      else if (f - 1 < fp.nfd)
+        v = sums[(int64_t)snp * 2 * fp.nfd + (f - 1)] + w2 * sums[(int64_t)snp * 2 * fp.nfd + fp.nfd + (f - 1)];
+      else v = 0.0;
+    }
+    R[e] = v;
+  }
+  __syncwarp();
+
+  double* est = res.est + (int64_t)snp * P;
+  double* vcov = res.vcov + (int64_t)snp * P * P;
+  for (int k = lane; k < P; k += 32) est[k] = fp.par_start[k];
+  for (int k = lane; k < P * P; k += 32) vcov[k] = __longlong_as_double((long long)GWSEM_NA_BITS);
+  if (lane == 0) {
+    double maf = ((double)n1 + 2.0 * (double)n2) / (2.0 * (double)n);
+    if (maf > 0.5) maf = 1 - maf;
+    res.maf[snp] = maf;
+    res.n_used[snp] = n;
+    res.fit[snp] = __longlong_as_double((long long)GWSEM_NA_BITS);
+    res.status[snp] = GWSEM_STATUS_NA;
+    res.catch_code[snp] = GWSEM_CATCH_NONE;
+    res.catch_var[snp] = -1;
+    res.iterations[snp] = 0;
+  }
+
+  // ---- O1/O2: means, covariance, Gamma
+  double* mu = sm + ws.mu;
+  for (int v = lane; v < p; v += 32) mu[v] = R[fp.idx4[((v * (p + 1) + p) * (p + 1) + p) * (p + 1) + p]] * inv_n;
+  __syncwarp();
+  double* c2 = sm + ws.c2;      // N-denominator central second moments
+  double* sobs = sm + ws.sobs;  // N-1 denominator: the observed covariance statistics
+  const double nm1 = (double)n / (double)(n - 1);
+  for (int e = lane; e < q; e += 32) {
+    const int vars[2] = {fp.stat_j[e], fp.stat_i[e]};  // sorted ascending (j <= i)
+    const double m = central_moment(fp, vars, 2, mu, R, inv_n);
+    c2[e] = m;
+    sobs[e] = m * nm1;
+  }
+  __syncwarp();
+  int bad_var = -1;
+  for (int v = 0; v < p; ++v) {
+    const double var = sobs[vech_index(v, v, p)];
+    if (!(var >= fp.min_variance)) { bad_var = v; break; }
+  }
+  if (n < 2) bad_var = 0;
+  if (bad_var >= 0) {
+    if (lane == 0) { res.catch_code[snp] = GWSEM_CATCH_MIN_VARIANCE; res.catch_var[snp] = bad_var; }
+    return;
+  }
+  double* L = sm + ws.L;
+  for (int idx = lane; idx < q * q; idx += 32) {
+    const int e1 = idx / q, e2 = idx % q;
+    if (e2 > e1) { continue; }
+    int vars[4] = {fp.stat_j[e1], fp.stat_i[e1], fp.stat_j[e2], fp.stat_i[e2]};
+    // sort 4 ints
+    for (int a = 1; a < 4; ++a) {
+      const int key = vars[a];
+      int b = a - 1;
+      while (b >= 0 && vars[b] > key) { vars[b + 1] = vars[b]; --b; }
+      vars[b + 1] = key;
+    }
+    const double m4 = central_moment(fp, vars, 4, mu, R, inv_n);
+    const double gam = m4 - c2[e1] * c2[e2];
+    L[e1 * q + e2] = gam;
+    L[e2 * q + e1] = gam;
+  }
+  __syncwarp();
+  if (!warp_cholesky(L, q, lane)) {
+    if (lane == 0) res.catch_code[snp] = GWSEM_CATCH_ACOV_NOT_PD;
+    return;
+  }
+
+  // ---- O5-O7: damped Gauss-Newton on the whitened residual  r~ = L^-1 (s - sigma), F = n |r~|^2
+  double *theta = sm + ws.theta, *cand = sm + ws.cand, *sig = sm + ws.sig, *r = sm + ws.r, *J = sm + ws.J;
+  double *g = sm + ws.g, *H = sm + ws.H, *Hc = sm + ws.Hc, *delta = sm + ws.delta;
+  ModelEval ev{fp, ws, sm, lane};
+  const double dn = (double)n;
+
+  auto objective = [&](const double* th, double* resid) -> double {
+    ev.implied(th, sig);
+    for (int e = lane; e < q; e += 32) resid[e] = sobs[e] - sig[e];
+    __syncwarp();
+    warp_forward_solve(L, q, resid, 1, 1, lane);
+    double f = 0.0;
+    for (int e = 0; e < q; ++e) f += resid[e] * resid[e];
+    return dn * f;
+  };
+
+  for (int k = lane; k < P; k += 32) theta[k] = fp.par_start[k];
+  __syncwarp();
+  double F = objective(theta, r);
+  double lam = 1e-4;
+  int status = GWSEM_STATUS_ITERATION_LIMIT;
+  int it = 0;
+  const int max_iter = 200;
+  for (it = 1; it <= max_iter; ++it) {
+    // implied() for theta was the last evaluation at this point (Z, C valid)
+    ev.implied(theta, sig);
+    ev.jacobian(J);
+    warp_forward_solve(L, q, J, P, P, lane);  // J~ = L^-1 J
+    for (int k = lane; k < P; k += 32) {
+      double v = 0.0;
+      for (int e = 0; e < q; ++e) v += J[e * P + k] * r[e];
+      g[k] = dn * v;
+    }
+    for (int idx = lane; idx < P * P; idx += 32) {
+      const int a = idx / P, b = idx % P;
+      double v = 0.0;
+      for (int e = 0; e < q; ++e) v += J[e * P + a] * J[e * P + b];
+      H[idx] = dn * v;
+    }
+    __syncwarp();
+    bool improved = false;
+    double Fc = F;
+    for (int attempt = 0; attempt < 30; ++attempt) {
+      for (int idx = lane; idx < P * P; idx += 32) {
+        const int a = idx / P, b = idx % P;
+        double v = H[idx];
+        if (a == b) v += lam * fmax(H[idx], 1e-12);
+        Hc[idx] = v;
+      }
+      __syncwarp();
+      if (!warp_cholesky(Hc, P, lane)) { lam *= 10; continue; }
+      if (lane == 0) {  // solve Hc Hc' delta = g
+        for (int i = 0; i < P; ++i) {
+          double v = g[i];
+          for (int k = 0; k < i; ++k) v -= Hc[i * P + k] * delta[k];
+          delta[i] = v / Hc[i * P + i];
+        }
+        for (int i = P - 1; i >= 0; --i) {
+          double v = delta[i];
+          for (int k = i + 1; k < P; ++k) v -= Hc[k * P + i] * delta[k];
+          delta[i] = v / Hc[i * P + i];
+        }
+      }
+      __syncwarp();
+      for (int k = lane; k < P; k += 32) {
+        double c = theta[k] + delta[k];
+        const double lb = fp.par_lbound[k];
+        if (lb == lb && c < lb) c = lb;
+        cand[k] = c;
+      }
+      __syncwarp();
+      Fc = objective(cand, sm + ws.rc);
+      if (isfinite(Fc) && Fc <= F) { improved = true; break; }
+      lam *= 10;
+    }
+    if (!improved) {
+      double gmax = 0.0;
+      for (int k = 0; k < P; ++k) gmax = fmax(gmax, fabs(g[k]));
+      status = gmax < 1e-6 * (1 + F) ? GWSEM_STATUS_OK : GWSEM_STATUS_NONZERO_GRADIENT;
+      break;
+    }
+    double step = 0.0;
+    for (int k = 0; k < P; ++k) step = fmax(step, fabs(cand[k] - theta[k]) / (fabs(theta[k]) + 1e-3));
+    const double dF = F - Fc;
+    __syncwarp();
+    for (int k = lane; k < P; k += 32) theta[k] = cand[k];
+    for (int e = lane; e < q; e += 32) r[e] = (sm + ws.rc)[e];
+    __syncwarp();
+    F = Fc;
+    lam = fmax(lam / 10, 1e-12);
+    if (step < 1e-10 || dF <= 1e-14 * (1 + F)) { status = GWSEM_STATUS_OK; break; }
+  }
+  if (it > max_iter) it = max_iter;
+
+  // ---- O8: vcov = (J' W J)^-1 at the solution
+  ev.implied(theta, sig);
+  ev.jacobian(J);
+  warp_forward_solve(L, q, J, P, P, lane);
+  for (int idx = lane; idx < P * P; idx += 32) {
+    const int a = idx / P, b = idx % P;
+    double v = 0.0;
+    for (int e = 0; e < q; ++e) v += J[e * P + a] * J[e * P + b];
+    H[idx] = dn * v;
+  }
+  __syncwarp();
+  const bool pd = warp_cholesky(H, P, lane);
+  if (pd) {
+    // inverse via solves against the identity: column c handled by lane c
+    for (int c = lane; c < P; c += 32) {
+      double* x = Hc + c;  // column c of Hc (stride P)
+      for (int i = 0; i < P; ++i) {
+        double v = (i == c) ? 1.0 : 0.0;
+        for (int k = 0; k < i; ++k) v -= H[i * P + k] * x[k * P];
+        x[i * P] = v / H[i * P + i];
+      }
+      for (int i = P - 1; i >= 0; --i) {
+        double v = x[i * P];
+        for (int k = i + 1; k < P; ++k) v -= H[k * P + i] * x[k * P];
+        x[i * P] = v / H[i * P + i];
+      }
+    }
+    __syncwarp();
+    for (int idx = lane; idx < P * P; idx += 32) vcov[idx] = Hc[idx];
+  }
+  for (int k = lane; k < P; k += 32) est[k] = theta[k];
+  if (lane == 0) {
+    res.fit[snp] = F;
+    res.status[snp] = status;
+    res.iterations[snp] = it;
+  }
+}
+
+void launch_fit_cumulants(gwsem_engine* e, const FitProgram& fp, int n_snps, const int32_t* d_counts,
+                          const double* d_sums, const double* d_miss, const gwsem_result& d_res) {
+  if (n_snps <= 0) return;
+  const size_t per_warp = fit_scratch_doubles(fp.p, fp.q, fp.nv, fp.P, fp.nf) * sizeof(double);
+  int warps = 4;
+  while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
+  if (per_warp * warps > 227 * 1024) fail("model too large for the per-SNP fit kernel (%zu bytes of scratch)", per_warp);
+  const size_t smem = per_warp * warps;
+  GW_CUDA(cudaFuncSetAttribute(fit_cumulants_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (n_snps + warps - 1) / warps;
+  fit_cumulants_kernel<<<grid, warps * 32, smem, e->stream>>>(fp, n_snps, d_counts, d_sums, d_miss, d_res);
+  GW_CUDA(cudaGetLastError());
+  e->launches++;
+}
+
+}  // namespace gwsem

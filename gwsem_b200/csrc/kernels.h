@@ -1,0 +1,37 @@
+// Internal launch interfaces between the engine's translation units.
+#pragma once
+#include "common.h"
+
+namespace gwsem {
+
+// ---- decode.cu
+void launch_decode_2bit(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int n_samples,
+                        int plink1, const int32_t* d_dest_of, int dest_rows, double* d_out, double* d_maf);
+
+// ---- stats.cu : genotype-class sums of SNP-independent per-person features
+// Device-side description of the people axis, shared by all statistics kernels.
+struct PeopleLayout {
+  int n_src = 0;        // people in the genotype file (source rows)
+  int n_pad = 0;        // n_src rounded up to a multiple of 32
+  int n_incl = 0;       // people that enter the model (rowFilter == 0 and complete phenotype row)
+  const uint8_t* d_inc8 = nullptr;                // n_pad: 3 = included, 0 = excluded
+  const unsigned long long* d_incmask = nullptr;  // n_pad/32 words, 0b01 per included person
+};
+
+// classes 1 and 2 (het, hom-ALT) sums of `n_feat` feature rows (feature-major, n_pad doubles each):
+// d_sums[snp][2][n_feat].  Launches one kernel per chunk of <= 8 features.
+void launch_class_sums(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
+                       const PeopleLayout& pl, const double* d_feat, int n_feat, double* d_sums);
+
+// counts[snp][4] = {n_class1, n_class2, n_missing, 0} over included people and, for the missing
+// class, sums of `n_featm` person-major features (d_featT[person][n_featm_pad]): d_miss[snp][n_featm].
+void launch_count_missing(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
+                          const PeopleLayout& pl, const double* d_featT, int n_featm, int n_featm_pad,
+                          int32_t* d_counts, double* d_miss);
+
+// ---- fit.cu
+struct FitProgram;  // device-resident model description, built in model.cu
+void launch_fit_cumulants(gwsem_engine* e, const FitProgram& fp, int n_snps, const int32_t* d_counts,
+                          const double* d_sums, const double* d_miss, const gwsem_result& d_res);
+
+}  // namespace gwsem

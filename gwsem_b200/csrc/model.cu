@@ -1,0 +1,291 @@
+// Host side of a model: turns the flat RAM specification + phenotype columns into the
+// device-resident FitProgram (feature matrix, moment index tables, RAM cells) and runs the
+// per-batch kernel sequence.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+
+#include "common.h"
+#include "fit_program.h"
+#include "kernels.h"
+#include "model.h"
+
+namespace gwsem {
+
+template <typename T>
+static const T* upload_vec(std::vector<DeviceBuffer<uint8_t>>& pool, const std::vector<T>& v, cudaStream_t st) {
+  pool.emplace_back();
+  auto& b = pool.back();
+  b.ensure(std::max<size_t>(v.size() * sizeof(T), 16));
+  if (!v.empty()) GW_CUDA(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+  return reinterpret_cast<const T*>(b.p);
+}
+
+}  // namespace gwsem
+
+using namespace gwsem;
+
+gwsem_model::gwsem_model(gwsem_engine* e, const gwsem_model_spec* s) : engine(e) {
+  if (s->fit != 0) fail("only WLS with cumulants summary statistics (fit=0) is implemented on the device so far");
+  nv = s->n_vars;
+  p = s->n_manifest;
+  P = s->n_params;
+  n_rows = s->n_rows;
+  min_variance = s->min_variance;
+  if (p < 1 || nv < p || P < 1 || n_rows < 2) fail("degenerate model specification");
+  cells.assign(s->cells, s->cells + 5 * (size_t)s->n_cells);
+  par_start.assign(s->par_start, s->par_start + P);
+  par_lbound.assign(s->par_lbound, s->par_lbound + P);
+  kind.assign(s->manifest_kind, s->manifest_kind + p);
+  // distinct SNP-independent base columns
+  std::map<const double*, int> base_of;
+  var_base.assign(p, -1);
+  std::vector<bool> used_as_moderator;
+  for (int v = 0; v < p; ++v) {
+    if (kind[v] == 1) continue;
+    const double* col = s->manifest_data[v];
+    if (!col) fail("manifest variable %d has no data column", v);
+    auto it = base_of.find(col);
+    if (it == base_of.end()) {
+      it = base_of.emplace(col, (int)base.size()).first;
+      base.emplace_back(col, col + n_rows);
+      used_as_moderator.push_back(false);
+    }
+    var_base[v] = it->second;
+    if (kind[v] == 2) used_as_moderator[it->second] = true;
+  }
+  // naAction='omit' on the SNP-independent columns is static: drop those people once
+  row_ok.assign(n_rows, 1);
+  for (auto& col : base)
+    for (int r = 0; r < n_rows; ++r)
+      if (!std::isfinite(col[r])) row_ok[r] = 0;
+  // centre the pure phenotype columns (covariances are shift invariant; keeps moments well scaled)
+  for (size_t b = 0; b < base.size(); ++b) {
+    if (used_as_moderator[b]) continue;
+    long double sum = 0;
+    long cnt = 0;
+    for (int r = 0; r < n_rows; ++r)
+      if (row_ok[r]) { sum += base[b][r]; ++cnt; }
+    const double mean = cnt ? (double)(sum / cnt) : 0.0;
+    for (int r = 0; r < n_rows; ++r) base[b][r] -= mean;
+  }
+  build_program();
+}
+
+// Enumerate every multiset of <= 4 manifest variables; each is g^a times a monomial of base columns.
+void gwsem_model::build_program() {
+  const int p1 = p + 1;
+  q = p * (p + 1) / 2;
+  std::map<std::vector<int>, int> mono_id;  // monomial (sorted base columns) -> provisional id
+  std::vector<std::vector<int>> monos;
+  std::vector<bool> dense;
+  auto intern = [&](const std::vector<int>& m) {
+    auto it = mono_id.find(m);
+    if (it != mono_id.end()) return it->second;
+    mono_id.emplace(m, (int)monos.size());
+    monos.push_back(m);
+    dense.push_back(false);
+    return (int)monos.size() - 1;
+  };
+  intern({});  // the constant
+  struct Slot { int a, mono; };
+  std::vector<Slot> slot((size_t)p1 * p1 * p1 * p1, Slot{-1, -1});
+  int v[4];
+  for (v[0] = 0; v[0] <= p; ++v[0])
+    for (v[1] = v[0]; v[1] <= p; ++v[1])
+      for (v[2] = v[1]; v[2] <= p; ++v[2])
+        for (v[3] = v[2]; v[3] <= p; ++v[3]) {
+          if (v[0] == p) continue;  // empty multiset
+          int a = 0;
+          std::vector<int> m;
+          for (int k = 0; k < 4; ++k) {
+            if (v[k] == p) continue;
+            if (kind[v[k]] != 0) ++a;
+            if (var_base[v[k]] >= 0) m.push_back(var_base[v[k]]);
+          }
+          std::sort(m.begin(), m.end());
+          const int id = intern(m);
+          if (a >= 1) dense[id] = true;
+          slot[((v[0] * p1 + v[1]) * p1 + v[2]) * p1 + v[3]] = Slot{a, id};
+        }
+  // final order: constant, dense monomials, the rest
+  std::vector<int> order(monos.size()), rank(monos.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+  std::stable_sort(order.begin() + 1, order.end(), [&](int x, int y) { return dense[x] > dense[y]; });
+  for (size_t i = 0; i < order.size(); ++i) rank[order[i]] = (int)i;
+  nf = (int)monos.size();
+  nfd = 0;
+  for (size_t i = 1; i < monos.size(); ++i) nfd += dense[i];
+  nfm = nf - 1;
+  feature_monos.resize(nf);
+  for (int i = 0; i < nf; ++i) feature_monos[rank[i]] = monos[i];
+  idx4.assign(slot.size(), -1);
+  for (size_t i = 0; i < slot.size(); ++i)
+    if (slot[i].a >= 0) idx4[i] = slot[i].a * nf + rank[slot[i].mono];
+  stat_i.clear();
+  stat_j.clear();
+  for (int j = 0; j < p; ++j)
+    for (int i = j; i < p; ++i) { stat_i.push_back(i); stat_j.push_back(j); }
+}
+
+// Lay the people axis out in genotype-file order and upload everything.
+void gwsem_model::prepare(const int32_t* row_filter, int src_rows) {
+  cudaStream_t st = engine->stream;
+  GW_CUDA(cudaSetDevice(engine->device));
+  pool.clear();
+  int dest = 0;
+  std::vector<int> dest_of(src_rows, -1);
+  for (int s = 0; s < src_rows; ++s)
+    if (!row_filter || !row_filter[s]) dest_of[s] = dest++;
+  if (dest != n_rows)
+    fail("rowFilter keeps %d of %d people, which does not match the number of rows of observed data (%d)", dest,
+         src_rows, n_rows);
+  n_src = src_rows;
+  n_pad = (src_rows + 31) / 32 * 32;
+  std::vector<uint8_t> inc8(n_pad, 0);
+  std::vector<unsigned long long> incmask(n_pad / 32, 0);
+  n_incl = 0;
+  for (int s = 0; s < src_rows; ++s)
+    if (dest_of[s] >= 0 && row_ok[dest_of[s]]) {
+      inc8[s] = 3;
+      incmask[s >> 5] |= 1ull << (2 * (s & 31));
+      ++n_incl;
+    }
+  // features
+  const int nfm_pad = std::max(1, (nfm + 3) / 4 * 4);
+  std::vector<double> feat((size_t)std::max(nfd, 1) * n_pad, 0.0), featT((size_t)n_pad * nfm_pad, 0.0), tot(nf, 0.0);
+  std::vector<long double> acc(nf, 0.0L);
+  for (int s = 0; s < src_rows; ++s) {
+    if (!inc8[s]) continue;
+    const int r = dest_of[s];
+    for (int f = 1; f < nf; ++f) {
+      double h = 1.0;
+      for (int b : feature_monos[f]) h *= base[b][r];
+      if (f - 1 < nfd) feat[(size_t)(f - 1) * n_pad + s] = h;
+      featT[(size_t)s * nfm_pad + (f - 1)] = h;
+      acc[f] += h;
+    }
+  }
+  tot[0] = n_incl;
+  for (int f = 1; f < nf; ++f) tot[f] = (double)acc[f];
+  this->nfm_pad = nfm_pad;
+
+  // RAM cells, grouped by parameter
+  const int n_cells = (int)cells.size() / 5;
+  std::vector<int32_t> cm, cr, cc, cp;
+  std::vector<double> cv;
+  std::vector<std::vector<int>> by_par(P);
+  for (int c = 0; c < n_cells; ++c) {
+    const double* x = &cells[5 * (size_t)c];
+    if ((int)x[0] == 2) continue;  // means: no mean structure under cumulants
+    const int id = (int)cm.size();
+    cm.push_back((int)x[0]); cr.push_back((int)x[1]); cc.push_back((int)x[2]); cp.push_back((int)x[3]); cv.push_back(x[4]);
+    if ((int)x[3] >= P) fail("cell refers to parameter %d of %d", (int)x[3], P);
+    if ((int)x[3] >= 0) by_par[(int)x[3]].push_back(id);
+  }
+  std::vector<int32_t> ptr(P + 1, 0), flat;
+  for (int k = 0; k < P; ++k) {
+    ptr[k] = (int)flat.size();
+    for (int id : by_par[k]) flat.push_back(id);
+  }
+  ptr[P] = (int)flat.size();
+
+  fp = FitProgram();
+  fp.p = p; fp.q = q; fp.nv = nv; fp.P = P; fp.n_cells = (int)cm.size();
+  fp.nf = nf; fp.nfd = nfd; fp.nfm = nfm; fp.n_incl = n_incl; fp.min_variance = min_variance;
+  fp.tot = upload_vec(pool, tot, st);
+  fp.idx4 = upload_vec(pool, idx4, st);
+  fp.stat_i = upload_vec(pool, stat_i, st);
+  fp.stat_j = upload_vec(pool, stat_j, st);
+  fp.cell_mat = upload_vec(pool, cm, st);
+  fp.cell_row = upload_vec(pool, cr, st);
+  fp.cell_col = upload_vec(pool, cc, st);
+  fp.cell_par = upload_vec(pool, cp, st);
+  fp.cell_val = upload_vec(pool, cv, st);
+  fp.par_cell_ptr = upload_vec(pool, ptr, st);
+  fp.par_cells = upload_vec(pool, flat, st);
+  fp.par_start = upload_vec(pool, par_start, st);
+  fp.par_lbound = upload_vec(pool, par_lbound, st);
+  layout.n_src = n_src;
+  layout.n_pad = n_pad;
+  layout.n_incl = n_incl;
+  layout.d_inc8 = upload_vec(pool, inc8, st);
+  layout.d_incmask = upload_vec(pool, incmask, st);
+  d_feat = upload_vec(pool, feat, st);
+  d_featT = upload_vec(pool, featT, st);
+  d_dest_of = upload_vec(pool, dest_of, st);
+  GW_CUDA(cudaStreamSynchronize(st));
+  prepared = true;
+}
+
+void gwsem_model::fit_2bit_device(const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
+                                  const gwsem_result& d_res) {
+  if (!prepared) prepare(nullptr, n_rows);
+  GW_CUDA(cudaSetDevice(engine->device));
+  const int kMaxBatch = 1 << 16;
+  for (int s0 = 0; s0 < n_snps; s0 += kMaxBatch) {
+    const int n = std::min(kMaxBatch, n_snps - s0);
+    d_counts.ensure(4 * (size_t)n);
+    d_sums.ensure(2 * (size_t)std::max(nfd, 1) * n);
+    d_miss.ensure((size_t)std::max(nfm, 1) * n);
+    const uint8_t* rows = d_packed + (int64_t)s0 * pitch;
+    launch_count_missing(engine, rows, pitch, n, plink1, layout, d_featT, nfm, nfm_pad, d_counts.p, d_miss.p);
+    launch_class_sums(engine, rows, pitch, n, plink1, layout, d_feat, nfd, d_sums.p);
+    gwsem_result r = d_res;
+    r.est += (size_t)s0 * P; r.vcov += (size_t)s0 * P * P; r.fit += s0; r.maf += s0; r.n_used += s0;
+    r.status += s0; r.catch_code += s0; r.catch_var += s0; r.iterations += s0;
+    launch_fit_cumulants(engine, fp, n, d_counts.p, d_sums.p, d_miss.p, r);
+  }
+}
+
+void gwsem_model::ensure_result_buffers(int n) {
+  r_est.ensure((size_t)n * P); r_vcov.ensure((size_t)n * P * P); r_fit.ensure(n); r_maf.ensure(n);
+  r_n.ensure(n); r_status.ensure(n); r_catch.ensure(n); r_cvar.ensure(n); r_iter.ensure(n);
+}
+
+gwsem_result gwsem_model::device_result() {
+  gwsem_result r;
+  r.est = r_est.p; r.vcov = r_vcov.p; r.fit = r_fit.p; r.maf = r_maf.p; r.n_used = r_n.p;
+  r.status = r_status.p; r.catch_code = r_catch.p; r.catch_var = r_cvar.p; r.iterations = r_iter.p;
+  return r;
+}
+
+void gwsem_model::download_result(const gwsem_result& h, int n, int offset) {
+  cudaStream_t st = engine->stream;
+  auto dl = [&](void* dst, const void* src, size_t bytes) {
+    if (dst) GW_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+  };
+  dl(h.est ? h.est + (size_t)offset * P : nullptr, r_est.p, sizeof(double) * n * P);
+  dl(h.vcov ? h.vcov + (size_t)offset * P * P : nullptr, r_vcov.p, sizeof(double) * n * P * P);
+  dl(h.fit ? h.fit + offset : nullptr, r_fit.p, sizeof(double) * n);
+  dl(h.maf ? h.maf + offset : nullptr, r_maf.p, sizeof(double) * n);
+  dl(h.n_used ? h.n_used + offset : nullptr, r_n.p, sizeof(int32_t) * n);
+  dl(h.status ? h.status + offset : nullptr, r_status.p, sizeof(int32_t) * n);
+  dl(h.catch_code ? h.catch_code + offset : nullptr, r_catch.p, sizeof(int32_t) * n);
+  dl(h.catch_var ? h.catch_var + offset : nullptr, r_cvar.p, sizeof(int32_t) * n);
+  dl(h.iterations ? h.iterations + offset : nullptr, r_iter.p, sizeof(int32_t) * n);
+}
+
+// Host buffers in, host results out: H2D of the packed rows (re-pitched to 16 bytes), kernels, D2H.
+void gwsem_model::fit_2bit_host(const uint8_t* packed, int64_t pitch, int n_snps, int plink1, const gwsem_result& h) {
+  if (!prepared) prepare(nullptr, n_rows);
+  GW_CUDA(cudaSetDevice(engine->device));
+  cudaStream_t st = engine->stream;
+  const int64_t row_bytes = (n_src + 3) / 4;
+  if (pitch < row_bytes) fail("pitch %lld is smaller than a %d-person record (%lld bytes)", (long long)pitch, n_src, (long long)row_bytes);
+  const int64_t dpitch = std::max<int64_t>((row_bytes + 15) / 16 * 16, n_pad / 4);
+  const int64_t dpitch16 = (dpitch + 15) / 16 * 16;
+  const int kBatch = 1 << 15;
+  for (int s0 = 0; s0 < n_snps; s0 += kBatch) {
+    const int n = std::min(kBatch, n_snps - s0);
+    d_stage.ensure((size_t)n * dpitch16 + 16);
+    if (dpitch16 != row_bytes) GW_CUDA(cudaMemsetAsync(d_stage.p, 0, (size_t)n * dpitch16, st));
+    GW_CUDA(cudaMemcpy2DAsync(d_stage.p, dpitch16, packed + (int64_t)s0 * pitch, pitch, row_bytes, n,
+                              cudaMemcpyHostToDevice, st));
+    ensure_result_buffers(n);
+    fit_2bit_device(d_stage.p, dpitch16, n, plink1, device_result());
+    download_result(h, n, s0);
+    GW_CUDA(cudaStreamSynchronize(st));
+  }
+}

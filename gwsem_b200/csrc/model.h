@@ -1,0 +1,45 @@
+// gwsem_model: host-side state of one model bound to an engine (see model.cu).
+#pragma once
+#include <vector>
+
+#include "common.h"
+#include "fit_program.h"
+#include "kernels.h"
+
+struct gwsem_model {
+  gwsem_engine* engine;
+  // specification
+  int nv = 0, p = 0, P = 0, q = 0, n_rows = 0;
+  double min_variance = 0;
+  std::vector<double> cells, par_start, par_lbound;
+  std::vector<int32_t> kind, var_base;
+  std::vector<std::vector<double>> base;  // SNP-independent columns (centred unless used as moderator)
+  std::vector<uint8_t> row_ok;            // complete phenotype row
+  // moment program
+  int nf = 0, nfd = 0, nfm = 0, nfm_pad = 0;
+  std::vector<std::vector<int>> feature_monos;
+  std::vector<int32_t> idx4, stat_i, stat_j;
+  // people axis / device state
+  bool prepared = false;
+  int n_src = 0, n_pad = 0, n_incl = 0;
+  gwsem::FitProgram fp;
+  gwsem::PeopleLayout layout;
+  const double* d_feat = nullptr;
+  const double* d_featT = nullptr;
+  const int32_t* d_dest_of = nullptr;
+  std::vector<gwsem::DeviceBuffer<uint8_t>> pool;
+  gwsem::DeviceBuffer<int32_t> d_counts;
+  gwsem::DeviceBuffer<double> d_sums, d_miss;
+  gwsem::DeviceBuffer<uint8_t> d_stage;
+  gwsem::DeviceBuffer<double> r_est, r_vcov, r_fit, r_maf;
+  gwsem::DeviceBuffer<int32_t> r_n, r_status, r_catch, r_cvar, r_iter;
+
+  gwsem_model(gwsem_engine* e, const gwsem_model_spec* s);
+  void build_program();
+  void prepare(const int32_t* row_filter, int src_rows);
+  void fit_2bit_device(const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1, const gwsem_result& d_res);
+  void fit_2bit_host(const uint8_t* packed, int64_t pitch, int n_snps, int plink1, const gwsem_result& h);
+  void ensure_result_buffers(int n);
+  gwsem_result device_result();
+  void download_result(const gwsem_result& h, int n, int offset);
+};

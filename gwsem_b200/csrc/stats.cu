@@ -1,0 +1,290 @@
+// Per-SNP sufficient statistics on packed hardcalls.
+//
+// Every statistic the WLS path needs from the genotype column (SURVEY.md section 8a rows
+// O1, O2, O4) is a sum over people of g^a * h, with h a SNP-independent per-person
+// feature (a monomial of phenotype / moderator columns).  For hardcalls g takes three
+// values, so   sum_i g_i^a h_i = 1^a * S1[h] + 2^a * S2[h],   S_c[h] = sum over people
+// with genotype class c.  The hot kernel therefore computes genotype-class sums of a small
+// feature matrix, straight from the 2-bit records -- no double column is materialised.
+//
+//   class_sums_kernel   classes 1 and 2, FP64 accumulate (bound: FP64 pipe; genotype bytes
+//                       are read once from HBM through a cp.async.bulk (TMA) + mbarrier ring)
+//   count_missing_kernel  class counts by popcount and the (rare) missing class, one warp per SNP
+#include "common.h"
+#include "kernels.h"
+
+namespace gwsem {
+
+constexpr int kWarps = 4;            // warps per CTA; each owns S SNP rows
+constexpr int kTilePeople = 2048;    // people per pipeline stage
+constexpr int kTileBytes = kTilePeople / 4;
+constexpr int kRowStride = kTileBytes + 16;  // +16 B: rows land in different banks
+constexpr int kStages = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk async copy global -> shared, completion signalled on an mbarrier (TMA engine).
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// PLINK 1 .bed 2-bit codes -> PLINK 2 codes, 16 people at a time
+// (00->10, 01->11, 10->01, 11->00; reference src/pgenlib_read.cc:1979-1992).
+__device__ __forceinline__ uint32_t bed_to_plink2(uint32_t w) {
+  const uint32_t hi = w & 0xAAAAAAAAu, lo = w & 0x55555555u;
+  return (~hi & 0xAAAAAAAAu) | ((hi >> 1) ^ lo);
+}
+__device__ __forceinline__ unsigned long long bed_to_plink2(unsigned long long w) {
+  const unsigned long long hi = w & 0xAAAAAAAAAAAAAAAAull, lo = w & 0x5555555555555555ull;
+  return (~hi & 0xAAAAAAAAAAAAAAAAull) | ((hi >> 1) ^ lo);
+}
+
+
+// Grid: one CTA per kWarps*S SNP rows.  Warp w accumulates, for its S rows and F features,
+//   a1[s][f] = sum_{i: code_i == 1} feat[f][i],   a2[s][f] = sum_{i: code_i == 2} feat[f][i]
+// lane l taking people l, l+32, ...  All 32 lanes read the same 32-person word of a row
+// (shared-memory broadcast) and pick their own 2 bits; the adds are DFMAs with 0/1 weights.
+template <int S, int F, bool PLINK1>
+__global__ void __launch_bounds__(kWarps * 32)
+    class_sums_kernel(const uint8_t* __restrict__ packed, int64_t pitch, int n_snps, int n_src,
+                      const uint8_t* __restrict__ inc8, const double* __restrict__ feat, int n_pad,
+                      int feat_stride_out, double* __restrict__ sums) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // kStages barriers
+  uint8_t* tiles = smem + 128;
+  constexpr int kRows = kWarps * S;
+  constexpr int kStageBytes = kRows * kRowStride;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * kRows;
+  const int rows_here = min(kRows, n_snps - row0);
+  const int n_tiles = (n_src + kTilePeople - 1) / kTilePeople;
+  const int64_t row_bytes = (int64_t)((n_src + 3) / 4 + 15) / 16 * 16;  // bytes worth copying per row (<= pitch)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](int t) {
+    const int stage = t % kStages;
+    const int64_t off = (int64_t)t * kTileBytes;
+    const uint32_t bytes = (uint32_t)min((int64_t)kTileBytes, row_bytes - off);
+    mbar_expect_tx(&full[stage], bytes * rows_here);
+    uint8_t* dst = tiles + stage * kStageBytes;
+    for (int r = 0; r < rows_here; ++r)
+      bulk_g2s(dst + r * kRowStride, packed + (int64_t)(row0 + r) * pitch + off, bytes, &full[stage]);
+  };
+  if (threadIdx.x == 0)
+    for (int t = 0; t < kStages && t < n_tiles; ++t) issue(t);
+
+  double a1[S][F], a2[S][F];
+#pragma unroll
+  for (int s = 0; s < S; ++s)
+#pragma unroll
+    for (int f = 0; f < F; ++f) a1[s][f] = a2[s][f] = 0.0;
+
+  const int sh = 2 * (lane & 15);
+  const int half = lane >> 4;
+  for (int t = 0; t < n_tiles; ++t) {
+    const int stage = t % kStages;
+    mbar_wait(&full[stage], (t / kStages) & 1);
+    const uint8_t* base = tiles + stage * kStageBytes + warp * S * kRowStride;
+    const int people = min(kTilePeople, n_src - t * kTilePeople);
+    const int blocks = (people + 31) >> 5;
+    int i = t * kTilePeople + lane;
+    for (int b = 0; b < blocks; ++b, i += 32) {
+      double h[F];
+#pragma unroll
+      for (int f = 0; f < F; ++f) h[f] = feat[(int64_t)f * n_pad + i];
+      const uint32_t inc = inc8[i];
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        uint32_t w = *reinterpret_cast<const uint32_t*>(base + s * kRowStride + b * 8 + half * 4);
+        if (PLINK1) w = bed_to_plink2(w);
+        const uint32_t code = (w >> sh) & inc;
+        // class indicators as doubles (1.0 / 0.0: only the high word differs) feeding DFMAs;
+        // nvcc turns both "if (p) a += h" and predicated PTX adds into branches or FSEL pairs
+        const double w1 = __hiloint2double(code == 1u ? 0x3FF00000 : 0, 0);
+        const double w2 = __hiloint2double(code == 2u ? 0x3FF00000 : 0, 0);
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          a1[s][f] = fma(w1, h[f], a1[s][f]);
+          a2[s][f] = fma(w2, h[f], a2[s][f]);
+        }
+      }
+    }
+    __syncthreads();  // every warp is done with this stage
+    if (threadIdx.x == 0 && t + kStages < n_tiles) issue(t + kStages);
+  }
+
+#pragma unroll
+  for (int s = 0; s < S; ++s)
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        a1[s][f] += __shfl_xor_sync(0xffffffffu, a1[s][f], o);
+        a2[s][f] += __shfl_xor_sync(0xffffffffu, a2[s][f], o);
+      }
+    }
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int row = row0 + warp * S + s;
+      if (row < n_snps) {
+        double* o = sums + (int64_t)row * 2 * feat_stride_out;
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          o[f] = a1[s][f];
+          o[feat_stride_out + f] = a2[s][f];
+        }
+      }
+    }
+  }
+}
+
+template <int S, int F>
+static void launch_chunk(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
+                         const PeopleLayout& pl, const double* d_feat, int n_feat_total, double* d_sums) {
+  constexpr int kRows = kWarps * S;
+  const size_t smem = 128 + (size_t)kStages * kRows * kRowStride;
+  const int grid = (n_snps + kRows - 1) / kRows;
+  if (plink1) {
+    auto k = class_sums_kernel<S, F, true>;
+    GW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, kWarps * 32, smem, e->stream>>>(d_packed, pitch, n_snps, pl.n_src, pl.d_inc8, d_feat, pl.n_pad,
+                                               n_feat_total, d_sums);
+  } else {
+    auto k = class_sums_kernel<S, F, false>;
+    GW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, kWarps * 32, smem, e->stream>>>(d_packed, pitch, n_snps, pl.n_src, pl.d_inc8, d_feat, pl.n_pad,
+                                               n_feat_total, d_sums);
+  }
+  GW_CUDA(cudaGetLastError());
+  e->launches++;
+}
+
+void launch_class_sums(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
+                       const PeopleLayout& pl, const double* d_feat, int n_feat, double* d_sums) {
+  if (n_snps <= 0 || n_feat <= 0) return;
+  if (pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(d_packed) & 15))
+    fail("packed genotype rows must be 16-byte aligned with a pitch that is a multiple of 16 (pitch=%lld)",
+         (long long)pitch);
+  int f0 = 0;
+  while (f0 < n_feat) {  // widest chunks first
+    const int left = n_feat - f0;
+    const double* feat = d_feat + (size_t)f0 * pl.n_pad;
+    double* out = d_sums + f0;
+    if (left >= 8) { launch_chunk<4, 8>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 8; }
+    else if (left >= 4) { launch_chunk<8, 4>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 4; }
+    else if (left == 3) { launch_chunk<8, 3>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 3; }
+    else if (left == 2) { launch_chunk<8, 2>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 2; }
+    else { launch_chunk<8, 1>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 1; }
+  }
+}
+
+// One warp per SNP row: class counts by popcount over included people and the sums of the
+// person-major features over the missing class.  Lanes scan 32-person words; a word with
+// missing calls is handled by the whole warp (lane f accumulates feature f, f+32, ...), people
+// in index order, so the result does not depend on scheduling.
+template <bool PLINK1>
+__global__ void __launch_bounds__(128)
+    count_missing_kernel(const uint8_t* __restrict__ packed, int64_t pitch, int n_snps, int n_pad,
+                         const unsigned long long* __restrict__ incmask, const double* __restrict__ featT,
+                         int n_featm, int n_featm_pad, int32_t* __restrict__ counts, double* __restrict__ miss) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n_snps) return;
+  const unsigned long long* words = reinterpret_cast<const unsigned long long*>(packed + (int64_t)row * pitch);
+  const int n_words = n_pad >> 5;
+  int c1 = 0, c2 = 0, c3 = 0;
+  constexpr int kMaxAcc = 8;  // up to 256 missing-class features
+  double acc[kMaxAcc];
+#pragma unroll
+  for (int k = 0; k < kMaxAcc; ++k) acc[k] = 0.0;
+  for (int w0 = 0; w0 < n_words; w0 += 32) {
+    const int wi = w0 + lane;
+    unsigned long long m3 = 0;
+    if (wi < n_words) {
+      unsigned long long w = words[wi];
+      if (PLINK1) w = bed_to_plink2(w);
+      const unsigned long long inc = incmask[wi];
+      const unsigned long long lo = w & 0x5555555555555555ull, hi = (w >> 1) & 0x5555555555555555ull;
+      c1 += __popcll(lo & ~hi & inc);
+      c2 += __popcll(hi & ~lo & inc);
+      m3 = lo & hi & inc;
+      c3 += __popcll(m3);
+    }
+    unsigned any = __ballot_sync(0xffffffffu, m3 != 0);
+    while (any) {
+      const int src = __ffs(any) - 1;
+      any &= any - 1;
+      unsigned long long bits = __shfl_sync(0xffffffffu, m3, src);
+      const int person0 = (w0 + src) << 5;
+      while (bits) {
+        const int person = person0 + ((__ffsll((long long)bits) - 1) >> 1);
+        bits &= bits - 1;
+        const double* f = featT + (int64_t)person * n_featm_pad;
+#pragma unroll
+        for (int k = 0; k < kMaxAcc; ++k)
+          if (lane + 32 * k < n_featm) acc[k] += f[lane + 32 * k];
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+    c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+  }
+  if (lane == 0) {
+    counts[4 * row + 0] = c1;
+    counts[4 * row + 1] = c2;
+    counts[4 * row + 2] = c3;
+    counts[4 * row + 3] = 0;
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxAcc; ++k)
+    if (lane + 32 * k < n_featm) miss[(int64_t)row * n_featm + lane + 32 * k] = acc[k];
+}
+
+void launch_count_missing(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
+                          const PeopleLayout& pl, const double* d_featT, int n_featm, int n_featm_pad,
+                          int32_t* d_counts, double* d_miss) {
+  if (n_snps <= 0) return;
+  if (n_featm > 256) fail("too many missing-class features (%d > 256)", n_featm);
+  if (pitch % 8 != 0 || pitch * 4 < pl.n_pad) fail("pitch %lld too small for %d padded people", (long long)pitch, pl.n_pad);
+  const int warps = 4;
+  const int grid = (n_snps + warps - 1) / warps;
+  if (plink1)
+    count_missing_kernel<true><<<grid, warps * 32, 0, e->stream>>>(d_packed, pitch, n_snps, pl.n_pad, pl.d_incmask,
+                                                                   d_featT, n_featm, n_featm_pad, d_counts, d_miss);
+  else
+    count_missing_kernel<false><<<grid, warps * 32, 0, e->stream>>>(d_packed, pitch, n_snps, pl.n_pad, pl.d_incmask,
+                                                                    d_featT, n_featm, n_featm_pad, d_counts, d_miss);
+  GW_CUDA(cudaGetLastError());
+  e->launches++;
+}
+
+}  // namespace gwsem

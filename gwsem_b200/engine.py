@@ -1,0 +1,149 @@
+"""Python handles over the C ABI: Engine (one per GPU), Model, result containers."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+
+STATUS_TEXT = {0: "OK", 1: "OK/green", 4: "iteration limit/blue", 5: "not convex/red",
+               6: "nonzero gradient/red", -1: "NA"}
+
+
+def _ptr(a):
+    """address of a numpy array, torch tensor (host or device) or None"""
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    return a.ctypes.data
+
+
+class Engine:
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        check(lib().gwsem_engine_create(int(device), C.byref(self.h)))
+        self.device = device
+
+    def set_stream(self, cuda_stream_ptr):
+        check(lib().gwsem_engine_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def synchronize(self):
+        check(lib().gwsem_engine_synchronize(self.h))
+
+    @property
+    def launches(self):
+        return int(lib().gwsem_engine_launch_count(self.h))
+
+    def decode_2bit(self, packed, n_samples, plink1=False, row_filter=None):
+        """packed: uint8 [n_snps, pitch] host array -> (geno[n_snps, dest_rows], maf[n_snps])"""
+        packed = np.ascontiguousarray(packed, np.uint8)
+        n_snps, pitch = packed.shape
+        rf = None if row_filter is None else np.ascontiguousarray(np.asarray(row_filter).astype(np.int32))
+        dest = n_samples if rf is None else int((rf == 0).sum())
+        out = np.empty((n_snps, dest))
+        maf = np.empty(n_snps)
+        check(lib().gwsem_decode_2bit(self.h, _ptr(packed), pitch, n_snps, n_samples, int(plink1), _ptr(rf),
+                                      _ptr(out), _ptr(maf)))
+        return out, maf
+
+    def close(self):
+        if self.h:
+            lib().gwsem_engine_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FitResult:
+    """Host-side structure-of-arrays result of a batch of SNPs."""
+
+    def __init__(self, n_snps, n_params, alloc=np.empty):
+        self.n, self.P = n_snps, n_params
+        self.est = alloc((n_snps, n_params), dtype=np.float64)
+        self.vcov = alloc((n_snps, n_params, n_params), dtype=np.float64)
+        self.fit = alloc(n_snps, dtype=np.float64)
+        self.maf = alloc(n_snps, dtype=np.float64)
+        self.n_used = alloc(n_snps, dtype=np.int32)
+        self.status = alloc(n_snps, dtype=np.int32)
+        self.catch_code = alloc(n_snps, dtype=np.int32)
+        self.catch_var = alloc(n_snps, dtype=np.int32)
+        self.iterations = alloc(n_snps, dtype=np.int32)
+
+    def c_struct(self):
+        return _lib.Result(*[_ptr(getattr(self, f)) for f, _ in _lib.Result._fields_])
+
+
+class Model:
+    """A flattened RAM model (gwsem_b200.model.flatten) bound to an engine."""
+
+    FIT_CODES = {("WLS", "cumulants"): 0, ("WLS", "marginals"): 1, ("ML", "marginals"): 2, ("ML", "cumulants"): 2}
+
+    def __init__(self, engine, flat, data):
+        """data: {column name: float64 array over the model's rows (after rowFilter)}"""
+        self.engine, self.flat = engine, flat
+        self.names = list(flat["par_names"])
+        self.P = len(self.names)
+        nm = flat["nm"]
+        self._keep = []
+        kinds = np.zeros(nm, np.int32)
+        ptrs = (C.POINTER(C.c_double) * nm)()
+        n_rows = None
+        for j, name in enumerate(flat["manifest"]):
+            if name == "snp":
+                kinds[j] = 1
+                continue
+            col = name
+            if name.startswith("snp_") and name[4:] in flat["gxe"]:
+                kinds[j] = 2
+                col = name[4:]
+            arr = np.ascontiguousarray(np.asarray(data[col], dtype=np.float64))
+            self._keep.append(arr)
+            n_rows = len(arr)
+            ptrs[j] = arr.ctypes.data_as(C.POINTER(C.c_double))
+        if n_rows is None:
+            n_rows = len(next(iter(data.values())))
+        cells = np.ascontiguousarray(flat["cells"], np.float64)
+        start = np.ascontiguousarray(flat["par_start"], np.float64)
+        lb = np.ascontiguousarray(flat["par_lbound"], np.float64)
+        self._keep += [cells, start, lb, kinds, ptrs]
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        spec = _lib.ModelSpec(flat["nv"], nm, self.P, len(cells), dp(cells), dp(start), dp(lb),
+                              self.FIT_CODES[(flat["fitfun"], flat["continuous_type"])],
+                              float(flat["min_variance"]), n_rows,
+                              kinds.ctypes.data_as(C.POINTER(C.c_int32)), ptrs)
+        self.n_rows = n_rows
+        self.h = C.c_void_p()
+        check(lib().gwsem_model_create(engine.h, C.byref(spec), C.byref(self.h)))
+
+    def set_row_filter(self, row_filter, src_rows=None):
+        rf = None if row_filter is None else np.ascontiguousarray(np.asarray(row_filter).astype(np.int32))
+        n = len(rf) if rf is not None else int(src_rows)
+        check(lib().gwsem_model_set_row_filter(self.h, _ptr(rf), n))
+
+    def fit_2bit(self, packed, plink1=False, result=None):
+        """Host path: packed uint8 [n_snps, pitch] (numpy or pinned torch) -> FitResult"""
+        n_snps, pitch = packed.shape
+        res = result or FitResult(n_snps, self.P)
+        cs = res.c_struct()
+        check(lib().gwsem_fit_2bit(self.h, _ptr(packed), pitch, n_snps, int(plink1), C.byref(cs)))
+        return res
+
+    def fit_2bit_device(self, d_packed_ptr, pitch, n_snps, d_result_struct, plink1=False):
+        check(lib().gwsem_fit_2bit_device(self.h, C.c_void_p(d_packed_ptr), pitch, n_snps, int(plink1),
+                                          C.byref(d_result_struct)))
+
+    def close(self):
+        if self.h:
+            lib().gwsem_model_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -331,3 +331,31 @@ def write_bgen(path, prob_ints, layout=2, bits=8, compression=1, positions=None,
         con.executemany("INSERT INTO Variant VALUES (?,?,?,?,?,?,?,?)", index_rows)
         con.commit()
         con.close()
+
+
+# ------------------------------------------------------------------- device-side cohorts
+
+def device_hardcalls(n_people, n_snps, seed, device="cuda", maf_range=(0.05, 0.5), missing_rate=0.0,
+                     chunk=2048):
+    """Hardy-Weinberg hardcalls generated on the GPU, packed 2 bits per person in the engine's
+    HBM layout: uint8 tensor [n_snps, pitch], pitch = ceil(N/4) rounded up to 16 bytes, PLINK 2
+    coding.  (torch is used as the RNG / allocator only.)"""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    row_bytes = (n_people + 3) // 4
+    pitch = (row_bytes + 15) // 16 * 16
+    out = torch.zeros((n_snps, pitch), dtype=torch.uint8, device=device)
+    n4 = row_bytes * 4
+    for s0 in range(0, n_snps, chunk):
+        m = min(chunk, n_snps - s0)
+        p = torch.empty((m, 1), device=device).uniform_(maf_range[0], maf_range[1], generator=g)
+        u = torch.rand((m, n4), device=device, generator=g)
+        codes = (u < p * p).to(torch.uint8) * 2 + ((u >= p * p) & (u < p * p + 2 * p * (1 - p))).to(torch.uint8)
+        if missing_rate > 0:
+            miss = torch.rand((m, n4), device=device, generator=g) < missing_rate
+            codes[miss] = 3
+        codes[:, n_people:] = 0
+        c = codes.view(m, row_bytes, 4)
+        out[s0:s0 + m, :row_bytes] = c[..., 0] | (c[..., 1] << 2) | (c[..., 2] << 4) | (c[..., 3] << 6)
+    return out
