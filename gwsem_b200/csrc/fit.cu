@@ -56,16 +56,20 @@ __device__ __forceinline__ int vech_index(int i, int j, int p) {  // i >= j, col
   return j * p - j * (j - 1) / 2 + (i - j);
 }
 
-// In-place Cholesky (lower) of the n x n row-major matrix a; returns false if not positive definite.
-__device__ bool warp_cholesky(double* a, int n, int lane) {
+// In-place Cholesky (lower) of the n x n row-major matrix a; returns false if not positive
+// definite.  A pivot below 1e-10 of its natural scale (scale[j] if given, else the diagonal
+// entry itself) counts as zero, so exactly singular matrices are reported, not inverted.
+__device__ bool warp_cholesky(double* a, int n, int lane, const double* scale = nullptr) {
   for (int j = 0; j < n; ++j) {
-    double d = 0.0;
+    double d = 0.0, d0 = 0.0;
     if (lane == 0) {
-      d = a[j * n + j];
+      d0 = d = a[j * n + j];
+      if (scale) d0 = scale[j];
       for (int k = 0; k < j; ++k) d -= a[j * n + k] * a[j * n + k];
     }
     d = __shfl_sync(0xffffffffu, d, 0);
-    if (!(d > 0.0) || !isfinite(d)) return false;
+    d0 = __shfl_sync(0xffffffffu, d0, 0);
+    if (!(d > 1e-10 * d0) || !isfinite(d)) return false;
     const double dj = sqrt(d);
     if (lane == 0) a[j * n + j] = dj;
     for (int i = j + 1 + lane; i < n; i += 32) {
@@ -277,7 +281,11 @@ __global__ void __launch_bounds__(128)
     L[e2 * q + e1] = gam;
   }
   __syncwarp();
-  if (!warp_cholesky(L, q, lane)) {
+  // natural scale of Gamma[(ij),(ij)] is s_ii * s_jj; kept in `sig` until the optimiser needs it
+  for (int e = lane; e < q; e += 32)
+    (sm + ws.sig)[e] = c2[vech_index(fp.stat_i[e], fp.stat_i[e], p)] * c2[vech_index(fp.stat_j[e], fp.stat_j[e], p)];
+  __syncwarp();
+  if (!warp_cholesky(L, q, lane, sm + ws.sig)) {
     if (lane == 0) res.catch_code[snp] = GWSEM_CATCH_ACOV_NOT_PD;
     return;
   }

@@ -15,11 +15,7 @@
 
 namespace gwsem {
 
-constexpr int kWarps = 4;            // warps per CTA; each owns S SNP rows
-constexpr int kTilePeople = 2048;    // people per pipeline stage
-constexpr int kTileBytes = kTilePeople / 4;
-constexpr int kRowStride = kTileBytes + 16;  // +16 B: rows land in different banks
-constexpr int kStages = 4;
+constexpr int kRowPad = 16;  // bytes added to each staged genotype row: rows land in different banks
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -59,44 +55,55 @@ __device__ __forceinline__ unsigned long long bed_to_plink2(unsigned long long w
 }
 
 
-// Grid: one CTA per kWarps*S SNP rows.  Warp w accumulates, for its S rows and F features,
+// Grid: one CTA per WARPS*S SNP rows.  Warp w accumulates, for its S rows and F features,
 //   a1[s][f] = sum_{i: code_i == 1} feat[f][i],   a2[s][f] = sum_{i: code_i == 2} feat[f][i]
-// lane l taking people l, l+32, ...  All 32 lanes read the same 32-person word of a row
-// (shared-memory broadcast) and pick their own 2 bits; the adds are DFMAs with 0/1 weights.
-template <int S, int F, bool PLINK1>
-__global__ void __launch_bounds__(kWarps * 32)
+// lane l taking people l, l+32, ...  The people axis is cut into TILE-person tiles; a ring of
+// STAGES shared-memory stages is filled by cp.async.bulk (TMA) copies -- the 2-bit rows of the
+// CTA's SNPs, the F feature rows and the include bytes of the tile -- and signalled through
+// mbarriers.  All 32 lanes read the same 32-person word of a genotype row (shared-memory
+// broadcast) and pick their own 2 bits; the adds are DFMAs with 0/1 weights.
+template <int S, int F, int WARPS, int TILE, int STAGES, bool PLINK1>
+__global__ void __launch_bounds__(WARPS * 32)
     class_sums_kernel(const uint8_t* __restrict__ packed, int64_t pitch, int n_snps, int n_src,
                       const uint8_t* __restrict__ inc8, const double* __restrict__ feat, int n_pad,
                       int feat_stride_out, double* __restrict__ sums) {
+  constexpr int kRows = WARPS * S;
+  constexpr int kTileBytes = TILE / 4;
+  constexpr int kRowStride = kTileBytes + kRowPad;
+  constexpr int kGenoBytes = kRows * kRowStride;
+  constexpr int kFeatBytes = F * TILE * 8;
+  constexpr int kStageBytes = kGenoBytes + kFeatBytes + TILE;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // kStages barriers
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // STAGES barriers
   uint8_t* tiles = smem + 128;
-  constexpr int kRows = kWarps * S;
-  constexpr int kStageBytes = kRows * kRowStride;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * kRows;
   const int rows_here = min(kRows, n_snps - row0);
-  const int n_tiles = (n_src + kTilePeople - 1) / kTilePeople;
+  const int n_tiles = (n_src + TILE - 1) / TILE;
   const int64_t row_bytes = (int64_t)((n_src + 3) / 4 + 15) / 16 * 16;  // bytes worth copying per row (<= pitch)
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   auto issue = [&](int t) {
-    const int stage = t % kStages;
+    const int stage = t % STAGES;
     const int64_t off = (int64_t)t * kTileBytes;
-    const uint32_t bytes = (uint32_t)min((int64_t)kTileBytes, row_bytes - off);
-    mbar_expect_tx(&full[stage], bytes * rows_here);
-    uint8_t* dst = tiles + stage * kStageBytes;
+    const uint32_t gbytes = (uint32_t)min((int64_t)kTileBytes, row_bytes - off);
+    const int people = min(TILE, n_pad - t * TILE);  // n_pad is a multiple of 32
+    mbar_expect_tx(&full[stage], gbytes * rows_here + (uint32_t)people * (8 * F + 1));
+    uint8_t* dst = tiles + (size_t)stage * kStageBytes;
     for (int r = 0; r < rows_here; ++r)
-      bulk_g2s(dst + r * kRowStride, packed + (int64_t)(row0 + r) * pitch + off, bytes, &full[stage]);
+      bulk_g2s(dst + r * kRowStride, packed + (int64_t)(row0 + r) * pitch + off, gbytes, &full[stage]);
+    for (int f = 0; f < F; ++f)
+      bulk_g2s(dst + kGenoBytes + f * TILE * 8, feat + (int64_t)f * n_pad + (int64_t)t * TILE, people * 8, &full[stage]);
+    bulk_g2s(dst + kGenoBytes + kFeatBytes, inc8 + (int64_t)t * TILE, people, &full[stage]);
   };
   if (threadIdx.x == 0)
-    for (int t = 0; t < kStages && t < n_tiles; ++t) issue(t);
+    for (int t = 0; t < STAGES && t < n_tiles; ++t) issue(t);
 
   double a1[S][F], a2[S][F];
 #pragma unroll
@@ -107,20 +114,23 @@ __global__ void __launch_bounds__(kWarps * 32)
   const int sh = 2 * (lane & 15);
   const int half = lane >> 4;
   for (int t = 0; t < n_tiles; ++t) {
-    const int stage = t % kStages;
-    mbar_wait(&full[stage], (t / kStages) & 1);
-    const uint8_t* base = tiles + stage * kStageBytes + warp * S * kRowStride;
-    const int people = min(kTilePeople, n_src - t * kTilePeople);
+    const int stage = t % STAGES;
+    mbar_wait(&full[stage], (t / STAGES) & 1);
+    const uint8_t* stage_base = tiles + (size_t)stage * kStageBytes;
+    const uint8_t* base = stage_base + warp * S * kRowStride + half * 4;
+    const double* fs = reinterpret_cast<const double*>(stage_base + kGenoBytes) + lane;
+    const uint8_t* is = stage_base + kGenoBytes + kFeatBytes + lane;
+    const int people = min(TILE, n_src - t * TILE);
     const int blocks = (people + 31) >> 5;
-    int i = t * kTilePeople + lane;
-    for (int b = 0; b < blocks; ++b, i += 32) {
+#pragma unroll 1
+    for (int b = 0; b < blocks; ++b) {
       double h[F];
 #pragma unroll
-      for (int f = 0; f < F; ++f) h[f] = feat[(int64_t)f * n_pad + i];
-      const uint32_t inc = inc8[i];
+      for (int f = 0; f < F; ++f) h[f] = fs[f * TILE + b * 32];
+      const uint32_t inc = is[b * 32];
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        uint32_t w = *reinterpret_cast<const uint32_t*>(base + s * kRowStride + b * 8 + half * 4);
+        uint32_t w = *reinterpret_cast<const uint32_t*>(base + s * kRowStride + b * 8);
         if (PLINK1) w = bed_to_plink2(w);
         const uint32_t code = (w >> sh) & inc;
         // class indicators as doubles (1.0 / 0.0: only the high word differs) feeding DFMAs;
@@ -135,7 +145,7 @@ __global__ void __launch_bounds__(kWarps * 32)
       }
     }
     __syncthreads();  // every warp is done with this stage
-    if (threadIdx.x == 0 && t + kStages < n_tiles) issue(t + kStages);
+    if (threadIdx.x == 0 && t + STAGES < n_tiles) issue(t + STAGES);
   }
 
 #pragma unroll
@@ -164,22 +174,22 @@ __global__ void __launch_bounds__(kWarps * 32)
   }
 }
 
-template <int S, int F>
+template <int S, int F, int WARPS, int TILE, int STAGES>
 static void launch_chunk(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
                          const PeopleLayout& pl, const double* d_feat, int n_feat_total, double* d_sums) {
-  constexpr int kRows = kWarps * S;
-  const size_t smem = 128 + (size_t)kStages * kRows * kRowStride;
+  constexpr int kRows = WARPS * S;
+  const size_t smem = 128 + (size_t)STAGES * (kRows * (TILE / 4 + kRowPad) + F * TILE * 8 + TILE);
   const int grid = (n_snps + kRows - 1) / kRows;
   if (plink1) {
-    auto k = class_sums_kernel<S, F, true>;
+    auto k = class_sums_kernel<S, F, WARPS, TILE, STAGES, true>;
     GW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, kWarps * 32, smem, e->stream>>>(d_packed, pitch, n_snps, pl.n_src, pl.d_inc8, d_feat, pl.n_pad,
-                                               n_feat_total, d_sums);
+    k<<<grid, WARPS * 32, smem, e->stream>>>(d_packed, pitch, n_snps, pl.n_src, pl.d_inc8, d_feat, pl.n_pad,
+                                              n_feat_total, d_sums);
   } else {
-    auto k = class_sums_kernel<S, F, false>;
+    auto k = class_sums_kernel<S, F, WARPS, TILE, STAGES, false>;
     GW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, kWarps * 32, smem, e->stream>>>(d_packed, pitch, n_snps, pl.n_src, pl.d_inc8, d_feat, pl.n_pad,
-                                               n_feat_total, d_sums);
+    k<<<grid, WARPS * 32, smem, e->stream>>>(d_packed, pitch, n_snps, pl.n_src, pl.d_inc8, d_feat, pl.n_pad,
+                                              n_feat_total, d_sums);
   }
   GW_CUDA(cudaGetLastError());
   e->launches++;
@@ -196,11 +206,12 @@ void launch_class_sums(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, 
     const int left = n_feat - f0;
     const double* feat = d_feat + (size_t)f0 * pl.n_pad;
     double* out = d_sums + f0;
-    if (left >= 8) { launch_chunk<4, 8>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 8; }
-    else if (left >= 4) { launch_chunk<8, 4>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 4; }
-    else if (left == 3) { launch_chunk<8, 3>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 3; }
-    else if (left == 2) { launch_chunk<8, 2>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 2; }
-    else { launch_chunk<8, 1>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 1; }
+    //                          S  F  WARPS TILE STAGES
+    if (left >= 8) { launch_chunk<4, 8, 8, 512, 3>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 8; }
+    else if (left >= 4) { launch_chunk<8, 4, 4, 1024, 2>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 4; }
+    else if (left == 3) { launch_chunk<8, 3, 4, 1024, 2>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 3; }
+    else if (left == 2) { launch_chunk<8, 2, 4, 1024, 2>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 2; }
+    else { launch_chunk<8, 1, 4, 1024, 2>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 1; }
   }
 }
 

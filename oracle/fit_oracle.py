@@ -108,6 +108,22 @@ def jac_cumulants(ram, theta):
     return np.stack([[dS[k][i, j] for i, j in pairs] for k in range(ram.P)], 1)  # [q, P]
 
 
+def cholesky_checked(a, scale=None):
+    """Lower Cholesky factor; a pivot below 1e-10 of its natural scale (scale[j], default the
+    diagonal entry) counts as zero (raises LinAlgError), so exactly singular weight matrices are
+    reported, not inverted."""
+    a = np.array(a, float)
+    n = len(a)
+    L = np.zeros_like(a)
+    for j in range(n):
+        d = a[j, j] - L[j, :j] @ L[j, :j]
+        if not (d > 1e-10 * (a[j, j] if scale is None else scale[j])) or not np.isfinite(d):
+            raise np.linalg.LinAlgError("not positive definite")
+        L[j, j] = np.sqrt(d)
+        L[j + 1:, j] = (a[j + 1:, j] - L[j + 1:, :j] @ L[j, :j]) / L[j, j]
+    return L
+
+
 # ------------------------------------------------------------------------- optimiser
 
 def wls_fit(s, W, sigma_fn, jac_fn, theta0, lbound, max_iter=200, tol=1e-10):
@@ -186,8 +202,10 @@ def fit_snp_cumulants(flat, pheno_cols, snp):
             return out
     s, gamma, n = cumulants_stats(X)
     try:
+        p = X.shape[1]
+        v = X.var(0)
+        cholesky_checked(gamma, [v[i] * v[j] for i, j in vech_pairs(p)])
         W = n * np.linalg.inv(gamma)
-        np.linalg.cholesky(gamma)
     except np.linalg.LinAlgError:
         out["catch1"] = f"{flat['name']}.data: asymptotic covariance matrix is not positive definite"
         return out
