@@ -41,7 +41,50 @@ void fail(const char* fmt, ...) {
 
 using namespace gwsem;
 
+void gwsem_engine::prof_begin(int fam) {
+  if (!profiling) return;
+  std::pair<cudaEvent_t, cudaEvent_t> ev;
+  if (!prof_free.empty()) {
+    ev = prof_free.back();
+    prof_free.pop_back();
+  } else {
+    GW_CUDA(cudaEventCreate(&ev.first));
+    GW_CUDA(cudaEventCreate(&ev.second));
+  }
+  GW_CUDA(cudaEventRecord(ev.first, stream));
+  prof_events[fam].push_back(ev);
+}
+
+void gwsem_engine::prof_end(int fam) {
+  if (!profiling) return;
+  GW_CUDA(cudaEventRecord(prof_events[fam].back().second, stream));
+}
+
 extern "C" {
+
+int gwsem_engine_profile(gwsem_engine* e, int enable) {
+  return guarded([&] { e->profiling = enable != 0; });
+}
+
+// Collects (and clears) the per-family launch statistics gathered since the last call:
+// launches[f], total_ms[f] for f in {class_sums, count_missing, fit, decode}.  Synchronises.
+int gwsem_engine_profile_read(gwsem_engine* e, int64_t* launches, double* total_ms) {
+  return guarded([&] {
+    GW_CUDA(cudaSetDevice(e->device));
+    GW_CUDA(cudaStreamSynchronize(e->stream));
+    for (int f = 0; f < kFamCount; ++f) {
+      launches[f] = (int64_t)e->prof_events[f].size();
+      total_ms[f] = 0;
+      for (auto& ev : e->prof_events[f]) {
+        float ms = 0;
+        GW_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+        total_ms[f] += ms;
+        e->prof_free.push_back(ev);
+      }
+      e->prof_events[f].clear();
+    }
+  });
+}
 
 int gwsem_abi_version(void) { return GWSEM_ABI_VERSION; }
 const char* gwsem_last_error(void) { return g_error.c_str(); }

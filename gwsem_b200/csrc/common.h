@@ -72,7 +72,17 @@ struct DeviceBuffer {
 
 }  // namespace gwsem
 
+namespace gwsem {
+enum KernelFamily { kFamClassSums = 0, kFamCountMissing = 1, kFamFit = 2, kFamDecode = 3, kFamCount = 4 };
+}
+
 struct gwsem_engine {
+  // optional per-launch timing with CUDA events on the launch stream (bench.py's roofline leg)
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[gwsem::kFamCount];
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_free;
+  void prof_begin(int fam);
+  void prof_end(int fam);
   int device = 0;
   int sm_count = 148;
   cudaStream_t own_stream = nullptr;

@@ -432,8 +432,10 @@ void launch_fit_cumulants(gwsem_engine* e, const FitProgram& fp, int n_snps, con
   const size_t smem = per_warp * warps;
   GW_CUDA(cudaFuncSetAttribute(fit_cumulants_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (n_snps + warps - 1) / warps;
+  e->prof_begin(kFamFit);
   fit_cumulants_kernel<<<grid, warps * 32, smem, e->stream>>>(fp, n_snps, d_counts, d_sums, d_miss, d_res);
   GW_CUDA(cudaGetLastError());
+  e->prof_end(kFamFit);
   e->launches++;
 }
 

@@ -251,41 +251,67 @@ gwsem_result gwsem_model::device_result() {
   return r;
 }
 
-void gwsem_model::download_result(const gwsem_result& h, int n, int offset) {
+void gwsem_model::download_result(const gwsem_result& h, const gwsem_result& d, int n, int offset) {
   cudaStream_t st = engine->stream;
   auto dl = [&](void* dst, const void* src, size_t bytes) {
     if (dst) GW_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
   };
-  dl(h.est ? h.est + (size_t)offset * P : nullptr, r_est.p, sizeof(double) * n * P);
-  dl(h.vcov ? h.vcov + (size_t)offset * P * P : nullptr, r_vcov.p, sizeof(double) * n * P * P);
-  dl(h.fit ? h.fit + offset : nullptr, r_fit.p, sizeof(double) * n);
-  dl(h.maf ? h.maf + offset : nullptr, r_maf.p, sizeof(double) * n);
-  dl(h.n_used ? h.n_used + offset : nullptr, r_n.p, sizeof(int32_t) * n);
-  dl(h.status ? h.status + offset : nullptr, r_status.p, sizeof(int32_t) * n);
-  dl(h.catch_code ? h.catch_code + offset : nullptr, r_catch.p, sizeof(int32_t) * n);
-  dl(h.catch_var ? h.catch_var + offset : nullptr, r_cvar.p, sizeof(int32_t) * n);
-  dl(h.iterations ? h.iterations + offset : nullptr, r_iter.p, sizeof(int32_t) * n);
+  dl(h.est ? h.est + (size_t)offset * P : nullptr, d.est, sizeof(double) * n * P);
+  dl(h.vcov ? h.vcov + (size_t)offset * P * P : nullptr, d.vcov, sizeof(double) * n * P * P);
+  dl(h.fit ? h.fit + offset : nullptr, d.fit, sizeof(double) * n);
+  dl(h.maf ? h.maf + offset : nullptr, d.maf, sizeof(double) * n);
+  dl(h.n_used ? h.n_used + offset : nullptr, d.n_used, sizeof(int32_t) * n);
+  dl(h.status ? h.status + offset : nullptr, d.status, sizeof(int32_t) * n);
+  dl(h.catch_code ? h.catch_code + offset : nullptr, d.catch_code, sizeof(int32_t) * n);
+  dl(h.catch_var ? h.catch_var + offset : nullptr, d.catch_var, sizeof(int32_t) * n);
+  dl(h.iterations ? h.iterations + offset : nullptr, d.iterations, sizeof(int32_t) * n);
 }
 
-// Host buffers in, host results out: H2D of the packed rows (re-pitched to 16 bytes), kernels, D2H.
+// Host buffers in, host results out.  The packed rows are cut into chunks that alternate between
+// two HBM staging buffers: the H2D copy of chunk c+1 (copy stream) overlaps the kernels of chunk c
+// (engine stream); results come back once per chunk on the engine stream.
 void gwsem_model::fit_2bit_host(const uint8_t* packed, int64_t pitch, int n_snps, int plink1, const gwsem_result& h) {
   if (!prepared) prepare(nullptr, n_rows);
   GW_CUDA(cudaSetDevice(engine->device));
   cudaStream_t st = engine->stream;
   const int64_t row_bytes = (n_src + 3) / 4;
   if (pitch < row_bytes) fail("pitch %lld is smaller than a %d-person record (%lld bytes)", (long long)pitch, n_src, (long long)row_bytes);
-  const int64_t dpitch = std::max<int64_t>((row_bytes + 15) / 16 * 16, n_pad / 4);
-  const int64_t dpitch16 = (dpitch + 15) / 16 * 16;
-  const int kBatch = 1 << 15;
-  for (int s0 = 0; s0 < n_snps; s0 += kBatch) {
-    const int n = std::min(kBatch, n_snps - s0);
-    d_stage.ensure((size_t)n * dpitch16 + 16);
-    if (dpitch16 != row_bytes) GW_CUDA(cudaMemsetAsync(d_stage.p, 0, (size_t)n * dpitch16, st));
-    GW_CUDA(cudaMemcpy2DAsync(d_stage.p, dpitch16, packed + (int64_t)s0 * pitch, pitch, row_bytes, n,
-                              cudaMemcpyHostToDevice, st));
-    ensure_result_buffers(n);
-    fit_2bit_device(d_stage.p, dpitch16, n, plink1, device_result());
-    download_result(h, n, s0);
-    GW_CUDA(cudaStreamSynchronize(st));
+  const int64_t dpitch = (std::max<int64_t>(row_bytes, n_pad / 4) + 15) / 16 * 16;
+  if (!copy_stream) {
+    GW_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      GW_CUDA(cudaEventCreateWithFlags(&ev_copied[b], cudaEventDisableTiming));
+      GW_CUDA(cudaEventCreateWithFlags(&ev_done[b], cudaEventDisableTiming));
+    }
   }
+  // ~128 MiB of packed rows per chunk
+  const int chunk = (int)std::max<int64_t>(256, std::min<int64_t>(1 << 16, (128ll << 20) / dpitch));
+  ensure_result_buffers(std::min(chunk, n_snps) * 2);
+  for (int b = 0; b < 2; ++b) {
+    d_stage2[b].ensure((size_t)std::min(chunk, n_snps) * dpitch + 16);
+    if (dpitch != row_bytes) GW_CUDA(cudaMemsetAsync(d_stage2[b].p, 0, d_stage2[b].n, st));
+  }
+  GW_CUDA(cudaEventRecord(ev_done[0], st));
+  GW_CUDA(cudaEventRecord(ev_done[1], st));
+  int c = 0;
+  for (int s0 = 0; s0 < n_snps; s0 += chunk, ++c) {
+    const int b = c & 1;
+    const int n = std::min(chunk, n_snps - s0);
+    GW_CUDA(cudaStreamWaitEvent(copy_stream, ev_done[b], 0));  // staging buffer b is free again
+    if (dpitch == pitch)
+      GW_CUDA(cudaMemcpyAsync(d_stage2[b].p, packed + (int64_t)s0 * pitch, (size_t)n * pitch, cudaMemcpyHostToDevice, copy_stream));
+    else
+      GW_CUDA(cudaMemcpy2DAsync(d_stage2[b].p, dpitch, packed + (int64_t)s0 * pitch, pitch, row_bytes, n,
+                                cudaMemcpyHostToDevice, copy_stream));
+    GW_CUDA(cudaEventRecord(ev_copied[b], copy_stream));
+    GW_CUDA(cudaStreamWaitEvent(st, ev_copied[b], 0));
+    gwsem_result r = device_result();
+    const size_t o = (size_t)b * std::min(chunk, n_snps);
+    r.est += o * P; r.vcov += o * P * P; r.fit += o; r.maf += o; r.n_used += o;
+    r.status += o; r.catch_code += o; r.catch_var += o; r.iterations += o;
+    fit_2bit_device(d_stage2[b].p, dpitch, n, plink1, r);
+    download_result(h, r, n, s0);
+    GW_CUDA(cudaEventRecord(ev_done[b], st));
+  }
+  GW_CUDA(cudaStreamSynchronize(st));
 }

@@ -201,6 +201,7 @@ void launch_class_sums(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, 
   if (pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(d_packed) & 15))
     fail("packed genotype rows must be 16-byte aligned with a pitch that is a multiple of 16 (pitch=%lld)",
          (long long)pitch);
+  e->prof_begin(kFamClassSums);
   int f0 = 0;
   while (f0 < n_feat) {  // widest chunks first
     const int left = n_feat - f0;
@@ -213,6 +214,7 @@ void launch_class_sums(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, 
     else if (left == 2) { launch_chunk<8, 2, 4, 1024, 2>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 2; }
     else { launch_chunk<8, 1, 4, 1024, 2>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 1; }
   }
+  e->prof_end(kFamClassSums);
 }
 
 // One warp per SNP row: class counts by popcount over included people and the sums of the
@@ -288,6 +290,7 @@ void launch_count_missing(gwsem_engine* e, const uint8_t* d_packed, int64_t pitc
   if (pitch % 8 != 0 || pitch * 4 < pl.n_pad) fail("pitch %lld too small for %d padded people", (long long)pitch, pl.n_pad);
   const int warps = 4;
   const int grid = (n_snps + warps - 1) / warps;
+  e->prof_begin(kFamCountMissing);
   if (plink1)
     count_missing_kernel<true><<<grid, warps * 32, 0, e->stream>>>(d_packed, pitch, n_snps, pl.n_pad, pl.d_incmask,
                                                                    d_featT, n_featm, n_featm_pad, d_counts, d_miss);
@@ -295,6 +298,7 @@ void launch_count_missing(gwsem_engine* e, const uint8_t* d_packed, int64_t pitc
     count_missing_kernel<false><<<grid, warps * 32, 0, e->stream>>>(d_packed, pitch, n_snps, pl.n_pad, pl.d_incmask,
                                                                     d_featT, n_featm, n_featm_pad, d_counts, d_miss);
   GW_CUDA(cudaGetLastError());
+  e->prof_end(kFamCountMissing);
   e->launches++;
 }
 

@@ -35,6 +35,18 @@ class Engine:
     def launches(self):
         return int(lib().gwsem_engine_launch_count(self.h))
 
+    KERNEL_FAMILIES = ("class_sums", "count_missing", "fit", "decode")
+
+    def profile(self, enable=True):
+        check(lib().gwsem_engine_profile(self.h, int(enable)))
+
+    def profile_read(self):
+        """{family: (launches, total_ms)} since the last read (CUDA events on the launch stream)"""
+        n = (C.c_int64 * 4)()
+        ms = (C.c_double * 4)()
+        check(lib().gwsem_engine_profile_read(self.h, n, ms))
+        return {k: (int(n[i]), float(ms[i])) for i, k in enumerate(self.KERNEL_FAMILIES)}
+
     def decode_2bit(self, packed, n_samples, plink1=False, row_filter=None):
         """packed: uint8 [n_snps, pitch] host array -> (geno[n_snps, dest_rows], maf[n_snps])"""
         packed = np.ascontiguousarray(packed, np.uint8)

@@ -136,11 +136,14 @@ def encode_hphase_track(codes, rng, explicit):
 
 
 def write_pgen_fixed(path, codes):
-    """Mode 0x02: header + M records of ceil(N/4) bytes (pgenlib_misc.h:619-620)."""
+    """Mode 0x02: header + M records of ceil(N/4) bytes (pgenlib_misc.h:619-620).  Header control
+    byte 0: nonref flags unstored -- the reference provider passes nonref_flags_already_loaded=1 with
+    no flag array (src/loader.cpp:323), so fixed-width files that claim "all ref" / "never ref"
+    make pgenlib dereference a null pointer (pgenlib_read.cc:1081-1101)."""
     codes = np.asarray(codes, np.uint8)
     m, n = codes.shape
     with open(path, "wb") as f:
-        f.write(b"\x6c\x1b\x02" + struct.pack("<II", m, n) + b"\x40")
+        f.write(b"\x6c\x1b\x02" + struct.pack("<II", m, n) + b"\x00")
         f.write(pack_2bit(codes).tobytes())
 
 
@@ -149,7 +152,7 @@ def write_pgen_fixed_dosage(path, codes, dosage):
     codes = np.asarray(codes, np.uint8)
     m, n = codes.shape
     with open(path, "wb") as f:
-        f.write(b"\x6c\x1b\x03" + struct.pack("<II", m, n) + b"\x40")
+        f.write(b"\x6c\x1b\x03" + struct.pack("<II", m, n) + b"\x00")
         packed = pack_2bit(codes)
         for i in range(m):
             f.write(packed[i].tobytes() + np.asarray(dosage[i], "<u2").tobytes())

@@ -53,6 +53,11 @@ int gwsem_engine_set_stream(gwsem_engine* e, void* cuda_stream);
 int gwsem_engine_synchronize(gwsem_engine* e);
 /* kernels launched by this engine since creation (bench.py's gpu_launches) */
 int64_t gwsem_engine_launch_count(const gwsem_engine* e);
+/* Per-launch timing with CUDA events on the launch stream.  gwsem_engine_profile_read fills
+ * launches[4] / total_ms[4] for the kernel families {class sums, count+missing, fit, decode}
+ * seen since the previous read, and clears them (synchronises the stream). */
+int gwsem_engine_profile(gwsem_engine* e, int enable);
+int gwsem_engine_profile_read(gwsem_engine* e, int64_t* launches, double* total_ms);
 
 /* ----------------------------------------------------------- genotype sources (providers) */
 /* method: "pgen" (also PLINK 1 .bed, as R/model.R:36) or "bgen".  src_rows: number of people

@@ -1,4 +1,5 @@
-"""ctypes bindings for the test oracles (TEST INFRASTRUCTURE, never imported by gwsem_b200/).
+"""ctypes bindings for the test oracles (TEST INFRASTRUCTURE, never imported by gwsem_b200/;
+only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs use it).
 
 * ``RefPgen``    -- oracle/_ref/libgwsem_ref.so: the reference's own pgenlib, driven as
                     src/loader.cpp:290-406 drives it.
@@ -10,8 +11,8 @@ import subprocess
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_DIR = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(ORACLE_DIR)
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libgwsem_ref.so")
 ORC_SO = os.path.join(ORACLE_DIR, "libgwsem_oracle.so")
 NA_BITS = 0x7FF00000000007A2
