@@ -31,7 +31,8 @@ class Job(C.Structure):
     _fields_ = [("snp", C.POINTER(C.c_int32)), ("n_snp", C.c_int32), ("start_from", C.c_int32),
                 ("out_path", C.c_char_p), ("par_names", C.POINTER(C.c_char_p)),
                 ("context_path", C.c_char_p), ("vcov_pairs", C.POINTER(C.c_int32)),
-                ("n_vcov_pairs", C.c_int32), ("batch_snps", C.c_int32)]
+                ("n_vcov_pairs", C.c_int32), ("batch_snps", C.c_int32), ("model_name", C.c_char_p),
+                ("manifest_names", C.POINTER(C.c_char_p))]
 
 
 # every symbol include/gwsem_b200.h declares: (restype, argtypes)

@@ -212,19 +212,3 @@ int gwsem_fit_2bit(gwsem_model* m, const uint8_t* packed, int64_t pitch, int n_s
 
 }  // extern "C"
 
-// ---- not yet implemented entry points (declared in the header; fail loudly)
-extern "C" {
-#define GW_TODO(name) return guarded([&] { fail(name ": not implemented yet"); })
-int gwsem_source_open(const char*, const char*, int, gwsem_source**) { GW_TODO("gwsem_source_open"); }
-void gwsem_source_close(gwsem_source*) {}
-int gwsem_source_num_variants(const gwsem_source*) { return -1; }
-int gwsem_source_num_samples(const gwsem_source*) { return -1; }
-int gwsem_source_load_counter(const gwsem_source*) { return 0; }
-const char* gwsem_source_checkpoint_columns(const gwsem_source*) { return ""; }
-int gwsem_source_context(gwsem_source*, int, char*, size_t) { GW_TODO("gwsem_source_context"); }
-int gwsem_source_load_rows(gwsem_engine*, gwsem_source*, const int32_t*, int, const int32_t*, double*, double*) {
-  GW_TODO("gwsem_source_load_rows");
-}
-int gwsem_fit_rows_device(gwsem_model*, const double*, int, const gwsem_result*) { GW_TODO("gwsem_fit_rows_device"); }
-int gwsem_gwas_run(gwsem_model*, gwsem_source*, const gwsem_job*, int64_t*) { GW_TODO("gwsem_gwas_run"); }
-}

@@ -192,8 +192,8 @@ __device__ double central_moment(const FitProgram& fp, const int* vars, int k, c
 }
 
 __global__ void __launch_bounds__(128)
-    fit_cumulants_kernel(FitProgram fp, int n_snps, const int32_t* __restrict__ counts,
-                         const double* __restrict__ sums, const double* __restrict__ miss, gwsem_result res) {
+    fit_cumulants_kernel(FitProgram fp, int n_snps, const double* __restrict__ Rtab, const int32_t* __restrict__ n_rows,
+                         const double* __restrict__ maf_in, gwsem_result res) {
   extern __shared__ double smem_d[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int snp = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -202,25 +202,11 @@ __global__ void __launch_bounds__(128)
   const WarpScratch ws = scratch_layout(p, q, nv, P, nf);
   double* sm = smem_d + (size_t)warp * ws.total;
 
-  const int n1 = counts[4 * snp], n2 = counts[4 * snp + 1], n3 = counts[4 * snp + 2];
-  const int n = fp.n_incl - n3;
+  const int n = n_rows[snp];
   const double inv_n = 1.0 / (double)n;
   double* R = sm + ws.R;
   // raw moment table R[a][f] = sum over complete rows of g^a * h_f
-  for (int e = lane; e < 5 * nf; e += 32) {
-    const int a = e / nf, f = e % nf;
-    double v;
-    if (a == 0) {
-      v = f == 0 ? (double)n : fp.tot[f] - miss[(int64_t)snp * fp.nfm + (f - 1)];
-    } else {
-      const double w2 = (double)(1 << a);
-      if (f == 0) v = (double)n1 + w2 * (double)n2;
-      else if (f - 1 < fp.nfd)
-        v = sums[(int64_t)snp * 2 * fp.nfd + (f - 1)] + w2 * sums[(int64_t)snp * 2 * fp.nfd + fp.nfd + (f - 1)];
-      else v = 0.0;
-    }
-    R[e] = v;
-  }
+  for (int e = lane; e < 5 * nf; e += 32) R[e] = Rtab[(int64_t)snp * 5 * nf + e];
   __syncwarp();
 
   double* est = res.est + (int64_t)snp * P;
@@ -228,9 +214,7 @@ __global__ void __launch_bounds__(128)
   for (int k = lane; k < P; k += 32) est[k] = fp.par_start[k];
   for (int k = lane; k < P * P; k += 32) vcov[k] = __longlong_as_double((long long)GWSEM_NA_BITS);
   if (lane == 0) {
-    double maf = ((double)n1 + 2.0 * (double)n2) / (2.0 * (double)n);
-    if (maf > 0.5) maf = 1 - maf;
-    res.maf[snp] = maf;
+    res.maf[snp] = maf_in[snp];
     res.n_used[snp] = n;
     res.fit[snp] = __longlong_as_double((long long)GWSEM_NA_BITS);
     res.status[snp] = GWSEM_STATUS_NA;
@@ -422,8 +406,8 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-void launch_fit_cumulants(gwsem_engine* e, const FitProgram& fp, int n_snps, const int32_t* d_counts,
-                          const double* d_sums, const double* d_miss, const gwsem_result& d_res) {
+void launch_fit_cumulants(gwsem_engine* e, const FitProgram& fp, int n_snps, const double* d_R, const int32_t* d_n,
+                          const double* d_maf, const gwsem_result& d_res) {
   if (n_snps <= 0) return;
   const size_t per_warp = fit_scratch_doubles(fp.p, fp.q, fp.nv, fp.P, fp.nf) * sizeof(double);
   int warps = 4;
@@ -433,7 +417,7 @@ void launch_fit_cumulants(gwsem_engine* e, const FitProgram& fp, int n_snps, con
   GW_CUDA(cudaFuncSetAttribute(fit_cumulants_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (n_snps + warps - 1) / warps;
   e->prof_begin(kFamFit);
-  fit_cumulants_kernel<<<grid, warps * 32, smem, e->stream>>>(fp, n_snps, d_counts, d_sums, d_miss, d_res);
+  fit_cumulants_kernel<<<grid, warps * 32, smem, e->stream>>>(fp, n_snps, d_R, d_n, d_maf, d_res);
   GW_CUDA(cudaGetLastError());
   e->prof_end(kFamFit);
   e->launches++;

@@ -14,8 +14,10 @@ struct PeopleLayout {
   int n_src = 0;        // people in the genotype file (source rows)
   int n_pad = 0;        // n_src rounded up to a multiple of 32
   int n_incl = 0;       // people that enter the model (rowFilter == 0 and complete phenotype row)
+  int n_kept = 0;       // people kept by rowFilter (the provider's destRows; MAF is over these)
   const uint8_t* d_inc8 = nullptr;                // n_pad: 3 = included, 0 = excluded
   const unsigned long long* d_incmask = nullptr;  // n_pad/32 words, 0b01 per included person
+  const unsigned long long* d_rowmask = nullptr;  // n_pad/32 words, 0b01 per person kept by rowFilter
 };
 
 // classes 1 and 2 (het, hom-ALT) sums of `n_feat` feature rows (feature-major, n_pad doubles each):
@@ -23,15 +25,25 @@ struct PeopleLayout {
 void launch_class_sums(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
                        const PeopleLayout& pl, const double* d_feat, int n_feat, double* d_sums);
 
-// counts[snp][4] = {n_class1, n_class2, n_missing, 0} over included people and, for the missing
-// class, sums of `n_featm` person-major features (d_featT[person][n_featm_pad]): d_miss[snp][n_featm].
+// counts[snp][8] = {n_class1, n_class2, n_missing over included people; the same three over the
+// people kept by rowFilter (for MAF); 0; 0} and, for the missing class, sums of `n_featm`
+// person-major features (d_featT[person][n_featm_pad]): d_miss[snp][n_featm].
 void launch_count_missing(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
                           const PeopleLayout& pl, const double* d_featT, int n_featm, int n_featm_pad,
                           int32_t* d_counts, double* d_miss);
 
 // ---- fit.cu
 struct FitProgram;  // device-resident model description, built in model.cu
-void launch_fit_cumulants(gwsem_engine* e, const FitProgram& fp, int n_snps, const int32_t* d_counts,
-                          const double* d_sums, const double* d_miss, const gwsem_result& d_res);
+// Raw moment table of every SNP: d_R[snp][a * nf + f] = sum over complete rows of g^a * h_f
+// (a = 0..4), d_n[snp] = complete rows.
+// (i) hardcalls: from class counts / class sums / missing-class sums; also fills d_maf
+void launch_assemble_moments(gwsem_engine* e, const FitProgram& fp, const PeopleLayout& pl, int n_snps,
+                             const int32_t* d_counts, const double* d_sums, const double* d_miss, double* d_R,
+                             int32_t* d_n, double* d_maf);
+// (ii) any genotype column (dosages, bgen): d_geno[snp][n_pad] doubles in file order, NaN = missing
+void launch_power_sums(gwsem_engine* e, const FitProgram& fp, const PeopleLayout& pl, int n_snps,
+                       const double* d_geno, const double* d_featT, int n_featm_pad, double* d_R, int32_t* d_n);
+void launch_fit_cumulants(gwsem_engine* e, const FitProgram& fp, int n_snps, const double* d_R, const int32_t* d_n,
+                          const double* d_maf, const gwsem_result& d_res);
 
 }  // namespace gwsem

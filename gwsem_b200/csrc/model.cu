@@ -144,14 +144,17 @@ void gwsem_model::prepare(const int32_t* row_filter, int src_rows) {
   n_src = src_rows;
   n_pad = (src_rows + 31) / 32 * 32;
   std::vector<uint8_t> inc8(n_pad, 0);
-  std::vector<unsigned long long> incmask(n_pad / 32, 0);
+  std::vector<unsigned long long> incmask(n_pad / 32, 0), rowmask(n_pad / 32, 0);
   n_incl = 0;
-  for (int s = 0; s < src_rows; ++s)
-    if (dest_of[s] >= 0 && row_ok[dest_of[s]]) {
+  for (int s = 0; s < src_rows; ++s) {
+    if (dest_of[s] < 0) continue;
+    rowmask[s >> 5] |= 1ull << (2 * (s & 31));
+    if (row_ok[dest_of[s]]) {
       inc8[s] = 3;
       incmask[s >> 5] |= 1ull << (2 * (s & 31));
       ++n_incl;
     }
+  }
   // features
   const int nfm_pad = std::max(1, (nfm + 3) / 4 * 4);
   std::vector<double> feat((size_t)std::max(nfd, 1) * n_pad, 0.0), featT((size_t)n_pad * nfm_pad, 0.0), tot(nf, 0.0);
@@ -212,6 +215,8 @@ void gwsem_model::prepare(const int32_t* row_filter, int src_rows) {
   layout.n_incl = n_incl;
   layout.d_inc8 = upload_vec(pool, inc8, st);
   layout.d_incmask = upload_vec(pool, incmask, st);
+  layout.d_rowmask = upload_vec(pool, rowmask, st);
+  layout.n_kept = n_rows;
   d_feat = upload_vec(pool, feat, st);
   d_featT = upload_vec(pool, featT, st);
   d_dest_of = upload_vec(pool, dest_of, st);
@@ -226,16 +231,37 @@ void gwsem_model::fit_2bit_device(const uint8_t* d_packed, int64_t pitch, int n_
   const int kMaxBatch = 1 << 16;
   for (int s0 = 0; s0 < n_snps; s0 += kMaxBatch) {
     const int n = std::min(kMaxBatch, n_snps - s0);
-    d_counts.ensure(4 * (size_t)n);
+    d_counts.ensure(8 * (size_t)n);
     d_sums.ensure(2 * (size_t)std::max(nfd, 1) * n);
     d_miss.ensure((size_t)std::max(nfm, 1) * n);
+    d_R.ensure(5 * (size_t)nf * n);
+    d_nrows.ensure(n);
+    d_mafs.ensure(n);
     const uint8_t* rows = d_packed + (int64_t)s0 * pitch;
     launch_count_missing(engine, rows, pitch, n, plink1, layout, d_featT, nfm, nfm_pad, d_counts.p, d_miss.p);
     launch_class_sums(engine, rows, pitch, n, plink1, layout, d_feat, nfd, d_sums.p);
     gwsem_result r = d_res;
     r.est += (size_t)s0 * P; r.vcov += (size_t)s0 * P * P; r.fit += s0; r.maf += s0; r.n_used += s0;
     r.status += s0; r.catch_code += s0; r.catch_var += s0; r.iterations += s0;
-    launch_fit_cumulants(engine, fp, n, d_counts.p, d_sums.p, d_miss.p, r);
+    launch_assemble_moments(engine, fp, layout, n, d_counts.p, d_sums.p, d_miss.p, d_R.p, d_nrows.p, d_mafs.p);
+    launch_fit_cumulants(engine, fp, n, d_R.p, d_nrows.p, d_mafs.p, r);
+  }
+}
+
+// Generic path: genotype columns as doubles in file order (n_pad apart), NaN = missing.
+void gwsem_model::fit_rows_device(const double* d_geno, const double* d_maf, int n_snps, const gwsem_result& d_res) {
+  if (!prepared) prepare(nullptr, n_rows);
+  GW_CUDA(cudaSetDevice(engine->device));
+  const int kMaxBatch = 1 << 14;
+  for (int s0 = 0; s0 < n_snps; s0 += kMaxBatch) {
+    const int n = std::min(kMaxBatch, n_snps - s0);
+    d_R.ensure(5 * (size_t)nf * n);
+    d_nrows.ensure(n);
+    launch_power_sums(engine, fp, layout, n, d_geno + (size_t)s0 * n_pad, d_featT, nfm_pad, d_R.p, d_nrows.p);
+    gwsem_result r = d_res;
+    r.est += (size_t)s0 * P; r.vcov += (size_t)s0 * P * P; r.fit += s0; r.maf += s0; r.n_used += s0;
+    r.status += s0; r.catch_code += s0; r.catch_var += s0; r.iterations += s0;
+    launch_fit_cumulants(engine, fp, n, d_R.p, d_nrows.p, d_maf + s0, r);
   }
 }
 

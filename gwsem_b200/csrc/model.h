@@ -29,7 +29,8 @@ struct gwsem_model {
   const int32_t* d_dest_of = nullptr;
   std::vector<gwsem::DeviceBuffer<uint8_t>> pool;
   gwsem::DeviceBuffer<int32_t> d_counts;
-  gwsem::DeviceBuffer<double> d_sums, d_miss;
+  gwsem::DeviceBuffer<double> d_sums, d_miss, d_R, d_mafs;
+  gwsem::DeviceBuffer<int32_t> d_nrows;
   gwsem::DeviceBuffer<uint8_t> d_stage2[2];
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
@@ -40,6 +41,7 @@ struct gwsem_model {
   void build_program();
   void prepare(const int32_t* row_filter, int src_rows);
   void fit_2bit_device(const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1, const gwsem_result& d_res);
+  void fit_rows_device(const double* d_geno, const double* d_maf, int n_snps, const gwsem_result& d_res);
   void fit_2bit_host(const uint8_t* packed, int64_t pitch, int n_snps, int plink1, const gwsem_result& h);
   void ensure_result_buffers(int n);
   gwsem_result device_result();

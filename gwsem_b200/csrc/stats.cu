@@ -11,6 +11,7 @@
 //                       are read once from HBM through a cp.async.bulk (TMA) + mbarrier ring)
 //   count_missing_kernel  class counts by popcount and the (rare) missing class, one warp per SNP
 #include "common.h"
+#include "fit_program.h"
 #include "kernels.h"
 
 namespace gwsem {
@@ -224,14 +225,15 @@ void launch_class_sums(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, 
 template <bool PLINK1>
 __global__ void __launch_bounds__(128)
     count_missing_kernel(const uint8_t* __restrict__ packed, int64_t pitch, int n_snps, int n_pad,
-                         const unsigned long long* __restrict__ incmask, const double* __restrict__ featT,
+                         const unsigned long long* __restrict__ incmask,
+                         const unsigned long long* __restrict__ rowmask, const double* __restrict__ featT,
                          int n_featm, int n_featm_pad, int32_t* __restrict__ counts, double* __restrict__ miss) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n_snps) return;
   const unsigned long long* words = reinterpret_cast<const unsigned long long*>(packed + (int64_t)row * pitch);
   const int n_words = n_pad >> 5;
-  int c1 = 0, c2 = 0, c3 = 0;
+  int c1 = 0, c2 = 0, c3 = 0, r1 = 0, r2 = 0, r3 = 0;
   constexpr int kMaxAcc = 8;  // up to 256 missing-class features
   double acc[kMaxAcc];
 #pragma unroll
@@ -248,6 +250,10 @@ __global__ void __launch_bounds__(128)
       c2 += __popcll(hi & ~lo & inc);
       m3 = lo & hi & inc;
       c3 += __popcll(m3);
+      const unsigned long long rm = rowmask[wi];
+      r1 += __popcll(lo & ~hi & rm);
+      r2 += __popcll(hi & ~lo & rm);
+      r3 += __popcll(lo & hi & rm);
     }
     unsigned any = __ballot_sync(0xffffffffu, m3 != 0);
     while (any) {
@@ -270,12 +276,14 @@ __global__ void __launch_bounds__(128)
     c1 += __shfl_xor_sync(0xffffffffu, c1, o);
     c2 += __shfl_xor_sync(0xffffffffu, c2, o);
     c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+    r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+    r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+    r3 += __shfl_xor_sync(0xffffffffu, r3, o);
   }
   if (lane == 0) {
-    counts[4 * row + 0] = c1;
-    counts[4 * row + 1] = c2;
-    counts[4 * row + 2] = c3;
-    counts[4 * row + 3] = 0;
+    int4* o = reinterpret_cast<int4*>(counts + 8 * (int64_t)row);
+    o[0] = make_int4(c1, c2, c3, r1);
+    o[1] = make_int4(r2, r3, 0, 0);
   }
 #pragma unroll
   for (int k = 0; k < kMaxAcc; ++k)
@@ -293,12 +301,123 @@ void launch_count_missing(gwsem_engine* e, const uint8_t* d_packed, int64_t pitc
   e->prof_begin(kFamCountMissing);
   if (plink1)
     count_missing_kernel<true><<<grid, warps * 32, 0, e->stream>>>(d_packed, pitch, n_snps, pl.n_pad, pl.d_incmask,
-                                                                   d_featT, n_featm, n_featm_pad, d_counts, d_miss);
+                                                                   pl.d_rowmask, d_featT, n_featm, n_featm_pad, d_counts, d_miss);
   else
     count_missing_kernel<false><<<grid, warps * 32, 0, e->stream>>>(d_packed, pitch, n_snps, pl.n_pad, pl.d_incmask,
-                                                                    d_featT, n_featm, n_featm_pad, d_counts, d_miss);
+                                                                    pl.d_rowmask, d_featT, n_featm, n_featm_pad, d_counts, d_miss);
   GW_CUDA(cudaGetLastError());
   e->prof_end(kFamCountMissing);
+  e->launches++;
+}
+
+// R[a][f] from the hardcall class statistics: genotype g is 1 on class 1 and 2 on class 2, so
+// sum g^a h = S1[h] + 2^a S2[h]; a = 0 uses totals minus the missing class.  MAF as the reference
+// computes it (loader.cpp:386-394): over every person kept by rowFilter, folded to <= 0.5.
+__global__ void assemble_moments_kernel(FitProgram fp, int n_kept, int n_snps, const int32_t* __restrict__ counts,
+                                        const double* __restrict__ sums, const double* __restrict__ miss,
+                                        double* __restrict__ R, int32_t* __restrict__ n_out, double* __restrict__ maf) {
+  const int nf = fp.nf;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n_snps * 5 * nf) return;
+  const int snp = (int)(idx / (5 * nf)), e = (int)(idx % (5 * nf));
+  const int a = e / nf, f = e % nf;
+  const int32_t* c = counts + 8 * (int64_t)snp;
+  const int n = fp.n_incl - c[2];
+  double v;
+  if (a == 0) {
+    v = f == 0 ? (double)n : fp.tot[f] - miss[(int64_t)snp * fp.nfm + (f - 1)];
+  } else {
+    const double w2 = (double)(1 << a);
+    if (f == 0) v = (double)c[0] + w2 * (double)c[1];
+    else if (f - 1 < fp.nfd)
+      v = sums[(int64_t)snp * 2 * fp.nfd + (f - 1)] + w2 * sums[(int64_t)snp * 2 * fp.nfd + fp.nfd + (f - 1)];
+    else v = 0.0;
+  }
+  R[idx] = v;
+  if (e == 0) {
+    n_out[snp] = n;
+    double m = ((double)c[3] + 2.0 * (double)c[4]) / (2.0 * (double)(n_kept - c[5]));
+    if (m > 0.5) m = 1 - m;
+    maf[snp] = m;
+  }
+}
+
+void launch_assemble_moments(gwsem_engine* e, const FitProgram& fp, const PeopleLayout& pl, int n_snps,
+                             const int32_t* d_counts, const double* d_sums, const double* d_miss, double* d_R,
+                             int32_t* d_n, double* d_maf) {
+  if (n_snps <= 0) return;
+  const int64_t total = (int64_t)n_snps * 5 * fp.nf;
+  assemble_moments_kernel<<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(fp, pl.n_kept, n_snps, d_counts, d_sums,
+                                                                                   d_miss, d_R, d_n, d_maf);
+  GW_CUDA(cudaGetLastError());
+  e->launches++;
+}
+
+// Generic genotype column (dosage / bgen): one CTA per SNP.  Thread t owns features t, t+128, ...
+// (up to 2 per thread -> 256 features) and all five powers of g; people are walked in order, their
+// genotype value broadcast through shared memory, the person-major feature row read coalesced.
+// Deterministic (fixed order), FP64.  This is the fallback path, bound by the feature re-reads.
+__global__ void __launch_bounds__(128)
+    power_sums_kernel(FitProgram fp, int n_src, int n_pad, const uint8_t* __restrict__ inc8,
+                      const double* __restrict__ geno, const double* __restrict__ featT, int n_featm_pad,
+                      double* __restrict__ R, int32_t* __restrict__ n_out) {
+  __shared__ double g_tile[128];
+  __shared__ int cnt_sh;
+  const int snp = blockIdx.x, t = threadIdx.x;
+  const int nf = fp.nf;
+  const double* grow = geno + (int64_t)snp * n_pad;
+  double acc[2][5];
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int a = 0; a < 5; ++a) acc[k][a] = 0.0;
+  int cnt = 0;
+  if (t == 0) cnt_sh = 0;
+  for (int i0 = 0; i0 < n_src; i0 += 128) {
+    const int i = i0 + t;
+    double g = __longlong_as_double(0x7FF8000000000000ll);
+    if (i < n_src && inc8[i]) g = grow[i];
+    __syncthreads();
+    g_tile[t] = g;
+    __syncthreads();
+    const int lim = min(128, n_src - i0);
+    for (int j = 0; j < lim; ++j) {
+      const double gj = g_tile[j];
+      if (!(gj == gj) || isinf(gj)) continue;  // uniform across the CTA
+      if (t == 0) ++cnt;
+      const double g2 = gj * gj, g3 = g2 * gj, g4 = g2 * g2;
+      const double* frow = featT + (int64_t)(i0 + j) * n_featm_pad;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int f = t + 128 * k;
+        if (f < nf) {
+          const double h = f == 0 ? 1.0 : frow[f - 1];
+          acc[k][0] += h;
+          acc[k][1] = fma(gj, h, acc[k][1]);
+          acc[k][2] = fma(g2, h, acc[k][2]);
+          acc[k][3] = fma(g3, h, acc[k][3]);
+          acc[k][4] = fma(g4, h, acc[k][4]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int f = t + 128 * k;
+    if (f < nf)
+#pragma unroll
+      for (int a = 0; a < 5; ++a) R[(int64_t)snp * 5 * nf + a * nf + f] = acc[k][a];
+  }
+  if (t == 0) n_out[snp] = cnt;
+}
+
+void launch_power_sums(gwsem_engine* e, const FitProgram& fp, const PeopleLayout& pl, int n_snps,
+                       const double* d_geno, const double* d_featT, int n_featm_pad, double* d_R, int32_t* d_n) {
+  if (n_snps <= 0) return;
+  if (fp.nf > 256) fail("too many features for the generic statistics kernel (%d > 256)", fp.nf);
+  power_sums_kernel<<<n_snps, 128, 0, e->stream>>>(fp, pl.n_src, pl.n_pad, pl.d_inc8, d_geno, d_featT, n_featm_pad,
+                                                   d_R, d_n);
+  GW_CUDA(cudaGetLastError());
   e->launches++;
 }
 

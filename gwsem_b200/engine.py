@@ -159,3 +159,64 @@ class Model:
             self.close()
         except Exception:
             pass
+
+
+class Source:
+    """A genotype file (the reference's data providers, src/loader.cpp): pgen / bed / bgen."""
+
+    def __init__(self, path, method=None, src_rows=-1):
+        import os
+        self.h = C.c_void_p()
+        check(lib().gwsem_source_open(os.fsencode(path), method.encode() if method else None, int(src_rows),
+                                      C.byref(self.h)))
+        self.path = path
+
+    @property
+    def num_variants(self):
+        n = lib().gwsem_source_num_variants(self.h)
+        return None if n < 0 else n
+
+    @property
+    def num_samples(self):
+        return lib().gwsem_source_num_samples(self.h)
+
+    @property
+    def load_counter(self):
+        return lib().gwsem_source_load_counter(self.h)
+
+    @property
+    def checkpoint_columns(self):
+        return lib().gwsem_source_checkpoint_columns(self.h).decode().split("\t")
+
+    def context(self, index):
+        buf = C.create_string_buffer(4096)
+        check(lib().gwsem_source_context(self.h, int(index), buf, 4096))
+        return buf.value.decode().split("\t") if buf.value else []
+
+    def load_rows(self, engine, snp_index, row_filter=None):
+        """loadRow for a batch of 0-based SNP indices -> (geno[n, dest_rows], maf[n])"""
+        idx = np.ascontiguousarray(np.asarray(snp_index, dtype=np.int32))
+        n = self.num_samples
+        rf = None if row_filter is None else np.ascontiguousarray(np.asarray(row_filter).astype(np.int32))
+        dest = n if rf is None else int((rf == 0).sum())
+        out = np.empty((len(idx), dest))
+        maf = np.empty(len(idx))
+        check(lib().gwsem_source_load_rows(engine.h, self.h, _ptr(idx), len(idx), _ptr(rf), _ptr(out), _ptr(maf)))
+        return out, maf
+
+    def close(self):
+        if self.h:
+            lib().gwsem_source_close(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

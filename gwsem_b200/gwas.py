@@ -1,0 +1,158 @@
+"""GWAS(): the reference's driver API (R/model.R:24-45, 122-315) over the native engine.
+
+``GWAS(model, snpData, out, SNP=..., startFrom=..., rowFilter=...)`` keeps the argument
+names, defaults and error messages of the reference; instead of assembling an OpenMx compute
+plan it hands the flattened model, the genotype source and the job description to
+``gwsem_gwas_run`` (C ABI), which runs the whole per-SNP loop on the GPU and writes the same
+tab separated checkpoint log that ``loadResults`` reads.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+from .engine import Engine, Model, Source
+from .model import flatten
+
+_engines = {}
+
+
+def _engine(device):
+    if device not in _engines:
+        _engines[device] = Engine(device)
+    return _engines[device]
+
+
+def processSnpData(snpData):
+    """R/model.R:24-45: file extension -> data provider method."""
+    single = isinstance(snpData, str)
+    items = [snpData] if single else list(snpData)
+    ext, stem, method = [], [], []
+    for s in items:
+        pieces = s.split(".")
+        if len(pieces) < 2:
+            raise ValueError(f"Please rename snpData '{s}' to the form file.ext where ext reflects the format of the data")
+        e = pieces[-1]
+        if e in ("pgen", "bed"):
+            m = "pgen"
+        elif e == "bgen":
+            m = "bgen"
+        else:
+            raise ValueError(f"Unrecognized file extension '{e}' inferred from snpData '{s}'")
+        ext.append(e)
+        stem.append(".".join(pieces[:-1]))
+        method.append(m)
+    return dict(snpFileExt=ext, stem=stem, method=method)
+
+
+def numAvailableRecords(snpData):
+    """R/model.R:210-224.  NA (None) for a .bed, whose variant count needs the sample count."""
+    items = [snpData] if isinstance(snpData, str) else list(snpData)
+    psd = processSnpData(items)
+    out = {}
+    for path, method in zip(items, psd["method"]):
+        with Source(path, method, -1) as s:
+            out[path] = s.num_variants
+    return out
+
+
+def buildAnalysesPlan(snpData, sliceSize):
+    """R/model.R:249-274: split each file's SNP range into jobs of about sliceSize SNPs."""
+    import pandas as pd
+    items = [snpData] if isinstance(snpData, str) else list(snpData)
+    recs = numAvailableRecords(items)
+    rows = []
+    for path in items:
+        n = recs[path]
+        slices = max(n // int(round(sliceSize)), 1)
+        if slices == 1:
+            rows.append(dict(path=path, begin=1, end=n, count=n, slice=1))
+            continue
+        breaks = np.floor(np.linspace(1, n, slices + 1)).astype(int)
+        begin = breaks[:-1]
+        end = np.append(begin[1:] - 1, n)
+        for k in range(slices):
+            rows.append(dict(path=path, begin=int(begin[k]), end=int(end[k]), count=int(end[k] - begin[k] + 1), slice=k + 1))
+    return pd.DataFrame(rows)
+
+
+def _offdiag(model, names):
+    """R/model.R:176-185: off-diagonal vcov entries needed for gxe follow-up (signifGxE)."""
+    if not model.gxe:
+        return []
+    gxe = ["snp_" + e for e in model.gxe]
+    col = model.vars.index("snp")
+    outcome = [model.vars[r] for r in range(len(model.vars)) if model.A["free"][r, col]]
+    want = [f"snp_to_{o}" for o in outcome] + [f"{g}_to_{o}" for o in outcome for g in gxe + list(model.gxe)]
+    return [n for n in want if n in names]
+
+
+class GWASResult:
+    """What the reference's GWAS() returns invisibly: the model with the last SNP loaded."""
+
+    def __init__(self, model, out, rows, last_snp, load_counter):
+        self.model, self.out, self.rows_written = model, out, rows
+        self.last_snp = last_snp          # m$data$observed$snp after the run
+        self.loadCounter = load_counter   # m$compute$steps[[2]]$debug$loadCounter
+
+
+def GWAS(model, snpData, out="out.log", *dots, SNP=None, startFrom=1, rowFilter=None, device=0, batch_snps=0):
+    """R/model.R:305-315."""
+    if dots:
+        raise ValueError("Rejected are any values passed in the '...' argument")
+    if not isinstance(snpData, str):
+        raise NotImplementedError("multi-group snpData (one file per sub-model) is not implemented")
+    psd = processSnpData(snpData)
+    method, ext, stem = psd["method"][0], psd["snpFileExt"][0], psd["stem"][0]
+    if isinstance(rowFilter, dict):
+        unknown = [k for k in rowFilter if k != model.name]
+        if unknown:
+            raise ValueError("Cannot find model associated with rowFilter: " + ", ".join(f"'{k}'" for k in unknown))
+        rowFilter = rowFilter.get(model.name)
+    n_rows = len(model.data)
+    if rowFilter is not None:
+        rowFilter = np.asarray(rowFilter).astype(bool)
+        if int((~rowFilter).sum()) != n_rows:
+            raise ValueError(f"rowFilter keeps {int((~rowFilter).sum())} rows, which does not match the number of rows "
+                             f"of observed data ({n_rows})")
+        src_rows = len(rowFilter)
+    else:
+        src_rows = n_rows
+    flat = flatten(model)
+    if (flat["fitfun"], flat["continuous_type"]) != ("WLS", "cumulants"):
+        raise NotImplementedError(
+            f"fit function {flat['fitfun']} with {flat['continuous_type']} summary statistics (ordinal items, exogenous "
+            "covariates or ML) is not implemented on the device yet; only WLS/cumulants models run")
+    eng = _engine(device)
+    data = {c: model.data[c].to_numpy(dtype=np.float64) for c in model.data.columns
+            if c != "snp" and not c.startswith("snp_") and model.data[c].dtype.kind in "fiu"}
+    with Source(snpData, method, src_rows) as src:
+        gm = Model(eng, flat, data)
+        try:
+            gm.set_row_filter(rowFilter, src_rows)
+            names = flat["par_names"]
+            off = _offdiag(model, names)
+            pairs = [(names.index(a), names.index(b)) for i, a in enumerate(off) for b in off[i + 1:]]
+            ctx = {"pgen": stem + ".pvar", "bed": stem + ".bim"}.get(ext)
+            snp_arr = None if SNP is None else np.ascontiguousarray(np.asarray(SNP, dtype=np.int32).reshape(-1))
+            c_names = (C.c_char_p * len(names))(*[n.encode() for n in names])
+            c_manifest = (C.c_char_p * flat["nm"])(*[n.encode() for n in flat["manifest"]])
+            c_pairs = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1))
+            job = _lib.Job(snp_arr.ctypes.data_as(C.POINTER(C.c_int32)) if snp_arr is not None else None,
+                           0 if snp_arr is None else len(snp_arr), int(startFrom), os.fsencode(out), c_names,
+                           os.fsencode(ctx) if ctx else None,
+                           c_pairs.ctypes.data_as(C.POINTER(C.c_int32)) if len(pairs) else None, len(pairs),
+                           int(batch_snps), model.name.encode(), c_manifest)
+            written = C.c_int64()
+            check(lib().gwsem_gwas_run(gm.h, src.h, C.byref(job), C.byref(written)))
+            last = None
+            if written.value:
+                last_idx = int(snp_arr[-1]) - 1 if snp_arr is not None else src.num_variants - 1
+                last = src.load_rows(eng, [last_idx], rowFilter)[0][0]
+            counter = src.load_counter
+        finally:
+            gm.close()
+    print(f"Done. See '{out}' for results")
+    return GWASResult(model, out, int(written.value), last, counter)

@@ -152,6 +152,8 @@ typedef struct {
   const int32_t* vcov_pairs;  /* 2 * n_vcov_pairs parameter indices: off-diagonals to write */
   int32_t n_vcov_pairs;
   int32_t batch_snps;         /* SNPs per device batch, 0 = auto */
+  const char* model_name;     /* for catch1 messages ("<model>.data: ...") */
+  const char* const* manifest_names; /* n_manifest names, for catch1 messages */
 } gwsem_job;
 
 int gwsem_gwas_run(gwsem_model* m, gwsem_source* s, const gwsem_job* job, int64_t* rows_written);
