@@ -52,6 +52,20 @@ __host__ __device__ inline WarpScratch scratch_layout(int p, int q, int nv, int 
 
 size_t fit_scratch_doubles(int p, int q, int nv, int P, int nf) { return scratch_layout(p, q, nv, P, nf).total; }
 
+// A group of LANES threads (1 or 32) works on one SNP.
+template <int LANES>
+__device__ __forceinline__ void gsync() {
+  if (LANES > 1) gsync<LANES>();
+}
+template <int LANES>
+__device__ __forceinline__ double gbcast(double v) {
+  return LANES > 1 ? __shfl_sync(0xffffffffu, v, 0) : v;
+}
+template <int LANES>
+__device__ __forceinline__ bool gany(bool p) {
+  return LANES > 1 ? __any_sync(0xffffffffu, p) != 0 : p;
+}
+
 __device__ __forceinline__ int vech_index(int i, int j, int p) {  // i >= j, column-major lower triangle
   return j * p - j * (j - 1) / 2 + (i - j);
 }
@@ -59,6 +73,7 @@ __device__ __forceinline__ int vech_index(int i, int j, int p) {  // i >= j, col
 // In-place Cholesky (lower) of the n x n row-major matrix a; returns false if not positive
 // definite.  A pivot below 1e-10 of its natural scale (scale[j] if given, else the diagonal
 // entry itself) counts as zero, so exactly singular matrices are reported, not inverted.
+template <int LANES>
 __device__ bool warp_cholesky(double* a, int n, int lane, const double* scale = nullptr) {
   for (int j = 0; j < n; ++j) {
     double d = 0.0, d0 = 0.0;
@@ -67,33 +82,35 @@ __device__ bool warp_cholesky(double* a, int n, int lane, const double* scale = 
       if (scale) d0 = scale[j];
       for (int k = 0; k < j; ++k) d -= a[j * n + k] * a[j * n + k];
     }
-    d = __shfl_sync(0xffffffffu, d, 0);
-    d0 = __shfl_sync(0xffffffffu, d0, 0);
+    d = gbcast<LANES>(d);
+    d0 = gbcast<LANES>(d0);
     if (!(d > 1e-10 * d0) || !isfinite(d)) return false;
     const double dj = sqrt(d);
     if (lane == 0) a[j * n + j] = dj;
-    for (int i = j + 1 + lane; i < n; i += 32) {
+    for (int i = j + 1 + lane; i < n; i += LANES) {
       double v = a[i * n + j];
       for (int k = 0; k < j; ++k) v -= a[i * n + k] * a[j * n + k];
       a[i * n + j] = v / dj;
     }
-    __syncwarp();
+    gsync<LANES>();
   }
   return true;
 }
 
 // Solve L y = b in place for `ncol` right-hand sides stored as columns of b (row-major n x ld).
+template <int LANES>
 __device__ void warp_forward_solve(const double* L, int n, double* b, int ld, int ncol, int lane) {
-  for (int c = lane; c < ncol; c += 32) {
+  for (int c = lane; c < ncol; c += LANES) {
     for (int i = 0; i < n; ++i) {
       double v = b[i * ld + c];
       for (int k = 0; k < i; ++k) v -= L[i * n + k] * b[k * ld + c];
       b[i * ld + c] = v / L[i * n + i];
     }
   }
-  __syncwarp();
+  gsync<LANES>();
 }
 
+template <int LANES>
 struct ModelEval {
   const FitProgram& fp;
   const WarpScratch& ws;
@@ -104,59 +121,59 @@ struct ModelEval {
   __device__ void implied(const double* theta, double* sig) {
     const int nv = fp.nv, p = fp.p;
     double *A = sm + ws.A, *S = sm + ws.S, *Z = sm + ws.Z, *C = sm + ws.C, *T = sm + ws.T;
-    for (int e = lane; e < nv * nv; e += 32) { A[e] = 0.0; S[e] = 0.0; Z[e] = (e / nv == e % nv) ? 1.0 : 0.0; }
-    __syncwarp();
-    for (int e = lane; e < fp.n_cells; e += 32) {
+    for (int e = lane; e < nv * nv; e += LANES) { A[e] = 0.0; S[e] = 0.0; Z[e] = (e / nv == e % nv) ? 1.0 : 0.0; }
+    gsync<LANES>();
+    for (int e = lane; e < fp.n_cells; e += LANES) {
       const int m = fp.cell_mat[e], r = fp.cell_row[e], c = fp.cell_col[e], k = fp.cell_par[e];
       const double v = k >= 0 ? theta[k] : fp.cell_val[e];
       if (m == 0) A[r * nv + c] = v;
       else if (m == 1) S[r * nv + c] = v;
     }
-    __syncwarp();
+    gsync<LANES>();
     // Z = I + A + A^2 + ...   (A is nilpotent for recursive path models; nv terms suffice)
-    for (int e = lane; e < nv * nv; e += 32) T[e] = A[e];
-    __syncwarp();
+    for (int e = lane; e < nv * nv; e += LANES) T[e] = A[e];
+    gsync<LANES>();
     for (int it = 0; it < nv; ++it) {
       bool nz = false;
-      for (int e = lane; e < nv * nv; e += 32) { Z[e] += T[e]; nz |= (T[e] != 0.0); }
-      if (!__any_sync(0xffffffffu, nz)) break;
-      __syncwarp();
+      for (int e = lane; e < nv * nv; e += LANES) { Z[e] += T[e]; nz |= (T[e] != 0.0); }
+      if (!gany<LANES>(nz)) break;
+      gsync<LANES>();
       // C (temp) = T * A
-      for (int e = lane; e < nv * nv; e += 32) {
+      for (int e = lane; e < nv * nv; e += LANES) {
         const int i = e / nv, j = e % nv;
         double v = 0.0;
         for (int k = 0; k < nv; ++k) v += T[i * nv + k] * A[k * nv + j];
         C[e] = v;
       }
-      __syncwarp();
-      for (int e = lane; e < nv * nv; e += 32) T[e] = C[e];
-      __syncwarp();
+      gsync<LANES>();
+      for (int e = lane; e < nv * nv; e += LANES) T[e] = C[e];
+      gsync<LANES>();
     }
-    __syncwarp();
+    gsync<LANES>();
     // T = Z S ; C = T Z'
-    for (int e = lane; e < nv * nv; e += 32) {
+    for (int e = lane; e < nv * nv; e += LANES) {
       const int i = e / nv, j = e % nv;
       double v = 0.0;
       for (int k = 0; k < nv; ++k) v += Z[i * nv + k] * S[k * nv + j];
       T[e] = v;
     }
-    __syncwarp();
-    for (int e = lane; e < nv * nv; e += 32) {
+    gsync<LANES>();
+    for (int e = lane; e < nv * nv; e += LANES) {
       const int i = e / nv, j = e % nv;
       double v = 0.0;
       for (int k = 0; k < nv; ++k) v += T[i * nv + k] * Z[j * nv + k];
       C[e] = v;
     }
-    __syncwarp();
-    for (int e = lane; e < fp.q; e += 32) sig[e] = C[fp.stat_i[e] * nv + fp.stat_j[e]];
-    __syncwarp();
+    gsync<LANES>();
+    for (int e = lane; e < fp.q; e += LANES) sig[e] = C[fp.stat_i[e] * nv + fp.stat_j[e]];
+    gsync<LANES>();
   }
 
   // J[e][k] = d sig_e / d theta_k (uses Z, C left by implied())
   __device__ void jacobian(double* J) {
     const int nv = fp.nv, P = fp.P;
     const double *Z = sm + ws.Z, *C = sm + ws.C;
-    for (int idx = lane; idx < fp.q * P; idx += 32) {
+    for (int idx = lane; idx < fp.q * P; idx += LANES) {
       const int e = idx / P, k = idx % P;
       const int i = fp.stat_i[e], j = fp.stat_j[e];
       double v = 0.0;
@@ -168,7 +185,7 @@ struct ModelEval {
       }
       J[idx] = v;
     }
-    __syncwarp();
+    gsync<LANES>();
   }
 };
 
@@ -191,28 +208,29 @@ __device__ double central_moment(const FitProgram& fp, const int* vars, int k, c
   return sum;
 }
 
+template <int LANES>
 __global__ void __launch_bounds__(128)
     fit_cumulants_kernel(FitProgram fp, int n_snps, const double* __restrict__ Rtab, const int32_t* __restrict__ n_rows,
                          const double* __restrict__ maf_in, gwsem_result res) {
   extern __shared__ double smem_d[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int snp = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int group = threadIdx.x / LANES, lane = threadIdx.x % LANES;
+  const int snp = blockIdx.x * (blockDim.x / LANES) + group;
   if (snp >= n_snps) return;
   const int p = fp.p, q = fp.q, nv = fp.nv, P = fp.P, nf = fp.nf;
   const WarpScratch ws = scratch_layout(p, q, nv, P, nf);
-  double* sm = smem_d + (size_t)warp * ws.total;
+  double* sm = smem_d + (size_t)group * (LANES == 1 ? (ws.total | 1) : ws.total);  // odd stride: no bank conflicts
 
   const int n = n_rows[snp];
   const double inv_n = 1.0 / (double)n;
   double* R = sm + ws.R;
   // raw moment table R[a][f] = sum over complete rows of g^a * h_f
-  for (int e = lane; e < 5 * nf; e += 32) R[e] = Rtab[(int64_t)snp * 5 * nf + e];
-  __syncwarp();
+  for (int e = lane; e < 5 * nf; e += LANES) R[e] = Rtab[(int64_t)snp * 5 * nf + e];
+  gsync<LANES>();
 
   double* est = res.est + (int64_t)snp * P;
   double* vcov = res.vcov + (int64_t)snp * P * P;
-  for (int k = lane; k < P; k += 32) est[k] = fp.par_start[k];
-  for (int k = lane; k < P * P; k += 32) vcov[k] = __longlong_as_double((long long)GWSEM_NA_BITS);
+  for (int k = lane; k < P; k += LANES) est[k] = fp.par_start[k];
+  for (int k = lane; k < P * P; k += LANES) vcov[k] = __longlong_as_double((long long)GWSEM_NA_BITS);
   if (lane == 0) {
     res.maf[snp] = maf_in[snp];
     res.n_used[snp] = n;
@@ -225,18 +243,18 @@ __global__ void __launch_bounds__(128)
 
   // ---- O1/O2: means, covariance, Gamma
   double* mu = sm + ws.mu;
-  for (int v = lane; v < p; v += 32) mu[v] = R[fp.idx4[((v * (p + 1) + p) * (p + 1) + p) * (p + 1) + p]] * inv_n;
-  __syncwarp();
+  for (int v = lane; v < p; v += LANES) mu[v] = R[fp.idx4[((v * (p + 1) + p) * (p + 1) + p) * (p + 1) + p]] * inv_n;
+  gsync<LANES>();
   double* c2 = sm + ws.c2;      // N-denominator central second moments
   double* sobs = sm + ws.sobs;  // N-1 denominator: the observed covariance statistics
   const double nm1 = (double)n / (double)(n - 1);
-  for (int e = lane; e < q; e += 32) {
+  for (int e = lane; e < q; e += LANES) {
     const int vars[2] = {fp.stat_j[e], fp.stat_i[e]};  // sorted ascending (j <= i)
     const double m = central_moment(fp, vars, 2, mu, R, inv_n);
     c2[e] = m;
     sobs[e] = m * nm1;
   }
-  __syncwarp();
+  gsync<LANES>();
   int bad_var = -1;
   for (int v = 0; v < p; ++v) {
     const double var = sobs[vech_index(v, v, p)];
@@ -248,7 +266,7 @@ __global__ void __launch_bounds__(128)
     return;
   }
   double* L = sm + ws.L;
-  for (int idx = lane; idx < q * q; idx += 32) {
+  for (int idx = lane; idx < q * q; idx += LANES) {
     const int e1 = idx / q, e2 = idx % q;
     if (e2 > e1) { continue; }
     int vars[4] = {fp.stat_j[e1], fp.stat_i[e1], fp.stat_j[e2], fp.stat_i[e2]};
@@ -264,12 +282,12 @@ __global__ void __launch_bounds__(128)
     L[e1 * q + e2] = gam;
     L[e2 * q + e1] = gam;
   }
-  __syncwarp();
+  gsync<LANES>();
   // natural scale of Gamma[(ij),(ij)] is s_ii * s_jj; kept in `sig` until the optimiser needs it
-  for (int e = lane; e < q; e += 32)
+  for (int e = lane; e < q; e += LANES)
     (sm + ws.sig)[e] = c2[vech_index(fp.stat_i[e], fp.stat_i[e], p)] * c2[vech_index(fp.stat_j[e], fp.stat_j[e], p)];
-  __syncwarp();
-  if (!warp_cholesky(L, q, lane, sm + ws.sig)) {
+  gsync<LANES>();
+  if (!warp_cholesky<LANES>(L, q, lane, sm + ws.sig)) {
     if (lane == 0) res.catch_code[snp] = GWSEM_CATCH_ACOV_NOT_PD;
     return;
   }
@@ -277,21 +295,21 @@ __global__ void __launch_bounds__(128)
   // ---- O5-O7: damped Gauss-Newton on the whitened residual  r~ = L^-1 (s - sigma), F = n |r~|^2
   double *theta = sm + ws.theta, *cand = sm + ws.cand, *sig = sm + ws.sig, *r = sm + ws.r, *J = sm + ws.J;
   double *g = sm + ws.g, *H = sm + ws.H, *Hc = sm + ws.Hc, *delta = sm + ws.delta;
-  ModelEval ev{fp, ws, sm, lane};
+  ModelEval<LANES> ev{fp, ws, sm, lane};
   const double dn = (double)n;
 
   auto objective = [&](const double* th, double* resid) -> double {
     ev.implied(th, sig);
-    for (int e = lane; e < q; e += 32) resid[e] = sobs[e] - sig[e];
-    __syncwarp();
-    warp_forward_solve(L, q, resid, 1, 1, lane);
+    for (int e = lane; e < q; e += LANES) resid[e] = sobs[e] - sig[e];
+    gsync<LANES>();
+    warp_forward_solve<LANES>(L, q, resid, 1, 1, lane);
     double f = 0.0;
     for (int e = 0; e < q; ++e) f += resid[e] * resid[e];
     return dn * f;
   };
 
-  for (int k = lane; k < P; k += 32) theta[k] = fp.par_start[k];
-  __syncwarp();
+  for (int k = lane; k < P; k += LANES) theta[k] = fp.par_start[k];
+  gsync<LANES>();
   double F = objective(theta, r);
   double lam = 1e-4;
   int status = GWSEM_STATUS_ITERATION_LIMIT;
@@ -301,30 +319,30 @@ __global__ void __launch_bounds__(128)
     // implied() for theta was the last evaluation at this point (Z, C valid)
     ev.implied(theta, sig);
     ev.jacobian(J);
-    warp_forward_solve(L, q, J, P, P, lane);  // J~ = L^-1 J
-    for (int k = lane; k < P; k += 32) {
+    warp_forward_solve<LANES>(L, q, J, P, P, lane);  // J~ = L^-1 J
+    for (int k = lane; k < P; k += LANES) {
       double v = 0.0;
       for (int e = 0; e < q; ++e) v += J[e * P + k] * r[e];
       g[k] = dn * v;
     }
-    for (int idx = lane; idx < P * P; idx += 32) {
+    for (int idx = lane; idx < P * P; idx += LANES) {
       const int a = idx / P, b = idx % P;
       double v = 0.0;
       for (int e = 0; e < q; ++e) v += J[e * P + a] * J[e * P + b];
       H[idx] = dn * v;
     }
-    __syncwarp();
+    gsync<LANES>();
     bool improved = false;
     double Fc = F;
     for (int attempt = 0; attempt < 30; ++attempt) {
-      for (int idx = lane; idx < P * P; idx += 32) {
+      for (int idx = lane; idx < P * P; idx += LANES) {
         const int a = idx / P, b = idx % P;
         double v = H[idx];
         if (a == b) v += lam * fmax(H[idx], 1e-12);
         Hc[idx] = v;
       }
-      __syncwarp();
-      if (!warp_cholesky(Hc, P, lane)) { lam *= 10; continue; }
+      gsync<LANES>();
+      if (!warp_cholesky<LANES>(Hc, P, lane)) { lam *= 10; continue; }
       if (lane == 0) {  // solve Hc Hc' delta = g
         for (int i = 0; i < P; ++i) {
           double v = g[i];
@@ -337,14 +355,14 @@ __global__ void __launch_bounds__(128)
           delta[i] = v / Hc[i * P + i];
         }
       }
-      __syncwarp();
-      for (int k = lane; k < P; k += 32) {
+      gsync<LANES>();
+      for (int k = lane; k < P; k += LANES) {
         double c = theta[k] + delta[k];
         const double lb = fp.par_lbound[k];
         if (lb == lb && c < lb) c = lb;
         cand[k] = c;
       }
-      __syncwarp();
+      gsync<LANES>();
       Fc = objective(cand, sm + ws.rc);
       if (isfinite(Fc) && Fc <= F) { improved = true; break; }
       lam *= 10;
@@ -358,10 +376,10 @@ __global__ void __launch_bounds__(128)
     double step = 0.0;
     for (int k = 0; k < P; ++k) step = fmax(step, fabs(cand[k] - theta[k]) / (fabs(theta[k]) + 1e-3));
     const double dF = F - Fc;
-    __syncwarp();
-    for (int k = lane; k < P; k += 32) theta[k] = cand[k];
-    for (int e = lane; e < q; e += 32) r[e] = (sm + ws.rc)[e];
-    __syncwarp();
+    gsync<LANES>();
+    for (int k = lane; k < P; k += LANES) theta[k] = cand[k];
+    for (int e = lane; e < q; e += LANES) r[e] = (sm + ws.rc)[e];
+    gsync<LANES>();
     F = Fc;
     lam = fmax(lam / 10, 1e-12);
     if (step < 1e-10 || dF <= 1e-14 * (1 + F)) { status = GWSEM_STATUS_OK; break; }
@@ -371,18 +389,18 @@ __global__ void __launch_bounds__(128)
   // ---- O8: vcov = (J' W J)^-1 at the solution
   ev.implied(theta, sig);
   ev.jacobian(J);
-  warp_forward_solve(L, q, J, P, P, lane);
-  for (int idx = lane; idx < P * P; idx += 32) {
+  warp_forward_solve<LANES>(L, q, J, P, P, lane);
+  for (int idx = lane; idx < P * P; idx += LANES) {
     const int a = idx / P, b = idx % P;
     double v = 0.0;
     for (int e = 0; e < q; ++e) v += J[e * P + a] * J[e * P + b];
     H[idx] = dn * v;
   }
-  __syncwarp();
-  const bool pd = warp_cholesky(H, P, lane);
+  gsync<LANES>();
+  const bool pd = warp_cholesky<LANES>(H, P, lane);
   if (pd) {
     // inverse via solves against the identity: column c handled by lane c
-    for (int c = lane; c < P; c += 32) {
+    for (int c = lane; c < P; c += LANES) {
       double* x = Hc + c;  // column c of Hc (stride P)
       for (int i = 0; i < P; ++i) {
         double v = (i == c) ? 1.0 : 0.0;
@@ -395,10 +413,10 @@ __global__ void __launch_bounds__(128)
         x[i * P] = v / H[i * P + i];
       }
     }
-    __syncwarp();
-    for (int idx = lane; idx < P * P; idx += 32) vcov[idx] = Hc[idx];
+    gsync<LANES>();
+    for (int idx = lane; idx < P * P; idx += LANES) vcov[idx] = Hc[idx];
   }
-  for (int k = lane; k < P; k += 32) est[k] = theta[k];
+  for (int k = lane; k < P; k += LANES) est[k] = theta[k];
   if (lane == 0) {
     res.fit[snp] = F;
     res.status[snp] = status;
@@ -409,15 +427,22 @@ __global__ void __launch_bounds__(128)
 void launch_fit_cumulants(gwsem_engine* e, const FitProgram& fp, int n_snps, const double* d_R, const int32_t* d_n,
                           const double* d_maf, const gwsem_result& d_res) {
   if (n_snps <= 0) return;
-  const size_t per_warp = fit_scratch_doubles(fp.p, fp.q, fp.nv, fp.P, fp.nf) * sizeof(double);
-  int warps = 4;
-  while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
-  if (per_warp * warps > 227 * 1024) fail("model too large for the per-SNP fit kernel (%zu bytes of scratch)", per_warp);
-  const size_t smem = per_warp * warps;
-  GW_CUDA(cudaFuncSetAttribute(fit_cumulants_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (n_snps + warps - 1) / warps;
+  const size_t per_snp = fit_scratch_doubles(fp.p, fp.q, fp.nv, fp.P, fp.nf) * sizeof(double);
   e->prof_begin(kFamFit);
-  fit_cumulants_kernel<<<grid, warps * 32, smem, e->stream>>>(fp, n_snps, d_R, d_n, d_maf, d_res);
+  if (per_snp * 64 <= 96 * 1024) {
+    // small model: one thread per SNP, each with its own shared-memory slab
+    const int threads = 64;
+    const size_t smem = (per_snp + 8) * threads;
+    GW_CUDA(cudaFuncSetAttribute(fit_cumulants_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fit_cumulants_kernel<1><<<(n_snps + threads - 1) / threads, threads, smem, e->stream>>>(fp, n_snps, d_R, d_n, d_maf, d_res);
+  } else {
+    int warps = 4;
+    while (warps > 1 && per_snp * warps > 200 * 1024) warps >>= 1;
+    if (per_snp * warps > 227 * 1024) fail("model too large for the per-SNP fit kernel (%zu bytes of scratch)", per_snp);
+    const size_t smem = per_snp * warps;
+    GW_CUDA(cudaFuncSetAttribute(fit_cumulants_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fit_cumulants_kernel<32><<<(n_snps + warps - 1) / warps, warps * 32, smem, e->stream>>>(fp, n_snps, d_R, d_n, d_maf, d_res);
+  }
   GW_CUDA(cudaGetLastError());
   e->prof_end(kFamFit);
   e->launches++;

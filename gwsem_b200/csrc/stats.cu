@@ -10,6 +10,8 @@
 //   class_sums_kernel   classes 1 and 2, FP64 accumulate (bound: FP64 pipe; genotype bytes
 //                       are read once from HBM through a cp.async.bulk (TMA) + mbarrier ring)
 //   count_missing_kernel  class counts by popcount and the (rare) missing class, one warp per SNP
+#include <cstdlib>
+
 #include "common.h"
 #include "fit_program.h"
 #include "kernels.h"
@@ -35,6 +37,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // 1-D bulk async copy global -> shared, completion signalled on an mbarrier (TMA engine).
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -64,7 +69,7 @@ __device__ __forceinline__ unsigned long long bed_to_plink2(unsigned long long w
 // mbarriers.  All 32 lanes read the same 32-person word of a genotype row (shared-memory
 // broadcast) and pick their own 2 bits; the adds are DFMAs with 0/1 weights.
 template <int S, int F, int WARPS, int TILE, int STAGES, bool PLINK1>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32 + 32)
     class_sums_kernel(const uint8_t* __restrict__ packed, int64_t pitch, int n_snps, int n_src,
                       const uint8_t* __restrict__ inc8, const double* __restrict__ feat, int n_pad,
                       int feat_stride_out, double* __restrict__ sums) {
@@ -75,7 +80,8 @@ __global__ void __launch_bounds__(WARPS * 32)
   constexpr int kFeatBytes = F * TILE * 8;
   constexpr int kStageBytes = kGenoBytes + kFeatBytes + TILE;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // STAGES barriers
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // STAGES "tile landed" barriers
+  uint64_t* empty = full + STAGES;                     // STAGES "tile consumed" barriers
   uint8_t* tiles = smem + 128;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -85,7 +91,10 @@ __global__ void __launch_bounds__(WARPS * 32)
   const int64_t row_bytes = (int64_t)((n_src + 3) / 4 + 15) / 16 * 16;  // bytes worth copying per row (<= pitch)
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -103,8 +112,15 @@ __global__ void __launch_bounds__(WARPS * 32)
       bulk_g2s(dst + kGenoBytes + f * TILE * 8, feat + (int64_t)f * n_pad + (int64_t)t * TILE, people * 8, &full[stage]);
     bulk_g2s(dst + kGenoBytes + kFeatBytes, inc8 + (int64_t)t * TILE, people, &full[stage]);
   };
-  if (threadIdx.x == 0)
-    for (int t = 0; t < STAGES && t < n_tiles; ++t) issue(t);
+  if (warp == WARPS) {
+    // producer warp: one lane keeps the ring full; consumers never meet at a CTA-wide barrier
+    if (lane == 0)
+      for (int t = 0; t < n_tiles; ++t) {
+        if (t >= STAGES) mbar_wait(&empty[t % STAGES], ((t / STAGES) - 1) & 1);
+        issue(t);
+      }
+    return;
+  }
 
   double a1[S][F], a2[S][F];
 #pragma unroll
@@ -145,8 +161,8 @@ __global__ void __launch_bounds__(WARPS * 32)
         }
       }
     }
-    __syncthreads();  // every warp is done with this stage
-    if (threadIdx.x == 0 && t + STAGES < n_tiles) issue(t + STAGES);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);  // this warp is done with the stage
   }
 
 #pragma unroll
@@ -184,13 +200,13 @@ static void launch_chunk(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch
   if (plink1) {
     auto k = class_sums_kernel<S, F, WARPS, TILE, STAGES, true>;
     GW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, WARPS * 32, smem, e->stream>>>(d_packed, pitch, n_snps, pl.n_src, pl.d_inc8, d_feat, pl.n_pad,
-                                              n_feat_total, d_sums);
+    k<<<grid, WARPS * 32 + 32, smem, e->stream>>>(d_packed, pitch, n_snps, pl.n_src, pl.d_inc8, d_feat, pl.n_pad,
+                                                   n_feat_total, d_sums);
   } else {
     auto k = class_sums_kernel<S, F, WARPS, TILE, STAGES, false>;
     GW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, WARPS * 32, smem, e->stream>>>(d_packed, pitch, n_snps, pl.n_src, pl.d_inc8, d_feat, pl.n_pad,
-                                              n_feat_total, d_sums);
+    k<<<grid, WARPS * 32 + 32, smem, e->stream>>>(d_packed, pitch, n_snps, pl.n_src, pl.d_inc8, d_feat, pl.n_pad,
+                                                   n_feat_total, d_sums);
   }
   GW_CUDA(cudaGetLastError());
   e->launches++;
@@ -210,10 +226,23 @@ void launch_class_sums(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, 
     double* out = d_sums + f0;
     //                          S  F  WARPS TILE STAGES
     if (left >= 8) { launch_chunk<4, 8, 8, 512, 3>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 8; }
-    else if (left >= 4) { launch_chunk<8, 4, 4, 1024, 2>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 4; }
-    else if (left == 3) { launch_chunk<8, 3, 4, 1024, 2>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 3; }
-    else if (left == 2) { launch_chunk<8, 2, 4, 1024, 2>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 2; }
-    else { launch_chunk<8, 1, 4, 1024, 2>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 1; }
+    else if (left >= 4) { launch_chunk<8, 4, 4, 1024, 3>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 4; }
+    else if (left == 3) {
+      static const int variant = getenv("GWSEM_CS_VARIANT") ? atoi(getenv("GWSEM_CS_VARIANT")) : 0;  // tuning aid
+      switch (variant) {
+        case 1: launch_chunk<8, 3, 4, 512, 4>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); break;
+        case 2: launch_chunk<8, 3, 4, 512, 3>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); break;
+        case 3: launch_chunk<8, 3, 8, 512, 3>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); break;
+        case 4: launch_chunk<4, 3, 8, 512, 3>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); break;
+        case 5: launch_chunk<4, 3, 4, 256, 4>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); break;
+        case 6: launch_chunk<8, 3, 4, 256, 4>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); break;
+        case 7: launch_chunk<8, 3, 4, 1024, 2>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); break;
+        default: launch_chunk<8, 3, 4, 1024, 3>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); break;
+      }
+      f0 += 3;
+    }
+    else if (left == 2) { launch_chunk<8, 2, 4, 1024, 3>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 2; }
+    else { launch_chunk<8, 1, 4, 1024, 3>(e, d_packed, pitch, n_snps, plink1, pl, feat, n_feat, out); f0 += 1; }
   }
   e->prof_end(kFamClassSums);
 }
@@ -242,7 +271,7 @@ __global__ void __launch_bounds__(128)
     const int wi = w0 + lane;
     unsigned long long m3 = 0;
     if (wi < n_words) {
-      unsigned long long w = words[wi];
+      unsigned long long w = __ldg(&words[wi]);
       if (PLINK1) w = bed_to_plink2(w);
       const unsigned long long inc = incmask[wi];
       const unsigned long long lo = w & 0x5555555555555555ull, hi = (w >> 1) & 0x5555555555555555ull;

@@ -36,5 +36,9 @@ for it in range(3):
     st.synchronize()
     ms = e0.elapsed_time(e1)
     print(f"{which} N={N} M={M}: {ms:.3f} ms  {M / ms * 1e3:.3e} SNP/s  {M * packed.shape[1] / ms / 1e6:.1f} GB/s of genotype bytes", flush=True)
+eng.profile(True); eng.profile_read()
+with torch.cuda.stream(st):
+    gm.fit_2bit_device(packed.data_ptr(), packed.shape[1], M, rs)
+print("per-kernel ms:", {k: round(v[1], 3) for k, v in eng.profile_read().items() if v[0]})
 print("status OK frac", (bufs["status"] == 0).float().mean().item(), "iters mean", bufs["iterations"].float().mean().item())
 print("est[0]", bufs["est"][0].cpu().numpy(), "launches", eng.launches)
