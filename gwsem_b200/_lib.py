@@ -18,7 +18,11 @@ class ModelSpec(C.Structure):
                 ("par_start", C.POINTER(C.c_double)), ("par_lbound", C.POINTER(C.c_double)),
                 ("fit", C.c_int32), ("min_variance", C.c_double), ("n_rows", C.c_int32),
                 ("manifest_kind", C.POINTER(C.c_int32)),
-                ("manifest_data", C.POINTER(C.POINTER(C.c_double)))]
+                ("manifest_data", C.POINTER(C.POINTER(C.c_double))),
+                ("n_categories", C.POINTER(C.c_int32)), ("n_exo", C.c_int32),
+                ("exo_data", C.POINTER(C.POINTER(C.c_double))), ("exo_latent", C.POINTER(C.c_int32)),
+                ("exo_free", C.POINTER(C.c_uint8)), ("n_thresholds", C.c_int32),
+                ("thresholds", C.POINTER(C.c_double))]
 
 
 class Result(C.Structure):

@@ -29,6 +29,11 @@ struct FitProgram {
   const int32_t* par_cells = nullptr;
   const double* par_start = nullptr;
   const double* par_lbound = nullptr;
+  // marginals only: per statistic, the free threshold parameter (or -1 and its fixed value);
+  // RAM index of each exogenous covariate's latent variable
+  const int32_t* thr_par = nullptr;
+  const double* thr_val = nullptr;
+  const int32_t* exo_latent = nullptr;
 };
 
 size_t fit_scratch_doubles(int p, int q, int nv, int P, int nf);

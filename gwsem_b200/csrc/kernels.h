@@ -46,4 +46,13 @@ void launch_power_sums(gwsem_engine* e, const FitProgram& fp, const PeopleLayout
 void launch_fit_cumulants(gwsem_engine* e, const FitProgram& fp, int n_snps, const double* d_R, const int32_t* d_n,
                           const double* d_maf, const gwsem_result& d_res);
 
+// ---- marginals.cu / marg_fit.cu : WLS "marginals" path (ordinal items, exogenous covariates)
+struct MargProgram;
+void launch_marg_stats(gwsem_engine* e, const MargProgram& mp, const uint8_t* d_rows, int64_t pitch, int n_snps,
+                       int n_src, const uint8_t* d_inc8, const int32_t* d_counts, int plink1, const double* d_geno,
+                       int n_pad, double* d_summary);
+void launch_maf_from_counts(gwsem_engine* e, const int32_t* d_counts, int n_kept, int n_snps, double* d_maf);
+void launch_marg_fit(gwsem_engine* e, const FitProgram& fp, const MargProgram& mp, int n_snps, const double* d_summary,
+                     const double* d_maf, const gwsem_result& d_res);
+
 }  // namespace gwsem

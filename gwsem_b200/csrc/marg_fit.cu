@@ -1,0 +1,437 @@
+// WLS "marginals": from the per-SNP summary record (marginals.cu) to Muthen's asymptotic
+// covariance, the statistic vector, and the fit, one warp per SNP:
+//   theta = (snp mean, snp var | item stage-1 | rho(snp,item_j) | rho(item,item))
+//   acov(theta) = A^-1 B A^-T with A = [[A11, 0], [A21, A22]] in outer-product form
+//   statistics s = (means | thresholds, slopes, variances, covariances) by the delta method;
+//   a continuous variable contributes sd * rho to a covariance
+//   model-implied vector: RAM moments conditional on the exogenous covariates, ordinal rows
+//   standardised by the implied sd; damped Gauss-Newton with a central-difference Jacobian.
+// Mirrors oracle/marginals_oracle.py (fit_snp_marginals).
+#include "common.h"
+#include "fit_device.cuh"
+#include "kernels.h"
+#include "marginals.h"
+
+namespace gwsem {
+
+namespace {
+
+constexpr int LANES = 32;
+
+struct MargScratch {
+  int th, A, B, Ai, T, s, hidx, hcoef, L, scale, theta, cand, sig, sigp, r, rc, J, g, H, Hc, delta, total;
+};
+
+__host__ __device__ inline MargScratch marg_layout(int nt, int ns, int P) {
+  MargScratch m;
+  int o = 0;
+  auto take = [&](int n) { int at = o; o += n; return at; };
+  m.th = take(nt);
+  m.A = take(nt * nt);
+  m.B = take(nt * nt);
+  m.Ai = take(nt * nt);
+  m.T = take(nt * nt);
+  m.s = take(ns);
+  m.hidx = take(3 * ns);   // stored as doubles for simplicity
+  m.hcoef = take(3 * ns);
+  m.L = take(ns * ns);
+  m.scale = take(ns);
+  m.theta = take(P);
+  m.cand = take(P);
+  m.sig = take(ns);
+  m.sigp = take(ns);
+  m.r = take(ns);
+  m.rc = take(ns);
+  m.J = take(ns * P);
+  m.g = take(P);
+  m.H = take(P * P);
+  m.Hc = take(P * P);
+  m.delta = take(P);
+  m.total = o;
+  return m;
+}
+
+// model-implied statistic vector in the layout of mp.stat_*
+__device__ void implied_stats(const FitProgram& fp, const MargProgram& mp, ModelEval<LANES>& ev, const WarpScratch& ws,
+                              double* sm, const double* theta, double* sig, int lane) {
+  const int nv = fp.nv;
+  ev.implied(theta, sm + ws.sig);  // fills Z, C (and the covariance vech, unused here)
+  double* Mv = sm + ws.T;          // T is free after implied()
+  double* mu = Mv + nv;
+  for (int e = lane; e < nv; e += LANES) Mv[e] = 0.0;
+  gsync<LANES>();
+  for (int e = lane; e < fp.n_cells; e += LANES)
+    if (fp.cell_mat[e] == 2) Mv[fp.cell_col[e]] = fp.cell_par[e] >= 0 ? theta[fp.cell_par[e]] : fp.cell_val[e];
+  gsync<LANES>();
+  const double *Z = sm + ws.Z, *C = sm + ws.C;
+  for (int i = lane; i < nv; i += LANES) {
+    double v = 0.0;
+    for (int k = 0; k < nv; ++k) v += Z[i * nv + k] * Mv[k];
+    mu[i] = v;
+  }
+  gsync<LANES>();
+  for (int e = lane; e < mp.n_stat; e += LANES) {
+    const int kind = mp.stat_kind[e], a = mp.stat_a[e], b = mp.stat_b[e];
+    // manifest 0 is snp (continuous); item j is manifest j + 1
+    const bool ord_a = a > 0 && mp.n_cat[a - 1] > 0;
+    const double sda = ord_a ? sqrt(C[a * nv + a]) : 1.0;
+    double v;
+    if (kind == 0) v = mu[a];
+    else if (kind == 1) {
+      const int par = fp.thr_par[e];
+      v = ((par >= 0 ? theta[par] : fp.thr_val[e]) - mu[a]) / sda;
+    } else if (kind == 2) v = Z[a * nv + fp.exo_latent[b]] / sda;
+    else if (kind == 3) v = C[a * nv + a];
+    else {
+      const bool ord_b = b > 0 && mp.n_cat[b - 1] > 0;
+      const double sdb = ord_b ? sqrt(C[b * nv + b]) : 1.0;
+      v = C[a * nv + b] / (sda * sdb);
+    }
+    sig[e] = v;
+  }
+  gsync<LANES>();
+}
+
+__global__ void __launch_bounds__(64)
+    marg_fit_kernel(FitProgram fp, MargProgram mp, int n_snps, const double* __restrict__ summary,
+                    const double* __restrict__ maf_in, gwsem_result res) {
+  extern __shared__ double smem_d[];
+  const int group = threadIdx.x / LANES, lane = threadIdx.x % LANES;
+  const int snp = blockIdx.x * (blockDim.x / LANES) + group;
+  if (snp >= n_snps) return;
+  const int J = mp.J, n1 = mp.n1, npii = mp.npii, q0 = mp.q0, D = 2 + J;
+  const int nt = 2 + n1 + J + npii, ns = mp.n_stat, P = fp.P, nv = fp.nv;
+  const WarpScratch ws = scratch_layout(fp.p, fp.q, nv, P, 1);
+  const MargScratch ms = marg_layout(nt, ns, P);
+  double* sm = smem_d + (size_t)group * (ws.total + ms.total);
+  double* mx = sm + ws.total;
+  const double* rec = summary + (int64_t)snp * mp.sum_stride;
+  const int n = (int)rec[0];
+  const double mu_g = rec[1], var_g = rec[2];
+
+  double* est = res.est + (int64_t)snp * P;
+  double* vcov = res.vcov + (int64_t)snp * P * P;
+  const double na = __longlong_as_double((long long)GWSEM_NA_BITS);
+  for (int k = lane; k < P; k += LANES) est[k] = fp.par_start[k];
+  for (int k = lane; k < P * P; k += LANES) vcov[k] = na;
+  if (lane == 0) {
+    res.maf[snp] = maf_in[snp];
+    res.n_used[snp] = n;
+    res.fit[snp] = na;
+    res.status[snp] = GWSEM_STATUS_NA;
+    res.catch_code[snp] = GWSEM_CATCH_NONE;
+    res.catch_var[snp] = -1;
+    res.iterations[snp] = 0;
+  }
+  if (n < 2 || !(var_g * (double)n / (double)(n - 1) >= fp.min_variance)) {
+    if (lane == 0) { res.catch_code[snp] = GWSEM_CATCH_MIN_VARIANCE; res.catch_var[snp] = 0; }
+    return;
+  }
+  const double scale = (double)n / (double)mp.n_incl;  // item-only sums were taken over all included people
+
+  // ---- theta, A, B.   index map: [0,1] snp | 2.. items | ir = 2+n1 .. rho(snp,item) | ii .. rho(item,item)
+  const int ir = 2 + n1, ii = ir + J;
+  double *th = mx + ms.th, *A = mx + ms.A, *B = mx + ms.B, *Ai = mx + ms.Ai, *T = mx + ms.T;
+  for (int e = lane; e < nt; e += LANES) {
+    double v;
+    if (e == 0) v = mu_g;
+    else if (e == 1) v = var_g;
+    else if (e < ir) v = mp.theta1[e - 2];
+    else if (e < ii) v = rec[mp.o_rho + (e - ir)];
+    else v = mp.rho_ii[e - ii];
+    th[e] = v;
+  }
+  // column x of theta as a score column: SNP-dependent set D (0,1 -> 0,1; ir+j -> 2+j) or SC0 column
+  auto dcol = [&](int x) { return x < 2 ? x : (x >= ir && x < ii ? 2 + (x - ir) : -1); };
+  auto ccol = [&](int x) { return x >= 2 && x < ir ? x - 2 : (x >= ii ? n1 + (x - ii) : -1); };
+  for (int e = lane; e < nt * nt; e += LANES) {
+    const int x = e / nt, y = e % nt;
+    const int dx = dcol(x), dy = dcol(y), cx = ccol(x), cy = ccol(y);
+    double v;
+    if (dx >= 0 && dy >= 0) v = rec[mp.o_bdd + dx * D + dy];
+    else if (dx >= 0) v = rec[mp.o_bd0 + dx * q0 + cy];
+    else if (dy >= 0) v = rec[mp.o_bd0 + dy * q0 + cx];
+    else v = mp.B00[cx * q0 + cy] * scale;
+    B[e] = v;
+    // A: block diagonal stage-1 information (outer products), A21 rows, diagonal A22
+    double a = 0.0;
+    if (x < 2 && y < 2) a = rec[mp.o_bdd + x * D + y];
+    else if (x >= 2 && x < ir && y >= 2 && y < ir) {
+      int jx = -1, jy = -1;
+      for (int j = 0; j < J; ++j) {
+        if (x - 2 >= mp.col_of[j] && x - 2 < mp.col_of[j + 1]) jx = j;
+        if (y - 2 >= mp.col_of[j] && y - 2 < mp.col_of[j + 1]) jy = j;
+      }
+      if (jx == jy) a = mp.B00[(x - 2) * q0 + (y - 2)] * scale;
+    } else if (x >= ir && x < ii) {
+      const int j = x - ir;
+      if (y < 2) a = rec[mp.o_a21snp + 2 * j + y];
+      else if (y < ir && y - 2 >= mp.col_of[j] && y - 2 < mp.col_of[j + 1]) a = rec[mp.o_a21item + (y - 2)];
+      else if (y == x) a = rec[mp.o_a22 + j];
+    } else if (x >= ii) {
+      if (y >= 2 && y < ir) a = mp.A21ii[(x - ii) * n1 + (y - 2)] * scale;
+      else if (y == x) a = mp.B00[(n1 + x - ii) * q0 + (n1 + x - ii)] * scale;
+    }
+    A[e] = a;
+    Ai[e] = x == y ? 1.0 : 0.0;
+  }
+  gsync<LANES>();
+  // ---- Ai = A^-1 by Gauss-Jordan with partial pivoting (A is block lower triangular, well conditioned)
+  bool singular = false;
+  for (int c = 0; c < nt; ++c) {
+    int piv = c;
+    double best = fabs(A[c * nt + c]);
+    for (int r = c + 1; r < nt; ++r)
+      if (fabs(A[r * nt + c]) > best) { best = fabs(A[r * nt + c]); piv = r; }
+    if (!(best > 0.0)) { singular = true; break; }
+    if (piv != c) {
+      for (int k = lane; k < nt; k += LANES) {
+        double t = A[c * nt + k]; A[c * nt + k] = A[piv * nt + k]; A[piv * nt + k] = t;
+        t = Ai[c * nt + k]; Ai[c * nt + k] = Ai[piv * nt + k]; Ai[piv * nt + k] = t;
+      }
+      gsync<LANES>();
+    }
+    const double inv = 1.0 / A[c * nt + c];
+    gsync<LANES>();
+    for (int k = lane; k < nt; k += LANES) { A[c * nt + k] *= inv; Ai[c * nt + k] *= inv; }
+    gsync<LANES>();
+    for (int r = 0; r < nt; ++r) {
+      if (r == c) continue;
+      const double f = A[r * nt + c];
+      gsync<LANES>();  // every lane has read f before column c of row r is overwritten
+      if (f == 0.0) continue;
+      for (int k = lane; k < nt; k += LANES) { A[r * nt + k] -= f * A[c * nt + k]; Ai[r * nt + k] -= f * Ai[c * nt + k]; }
+      gsync<LANES>();
+    }
+  }
+  if (singular) {
+    if (lane == 0) res.catch_code[snp] = GWSEM_CATCH_ACOV_NOT_PD;
+    return;
+  }
+  // T = Ai * B ; A <- acov = T * Ai'
+  for (int e = lane; e < nt * nt; e += LANES) {
+    const int x = e / nt, y = e % nt;
+    double v = 0.0;
+    for (int k = 0; k < nt; ++k) v += Ai[x * nt + k] * B[k * nt + y];
+    T[e] = v;
+  }
+  gsync<LANES>();
+  double* acov = A;
+  for (int e = lane; e < nt * nt; e += LANES) {
+    const int x = e / nt, y = e % nt;
+    double v = 0.0;
+    for (int k = 0; k < nt; ++k) v += T[x * nt + k] * Ai[y * nt + k];
+    acov[e] = v;
+  }
+  gsync<LANES>();
+
+  // ---- statistics and their delta-method rows (<= 3 non-zeros each)
+  double *s = mx + ms.s, *hidx = mx + ms.hidx, *hcoef = mx + ms.hcoef, *L = mx + ms.L, *gscale = mx + ms.scale;
+  const double sd_g = sqrt(var_g);
+  for (int e = lane; e < ns; e += LANES) {
+    const int kind = mp.stat_kind[e], x = mp.stat_theta[e];
+    double i0 = x, c0 = 1.0, i1 = 0, c1 = 0.0, i2 = 0, c2 = 0.0, v = th[x];
+    if (kind == 4) {  // covariance of variables a > b: rho * sd_a * sd_b, sd = 1 for ordinal
+      const int a = mp.stat_a[e], b = mp.stat_b[e];
+      const bool ca = a == 0 || mp.n_cat[a - 1] == 0, cb = b == 0 || mp.n_cat[b - 1] == 0;
+      const double sa = a == 0 ? sd_g : (ca ? mp.item_sd[a - 1] : 1.0), sb = b == 0 ? sd_g : (cb ? mp.item_sd[b - 1] : 1.0);
+      const double rho = th[x];
+      v = rho * sa * sb;
+      c0 = sa * sb;
+      // variance parameter of a continuous variable: snp -> theta 1; item j -> last column of its block
+      if (ca) { i1 = a == 0 ? 1 : 2 + mp.col_of[a] - 1; c1 = rho * sb / (2.0 * sa); }
+      if (cb) { i2 = b == 0 ? 1 : 2 + mp.col_of[b] - 1; c2 = rho * sa / (2.0 * sb); }
+    }
+    s[e] = v;
+    hidx[3 * e] = i0; hidx[3 * e + 1] = i1; hidx[3 * e + 2] = i2;
+    hcoef[3 * e] = c0; hcoef[3 * e + 1] = c1; hcoef[3 * e + 2] = c2;
+  }
+  gsync<LANES>();
+  for (int e = lane; e < ns * ns; e += LANES) {
+    const int x = e / ns, y = e % ns;
+    double v = 0.0;
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b)
+        v += hcoef[3 * x + a] * hcoef[3 * y + b] * acov[(int)hidx[3 * x + a] * nt + (int)hidx[3 * y + b]];
+    L[e] = v;
+  }
+  gsync<LANES>();
+  for (int e = lane; e < ns; e += LANES) gscale[e] = fabs(L[e * ns + e]);
+  gsync<LANES>();
+  for (int e = lane; e < ns * ns; e += LANES) {  // symmetrise before factorising
+    const int x = e / ns, y = e % ns;
+    if (y < x) { const double v = 0.5 * (L[x * ns + y] + L[y * ns + x]); L[x * ns + y] = v; }
+  }
+  gsync<LANES>();
+  for (int e = lane; e < ns * ns; e += LANES) {
+    const int x = e / ns, y = e % ns;
+    if (y > x) L[e] = L[y * ns + x];
+  }
+  gsync<LANES>();
+  if (!warp_cholesky<LANES>(L, ns, lane, gscale)) {
+    if (lane == 0) res.catch_code[snp] = GWSEM_CATCH_ACOV_NOT_PD;
+    return;
+  }
+
+  // ---- damped Gauss-Newton (same schedule as fit.cu / the oracle), numeric Jacobian
+  double *theta = mx + ms.theta, *cand = mx + ms.cand, *sig = mx + ms.sig, *sigp = mx + ms.sigp, *r = mx + ms.r;
+  double *rc = mx + ms.rc, *Jm = mx + ms.J, *g = mx + ms.g, *H = mx + ms.H, *Hc = mx + ms.Hc, *delta = mx + ms.delta;
+  ModelEval<LANES> ev{fp, ws, sm, lane};
+  auto objective = [&](const double* thv, double* resid) -> double {
+    implied_stats(fp, mp, ev, ws, sm, thv, sig, lane);
+    for (int e = lane; e < ns; e += LANES) resid[e] = s[e] - sig[e];
+    gsync<LANES>();
+    warp_forward_solve<LANES>(L, ns, resid, 1, 1, lane);
+    double f = 0.0;
+    for (int e = 0; e < ns; ++e) f += resid[e] * resid[e];
+    return f;
+  };
+  auto jacobian = [&](double* thv) {  // central differences, h = 1e-6 max(1, |theta_k|) as the oracle
+    for (int k = 0; k < P; ++k) {
+      const double t0 = thv[k], h = 1e-6 * fmax(1.0, fabs(t0));
+      gsync<LANES>();
+      if (lane == 0) thv[k] = t0 + h;
+      gsync<LANES>();
+      implied_stats(fp, mp, ev, ws, sm, thv, sigp, lane);
+      if (lane == 0) thv[k] = t0 - h;
+      gsync<LANES>();
+      implied_stats(fp, mp, ev, ws, sm, thv, sig, lane);
+      for (int e = lane; e < ns; e += LANES) Jm[e * P + k] = (sigp[e] - sig[e]) / (2.0 * h);
+      if (lane == 0) thv[k] = t0;
+      gsync<LANES>();
+    }
+  };
+  for (int k = lane; k < P; k += LANES) theta[k] = fp.par_start[k];
+  gsync<LANES>();
+  double F = objective(theta, r);
+  double lam = 1e-4;
+  int status = GWSEM_STATUS_ITERATION_LIMIT;
+  int it = 0;
+  const int max_iter = 200;
+  for (it = 1; it <= max_iter; ++it) {
+    jacobian(theta);
+    warp_forward_solve<LANES>(L, ns, Jm, P, P, lane);
+    for (int k = lane; k < P; k += LANES) {
+      double v = 0.0;
+      for (int e = 0; e < ns; ++e) v += Jm[e * P + k] * r[e];
+      g[k] = v;
+    }
+    for (int idx = lane; idx < P * P; idx += LANES) {
+      const int a = idx / P, b = idx % P;
+      double v = 0.0;
+      for (int e = 0; e < ns; ++e) v += Jm[e * P + a] * Jm[e * P + b];
+      H[idx] = v;
+    }
+    gsync<LANES>();
+    bool improved = false;
+    double Fc = F;
+    for (int attempt = 0; attempt < 30; ++attempt) {
+      for (int idx = lane; idx < P * P; idx += LANES) {
+        const int a = idx / P, b = idx % P;
+        double v = H[idx];
+        if (a == b) v += lam * fmax(H[idx], 1e-12);
+        Hc[idx] = v;
+      }
+      gsync<LANES>();
+      if (!warp_cholesky<LANES>(Hc, P, lane)) { lam *= 10; continue; }
+      if (lane == 0) {
+        for (int i = 0; i < P; ++i) {
+          double v = g[i];
+          for (int k = 0; k < i; ++k) v -= Hc[i * P + k] * delta[k];
+          delta[i] = v / Hc[i * P + i];
+        }
+        for (int i = P - 1; i >= 0; --i) {
+          double v = delta[i];
+          for (int k = i + 1; k < P; ++k) v -= Hc[k * P + i] * delta[k];
+          delta[i] = v / Hc[i * P + i];
+        }
+      }
+      gsync<LANES>();
+      for (int k = lane; k < P; k += LANES) {
+        double c = theta[k] + delta[k];
+        const double lb = fp.par_lbound[k];
+        if (lb == lb && c < lb) c = lb;
+        cand[k] = c;
+      }
+      gsync<LANES>();
+      Fc = objective(cand, rc);
+      if (isfinite(Fc) && Fc <= F) { improved = true; break; }
+      lam *= 10;
+    }
+    if (!improved) {
+      double gmax = 0.0;
+      for (int k = 0; k < P; ++k) gmax = fmax(gmax, fabs(g[k]));
+      status = gmax < 1e-6 * (1 + F) ? GWSEM_STATUS_OK : GWSEM_STATUS_NONZERO_GRADIENT;
+      break;
+    }
+    double step = 0.0;
+    for (int k = 0; k < P; ++k) step = fmax(step, fabs(cand[k] - theta[k]) / (fabs(theta[k]) + 1e-3));
+    const double dF = F - Fc;
+    gsync<LANES>();
+    for (int k = lane; k < P; k += LANES) theta[k] = cand[k];
+    for (int e = lane; e < ns; e += LANES) r[e] = rc[e];
+    gsync<LANES>();
+    F = Fc;
+    lam = fmax(lam / 10, 1e-12);
+    if (step < 1e-10 || dF <= 1e-14 * (1 + F)) { status = GWSEM_STATUS_OK; break; }
+  }
+  if (it > max_iter) it = max_iter;
+
+  jacobian(theta);
+  warp_forward_solve<LANES>(L, ns, Jm, P, P, lane);
+  for (int idx = lane; idx < P * P; idx += LANES) {
+    const int a = idx / P, b = idx % P;
+    double v = 0.0;
+    for (int e = 0; e < ns; ++e) v += Jm[e * P + a] * Jm[e * P + b];
+    H[idx] = v;
+  }
+  gsync<LANES>();
+  if (warp_cholesky<LANES>(H, P, lane)) {
+    for (int c = lane; c < P; c += LANES) {
+      double* x = Hc + c;
+      for (int i = 0; i < P; ++i) {
+        double v = (i == c) ? 1.0 : 0.0;
+        for (int k = 0; k < i; ++k) v -= H[i * P + k] * x[k * P];
+        x[i * P] = v / H[i * P + i];
+      }
+      for (int i = P - 1; i >= 0; --i) {
+        double v = x[i * P];
+        for (int k = i + 1; k < P; ++k) v -= H[k * P + i] * x[k * P];
+        x[i * P] = v / H[i * P + i];
+      }
+    }
+    gsync<LANES>();
+    for (int idx = lane; idx < P * P; idx += LANES) vcov[idx] = Hc[idx];
+  }
+  for (int k = lane; k < P; k += LANES) est[k] = theta[k];
+  if (lane == 0) {
+    res.fit[snp] = F;
+    res.status[snp] = status;
+    res.iterations[snp] = it;
+  }
+}
+
+}  // namespace
+
+size_t marg_fit_scratch_doubles(const FitProgram& fp, const MargProgram& mp) {
+  const int nt = 2 + mp.n1 + mp.J + mp.npii;
+  return (size_t)scratch_layout(fp.p, fp.q, fp.nv, fp.P, 1).total + marg_layout(nt, mp.n_stat, fp.P).total;
+}
+
+void launch_marg_fit(gwsem_engine* e, const FitProgram& fp, const MargProgram& mp, int n_snps, const double* d_summary,
+                     const double* d_maf, const gwsem_result& d_res) {
+  if (n_snps <= 0) return;
+  const size_t per = marg_fit_scratch_doubles(fp, mp) * sizeof(double);
+  int warps = 2;
+  if (per * warps > 220 * 1024) warps = 1;
+  if (per * warps > 227 * 1024) fail("marginals model too large for the per-SNP fit kernel (%zu bytes of scratch)", per);
+  const size_t smem = per * warps;
+  GW_CUDA(cudaFuncSetAttribute(marg_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  e->prof_begin(kFamFit);
+  marg_fit_kernel<<<(n_snps + warps - 1) / warps, warps * 32, smem, e->stream>>>(fp, mp, n_snps, d_summary, d_maf, d_res);
+  GW_CUDA(cudaGetLastError());
+  e->prof_end(kFamFit);
+  e->launches++;
+}
+
+}  // namespace gwsem

@@ -1,0 +1,64 @@
+// WLS "marginals" summary statistics (ordinal items / exogenous covariates), SURVEY.md section 8a
+// row O4.  Host precompute (marginals_host.cpp) + per-SNP kernels (marginals.cu).
+#pragma once
+#include <cstdint>
+#include <utility>
+#include <vector>
+
+namespace gwsem {
+
+constexpr int kMargMaxItems = 8;
+
+struct MargItem {
+  int n_cat = 0;                 // 0 = continuous, else ordinal with codes 0..n_cat-1
+  const double* values = nullptr; // model data rows (codes for ordinal)
+  int n_values = 0;
+  // stage-1 estimates
+  std::vector<double> th;        // ordinal thresholds
+  std::vector<double> beta;      // continuous: intercept + slopes; ordinal: slopes
+  double var = 1.0;              // continuous residual variance (ML)
+  int n_par = 0;                 // ordinal: C-1+K ; continuous: K+2
+  void fit(const std::vector<int>& rows, const std::vector<const double*>& X);
+};
+
+struct MarginalsHost {
+  std::vector<MargItem> items;
+  std::vector<const double*> X;              // exogenous covariates, model data rows
+  // results of build()
+  int n1 = 0, q0 = 0, n_rows_total = 0;
+  std::vector<int> col_of;                   // first stage-1 column of each item
+  std::vector<std::pair<int, int>> pairs;    // item pairs (a > b), column-major lower triangle
+  std::vector<double> rho;                   // per pair
+  std::vector<double> sc0;                   // [row][q0]: stage-1 scores of every item, then pair scores
+  std::vector<double> z1, z0;                // [row][J]: ordinal: standardised thresholds; continuous: z1 = std residual
+  std::vector<double> A21;                   // [pair][n1]
+  std::vector<double> B00;                   // [q0][q0]
+  void build(const std::vector<int>& rows);
+};
+
+// Device-resident program for the per-SNP kernels (plain struct, passed by value).
+struct MargProgram {
+  int J = 0, K = 0, Kp = 0, q0 = 0, q0p = 0, n1 = 0, npii = 0, n_incl = 0;
+  int n_cat[kMargMaxItems] = {0};
+  int col_of[kMargMaxItems + 1] = {0};
+  double item_sd[kMargMaxItems] = {0};       // continuous items: residual sd
+  const double* sc0 = nullptr;               // [n_pad][q0p] file order, zero rows for excluded people
+  const double* z1 = nullptr;                // [n_pad][J]
+  const double* z0 = nullptr;
+  const uint8_t* cat = nullptr;              // [n_pad][J]
+  const double* X = nullptr;                 // [n_pad][Kp]
+  const double* B00 = nullptr;               // [q0][q0]
+  const double* A21ii = nullptr;             // [npii][n1]
+  const double* theta1 = nullptr;            // n1 stage-1 estimates of the items, in column order
+  const double* rho_ii = nullptr;            // npii
+  // statistic vector layout (built on the host): kind 0 mean, 1 threshold, 2 slope, 3 variance, 4 covariance
+  int n_stat = 0;
+  const int32_t* stat_kind = nullptr;
+  const int32_t* stat_a = nullptr;           // manifest variable
+  const int32_t* stat_b = nullptr;           // threshold index / covariate index / second variable
+  const int32_t* stat_theta = nullptr;       // index into theta (snp 2 | items n1 | rho_j0 J | rho_ii)
+  // summary record per SNP (doubles)
+  int sum_stride = 0, o_rho = 0, o_a22 = 0, o_a21snp = 0, o_a21item = 0, o_bdd = 0, o_bd0 = 0;
+};
+
+}  // namespace gwsem

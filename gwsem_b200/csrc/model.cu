@@ -27,7 +27,8 @@ static const T* upload_vec(std::vector<DeviceBuffer<uint8_t>>& pool, const std::
 using namespace gwsem;
 
 gwsem_model::gwsem_model(gwsem_engine* e, const gwsem_model_spec* s) : engine(e) {
-  if (s->fit != 0) fail("only WLS with cumulants summary statistics (fit=0) is implemented on the device so far");
+  if (s->fit != 0 && s->fit != 1) fail("the ML fit function (fit=2) is not implemented on the device yet");
+  fit_kind = s->fit;
   nv = s->n_vars;
   p = s->n_manifest;
   P = s->n_params;
@@ -60,6 +61,34 @@ gwsem_model::gwsem_model(gwsem_engine* e, const gwsem_model_spec* s) : engine(e)
   for (auto& col : base)
     for (int r = 0; r < n_rows; ++r)
       if (!std::isfinite(col[r])) row_ok[r] = 0;
+  if (fit_kind == 1) {
+    if (kind[0] != 1) fail("marginals: the first manifest variable must be the snp column (buildOneFac / buildOneFacRes / buildTwoFac layout)");
+    for (int v = 1; v < p; ++v)
+      if (kind[v] != 0) fail("marginals: gxe product columns are not implemented yet");
+    if (p - 1 > gwsem::kMargMaxItems) fail("marginals: at most %d items", gwsem::kMargMaxItems);
+    n_categories.assign(s->n_categories, s->n_categories + p);
+    exo_latent.assign(s->exo_latent, s->exo_latent + s->n_exo);
+    exo_free.assign(s->exo_free, s->exo_free + (size_t)p * s->n_exo);
+    for (int k = 0; k < s->n_exo; ++k) {
+      exo_cols.emplace_back(s->exo_data[k], s->exo_data[k] + n_rows);
+      for (int r = 0; r < n_rows; ++r)
+        if (!std::isfinite(exo_cols[k][r])) row_ok[r] = 0;
+    }
+    for (int v = 0; v < p; ++v)
+      for (int k = 0; k < s->n_exo; ++k)
+        if (exo_free[(size_t)v * s->n_exo + k] != (v > 0))
+          fail("marginals: every item must be regressed on every exogenous covariate and snp on none");
+    thresholds.assign(s->thresholds, s->thresholds + 4 * (size_t)s->n_thresholds);
+    q = p * (p + 1) / 2;
+    nf = 1;
+    stat_i.clear();
+    stat_j.clear();
+    for (int j = 0; j < p; ++j)
+      for (int i = j; i < p; ++i) { stat_i.push_back(i); stat_j.push_back(j); }
+    idx4.assign(1, -1);
+    feature_monos.assign(1, {});
+    return;
+  }
   // centre the pure phenotype columns (covariances are shift invariant; keeps moments well scaled)
   for (size_t b = 0; b < base.size(); ++b) {
     if (used_as_moderator[b]) continue;
@@ -181,7 +210,7 @@ void gwsem_model::prepare(const int32_t* row_filter, int src_rows) {
   std::vector<std::vector<int>> by_par(P);
   for (int c = 0; c < n_cells; ++c) {
     const double* x = &cells[5 * (size_t)c];
-    if ((int)x[0] == 2) continue;  // means: no mean structure under cumulants
+    if ((int)x[0] == 2 && fit_kind == 0) continue;  // means: no mean structure under cumulants
     const int id = (int)cm.size();
     cm.push_back((int)x[0]); cr.push_back((int)x[1]); cc.push_back((int)x[2]); cp.push_back((int)x[3]); cv.push_back(x[4]);
     if ((int)x[3] >= P) fail("cell refers to parameter %d of %d", (int)x[3], P);
@@ -220,6 +249,7 @@ void gwsem_model::prepare(const int32_t* row_filter, int src_rows) {
   d_feat = upload_vec(pool, feat, st);
   d_featT = upload_vec(pool, featT, st);
   d_dest_of = upload_vec(pool, dest_of, st);
+  if (fit_kind == 1) prepare_marginals(dest_of);
   GW_CUDA(cudaStreamSynchronize(st));
   prepared = true;
 }
@@ -238,6 +268,13 @@ void gwsem_model::fit_2bit_device(const uint8_t* d_packed, int64_t pitch, int n_
     d_nrows.ensure(n);
     d_mafs.ensure(n);
     const uint8_t* rows = d_packed + (int64_t)s0 * pitch;
+    if (fit_kind == 1) {
+      gwsem_result r = d_res;
+      r.est += (size_t)s0 * P; r.vcov += (size_t)s0 * P * P; r.fit += s0; r.maf += s0; r.n_used += s0;
+      r.status += s0; r.catch_code += s0; r.catch_var += s0; r.iterations += s0;
+      run_marginals(rows, pitch, nullptr, nullptr, n, plink1, r);
+      continue;
+    }
     launch_count_missing(engine, rows, pitch, n, plink1, layout, d_featT, nfm, nfm_pad, d_counts.p, d_miss.p);
     launch_class_sums(engine, rows, pitch, n, plink1, layout, d_feat, nfd, d_sums.p);
     gwsem_result r = d_res;
@@ -255,6 +292,13 @@ void gwsem_model::fit_rows_device(const double* d_geno, const double* d_maf, int
   const int kMaxBatch = 1 << 14;
   for (int s0 = 0; s0 < n_snps; s0 += kMaxBatch) {
     const int n = std::min(kMaxBatch, n_snps - s0);
+    if (fit_kind == 1) {
+      gwsem_result r = d_res;
+      r.est += (size_t)s0 * P; r.vcov += (size_t)s0 * P * P; r.fit += s0; r.maf += s0; r.n_used += s0;
+      r.status += s0; r.catch_code += s0; r.catch_var += s0; r.iterations += s0;
+      run_marginals(nullptr, 0, d_geno + (size_t)s0 * n_pad, d_maf + s0, n, 0, r);
+      continue;
+    }
     d_R.ensure(5 * (size_t)nf * n);
     d_nrows.ensure(n);
     launch_power_sums(engine, fp, layout, n, d_geno + (size_t)s0 * n_pad, d_featT, nfm_pad, d_R.p, d_nrows.p);

@@ -5,6 +5,7 @@
 #include "common.h"
 #include "fit_program.h"
 #include "kernels.h"
+#include "marginals.h"
 
 struct gwsem_model {
   gwsem_engine* engine;
@@ -36,6 +37,19 @@ struct gwsem_model {
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   gwsem::DeviceBuffer<double> r_est, r_vcov, r_fit, r_maf;
   gwsem::DeviceBuffer<int32_t> r_n, r_status, r_catch, r_cvar, r_iter;
+
+  // WLS marginals (fit == 1)
+  int fit_kind = 0;
+  std::vector<int32_t> n_categories, exo_latent;
+  std::vector<std::vector<double>> exo_cols;
+  std::vector<uint8_t> exo_free;
+  std::vector<double> thresholds;  // n x 4
+  gwsem::MarginalsHost mh;
+  gwsem::MargProgram mp;
+  gwsem::DeviceBuffer<double> d_summary;
+  void prepare_marginals(const std::vector<int>& dest_of);
+  void run_marginals(const uint8_t* d_packed, int64_t pitch, const double* d_geno, const double* d_maf_in, int n,
+                     int plink1, const gwsem_result& r);
 
   gwsem_model(gwsem_engine* e, const gwsem_model_spec* s);
   void build_program();

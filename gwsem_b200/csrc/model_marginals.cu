@@ -1,0 +1,170 @@
+// Host glue of the WLS "marginals" path: runs the SNP-independent precompute (marginals_host.cpp)
+// on the people that enter the model, lays its results out in genotype-file order on the device,
+// builds the statistic-vector layout shared with oracle/marginals_oracle.py, and sequences the
+// per-batch kernels.
+#include <algorithm>
+#include <cmath>
+
+#include "common.h"
+#include "fit_program.h"
+#include "kernels.h"
+#include "marginals.h"
+#include "model.h"
+
+using namespace gwsem;
+
+namespace {
+template <typename T>
+const T* up(std::vector<DeviceBuffer<uint8_t>>& pool, const std::vector<T>& v, cudaStream_t st) {
+  pool.emplace_back();
+  auto& b = pool.back();
+  b.ensure(std::max<size_t>(v.size() * sizeof(T), 16));
+  if (!v.empty()) GW_CUDA(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+  return reinterpret_cast<const T*>(b.p);
+}
+}  // namespace
+
+void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
+  cudaStream_t st = engine->stream;
+  const int J = p - 1, K = (int)exo_cols.size();
+  std::vector<int> rows;
+  for (int r = 0; r < n_rows; ++r)
+    if (row_ok[r]) rows.push_back(r);
+  mh = MarginalsHost();
+  mh.items.resize(J);
+  for (int j = 0; j < J; ++j) {
+    MargItem& it = mh.items[j];
+    it.n_cat = n_categories[j + 1];
+    it.values = base[var_base[j + 1]].data();
+    it.n_values = n_rows;
+    if (it.n_cat == 1) fail("marginals: item %d has a single category", j + 1);
+    if (it.n_cat > 0)
+      for (int r : rows) {
+        const double c = it.values[r];
+        if (c < 0 || c >= it.n_cat || c != std::floor(c)) fail("marginals: item %d holds a code outside 0..%d", j + 1, it.n_cat - 1);
+      }
+  }
+  for (int k = 0; k < K; ++k) mh.X.push_back(exo_cols[k].data());
+  mh.build(rows);
+
+  mp = MargProgram();
+  mp.J = J; mp.K = K; mp.Kp = std::max(K, 1); mp.q0 = mh.q0; mp.q0p = mh.q0 <= 32 ? 32 : 64;
+  if (mh.q0 > 64) fail("marginals: %d item-side score columns (at most 64 supported)", mh.q0);
+  mp.n1 = mh.n1; mp.npii = (int)mh.pairs.size(); mp.n_incl = n_incl;
+  for (int j = 0; j < J; ++j) {
+    mp.n_cat[j] = mh.items[j].n_cat;
+    mp.item_sd[j] = mh.items[j].n_cat == 0 ? std::sqrt(mh.items[j].var) : 1.0;
+  }
+  for (int j = 0; j <= J; ++j) mp.col_of[j] = mh.col_of[j];
+  // person-major arrays in genotype-file order
+  std::vector<double> sc0((size_t)n_pad * mp.q0p, 0.0), z1((size_t)n_pad * J, 0.0), z0((size_t)n_pad * J, 0.0),
+      X((size_t)n_pad * mp.Kp, 0.0);
+  std::vector<uint8_t> cat((size_t)n_pad * J, 0);
+  for (int s = 0; s < n_src; ++s) {
+    const int r = dest_of[s];
+    if (r < 0 || !row_ok[r]) continue;
+    for (int b = 0; b < mh.q0; ++b) sc0[(size_t)s * mp.q0p + b] = mh.sc0[(size_t)r * mh.q0 + b];
+    for (int j = 0; j < J; ++j) {
+      z1[(size_t)s * J + j] = mh.z1[(size_t)r * J + j];
+      z0[(size_t)s * J + j] = mh.z0[(size_t)r * J + j];
+      if (mh.items[j].n_cat > 0) cat[(size_t)s * J + j] = (uint8_t)mh.items[j].values[r];
+    }
+    for (int k = 0; k < K; ++k) X[(size_t)s * mp.Kp + k] = exo_cols[k][r];
+  }
+  std::vector<double> theta1;
+  for (int j = 0; j < J; ++j) {
+    const MargItem& it = mh.items[j];
+    if (it.n_cat > 0) {
+      theta1.insert(theta1.end(), it.th.begin(), it.th.end());
+      theta1.insert(theta1.end(), it.beta.begin(), it.beta.end());
+    } else {
+      theta1.insert(theta1.end(), it.beta.begin(), it.beta.end());
+      theta1.push_back(it.var);
+    }
+  }
+  // statistic vector: (mean | thresholds per variable), slopes, variances, covariances
+  std::vector<int32_t> kind_, a_, b_, th_, tpar;
+  std::vector<double> tval;
+  auto push = [&](int kd, int a, int b, int th) { kind_.push_back(kd); a_.push_back(a); b_.push_back(b); th_.push_back(th); tpar.push_back(-1); tval.push_back(0.0); };
+  const int ir = 2 + mh.n1, ii = ir + J;
+  push(0, 0, 0, 0);  // snp mean
+  for (int j = 0; j < J; ++j) {
+    const MargItem& it = mh.items[j];
+    if (it.n_cat == 0) push(0, j + 1, 0, 2 + mh.col_of[j]);
+    else
+      for (int c = 0; c + 1 < it.n_cat; ++c) {
+        push(1, j + 1, c, 2 + mh.col_of[j] + c);
+        bool found = false;
+        for (size_t t = 0; t < thresholds.size() / 4; ++t)
+          if ((int)thresholds[4 * t] == j + 1 && (int)thresholds[4 * t + 1] == c) {
+            tpar.back() = (int)thresholds[4 * t + 2];
+            tval.back() = thresholds[4 * t + 3];
+            found = true;
+          }
+        if (!found) fail("marginals: no threshold %d given for ordinal item %d", c + 1, j + 1);
+      }
+  }
+  for (int j = 0; j < J; ++j) {
+    const MargItem& it = mh.items[j];
+    for (int k = 0; k < K; ++k) push(2, j + 1, k, 2 + mh.col_of[j] + (it.n_cat > 0 ? it.n_cat - 1 : 1) + k);
+  }
+  push(3, 0, 0, 1);  // snp variance
+  for (int j = 0; j < J; ++j)
+    if (mh.items[j].n_cat == 0) push(3, j + 1, j + 1, 2 + mh.col_of[j + 1] - 1);
+  for (int b = 0; b < p; ++b)
+    for (int a = b + 1; a < p; ++a) {
+      int th;
+      if (b == 0) th = ir + (a - 1);
+      else {
+        th = -1;
+        for (size_t k = 0; k < mh.pairs.size(); ++k)
+          if (mh.pairs[k].first == a - 1 && mh.pairs[k].second == b - 1) th = ii + (int)k;
+      }
+      push(4, a, b, th);
+    }
+  mp.n_stat = (int)kind_.size();
+  if (mp.n_stat > 128 || 2 + mh.n1 + J + (int)mh.pairs.size() > 128) fail("marginals: model too large");
+  // summary record layout
+  const int D = 2 + J;
+  int o = 3;
+  mp.o_rho = o; o += J;
+  mp.o_a22 = o; o += J;
+  mp.o_a21snp = o; o += 2 * J;
+  mp.o_a21item = o; o += mh.n1;
+  mp.o_bdd = o; o += D * D;
+  mp.o_bd0 = o; o += D * mh.q0;
+  mp.sum_stride = o;
+  mp.sc0 = up(pool, sc0, st);
+  mp.z1 = up(pool, z1, st);
+  mp.z0 = up(pool, z0, st);
+  mp.cat = up(pool, cat, st);
+  mp.X = up(pool, X, st);
+  mp.B00 = up(pool, mh.B00, st);
+  mp.A21ii = up(pool, mh.A21, st);
+  mp.theta1 = up(pool, theta1, st);
+  mp.rho_ii = up(pool, mh.rho, st);
+  mp.stat_kind = up(pool, kind_, st);
+  mp.stat_a = up(pool, a_, st);
+  mp.stat_b = up(pool, b_, st);
+  mp.stat_theta = up(pool, th_, st);
+  fp.thr_par = up(pool, tpar, st);
+  fp.thr_val = up(pool, tval, st);
+  fp.exo_latent = up(pool, exo_latent, st);
+}
+
+void gwsem_model::run_marginals(const uint8_t* d_packed, int64_t pitch, const double* d_geno, const double* d_maf_in,
+                                int n, int plink1, const gwsem_result& r) {
+  d_summary.ensure((size_t)n * mp.sum_stride);
+  const double* maf = d_maf_in;
+  if (!d_geno) {
+    d_counts.ensure(8 * (size_t)n);
+    d_miss.ensure(16);
+    d_mafs.ensure(n);
+    launch_count_missing(engine, d_packed, pitch, n, plink1, layout, d_featT, 0, 1, d_counts.p, d_miss.p);
+    launch_maf_from_counts(engine, d_counts.p, layout.n_kept, n, d_mafs.p);
+    maf = d_mafs.p;
+  }
+  launch_marg_stats(engine, mp, d_packed, pitch, n, n_src, layout.d_inc8, d_geno ? nullptr : d_counts.p, plink1, d_geno,
+                    n_pad, d_summary.p);
+  launch_marg_fit(engine, fp, mp, n, d_summary.p, maf, r);
+}

@@ -95,8 +95,9 @@ class Model:
 
     FIT_CODES = {("WLS", "cumulants"): 0, ("WLS", "marginals"): 1, ("ML", "marginals"): 2, ("ML", "cumulants"): 2}
 
-    def __init__(self, engine, flat, data):
-        """data: {column name: float64 array over the model's rows (after rowFilter)}"""
+    def __init__(self, engine, flat, data, n_categories=None):
+        """data: {column name: float64 array over the model's rows (after rowFilter)}; ordinal items
+        hold 0-based category codes (NaN = missing) and n_categories[name] their number of levels"""
         self.engine, self.flat = engine, flat
         self.names = list(flat["par_names"])
         self.P = len(self.names)
@@ -119,6 +120,21 @@ class Model:
             ptrs[j] = arr.ctypes.data_as(C.POINTER(C.c_double))
         if n_rows is None:
             n_rows = len(next(iter(data.values())))
+        # WLS marginals: ordinal codes, exogenous covariates, thresholds
+        ncat = np.zeros(nm, np.int32)
+        for j, name in enumerate(flat["manifest"]):
+            ncat[j] = int((n_categories or {}).get(name, 0))
+        exo = list(flat["exo_pred"])
+        exo_ptrs = (C.POINTER(C.c_double) * max(len(exo), 1))()
+        for k, name in enumerate(exo):
+            arr = np.ascontiguousarray(np.asarray(data[name], dtype=np.float64))
+            self._keep.append(arr)
+            exo_ptrs[k] = arr.ctypes.data_as(C.POINTER(C.c_double))
+        exo_latent = np.array([nm + flat["latent"].index(c) for c in exo], np.int32)
+        exo_free = np.ascontiguousarray(flat["exo_free"].astype(np.uint8) if flat["exo_free"] is not None
+                                        else np.zeros((nm, 0), np.uint8))
+        thr = np.ascontiguousarray(flat["thresholds"], np.float64)
+        self._keep += [ncat, exo_ptrs, exo_latent, exo_free, thr]
         cells = np.ascontiguousarray(flat["cells"], np.float64)
         start = np.ascontiguousarray(flat["par_start"], np.float64)
         lb = np.ascontiguousarray(flat["par_lbound"], np.float64)
@@ -127,7 +143,11 @@ class Model:
         spec = _lib.ModelSpec(flat["nv"], nm, self.P, len(cells), dp(cells), dp(start), dp(lb),
                               self.FIT_CODES[(flat["fitfun"], flat["continuous_type"])],
                               float(flat["min_variance"]), n_rows,
-                              kinds.ctypes.data_as(C.POINTER(C.c_int32)), ptrs)
+                              kinds.ctypes.data_as(C.POINTER(C.c_int32)), ptrs,
+                              ncat.ctypes.data_as(C.POINTER(C.c_int32)), len(exo), exo_ptrs,
+                              exo_latent.ctypes.data_as(C.POINTER(C.c_int32)),
+                              exo_free.ctypes.data_as(C.POINTER(C.c_uint8)), len(thr),
+                              thr.ctypes.data_as(C.POINTER(C.c_double)))
         self.n_rows = n_rows
         self.h = C.c_void_p()
         check(lib().gwsem_model_create(engine.h, C.byref(spec), C.byref(self.h)))

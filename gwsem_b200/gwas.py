@@ -78,6 +78,24 @@ def buildAnalysesPlan(snpData, sliceSize):
     return pd.DataFrame(rows)
 
 
+def model_columns(model):
+    """Observed columns as float64 (ordinal factors -> 0-based codes, NA -> NaN) and their level counts."""
+    import pandas as pd
+    data, n_categories = {}, {}
+    for c in model.data.columns:
+        col = model.data[c]
+        if c == "snp" or c.startswith("snp_"):
+            continue
+        if isinstance(col.dtype, pd.CategoricalDtype):
+            codes = col.cat.codes.to_numpy().astype(np.float64)
+            codes[codes < 0] = np.nan
+            data[c] = codes
+            n_categories[c] = len(col.cat.categories)
+        elif col.dtype.kind in "fiub":
+            data[c] = col.to_numpy(dtype=np.float64)
+    return data, n_categories
+
+
 def _offdiag(model, names):
     """R/model.R:176-185: off-diagonal vcov entries needed for gxe follow-up (signifGxE)."""
     if not model.gxe:
@@ -121,15 +139,15 @@ def GWAS(model, snpData, out="out.log", *dots, SNP=None, startFrom=1, rowFilter=
     else:
         src_rows = n_rows
     flat = flatten(model)
-    if (flat["fitfun"], flat["continuous_type"]) != ("WLS", "cumulants"):
-        raise NotImplementedError(
-            f"fit function {flat['fitfun']} with {flat['continuous_type']} summary statistics (ordinal items, exogenous "
-            "covariates or ML) is not implemented on the device yet; only WLS/cumulants models run")
+    if flat["fitfun"] != "WLS":
+        raise NotImplementedError("fitfun='ML' is not implemented on the device yet; only WLS models run")
+    if flat["continuous_type"] == "marginals" and (flat["manifest"][0] != "snp" or model.gxe):
+        raise NotImplementedError("WLS marginals is implemented for models whose first manifest variable is snp and "
+                                  "that have no gxe terms (buildOneFac / buildOneFacRes / buildTwoFac)")
     eng = _engine(device)
-    data = {c: model.data[c].to_numpy(dtype=np.float64) for c in model.data.columns
-            if c != "snp" and not c.startswith("snp_") and model.data[c].dtype.kind in "fiu"}
+    data, n_categories = model_columns(model)
     with Source(snpData, method, src_rows) as src:
-        gm = Model(eng, flat, data)
+        gm = Model(eng, flat, data, n_categories)
         try:
             gm.set_row_filter(rowFilter, src_rows)
             names = flat["par_names"]
