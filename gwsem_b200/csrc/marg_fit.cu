@@ -127,7 +127,9 @@ __global__ void __launch_bounds__(64)
     if (lane == 0) { res.catch_code[snp] = GWSEM_CATCH_MIN_VARIANCE; res.catch_var[snp] = 0; }
     return;
   }
-  const double scale = (double)n / (double)mp.n_incl;  // item-only sums were taken over all included people
+  // item-only sums were taken over all included people: outer products are down-dated exactly with the
+  // missing-call people's rows; the item-pair A21 rows (not outer products) by the retained fraction
+  const double scale = (double)n / (double)mp.n_incl;
 
   // ---- theta, A, B.   index map: [0,1] snp | 2.. items | ir = 2+n1 .. rho(snp,item) | ii .. rho(item,item)
   const int ir = 2 + n1, ii = ir + J;
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(64)
     if (dx >= 0 && dy >= 0) v = rec[mp.o_bdd + dx * D + dy];
     else if (dx >= 0) v = rec[mp.o_bd0 + dx * q0 + cy];
     else if (dy >= 0) v = rec[mp.o_bd0 + dy * q0 + cx];
-    else v = mp.B00[cx * q0 + cy] * scale;
+    else v = mp.B00[cx * q0 + cy] - rec[mp.o_mmat + cx * q0 + cy];
     B[e] = v;
     // A: block diagonal stage-1 information (outer products), A21 rows, diagonal A22
     double a = 0.0;
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(64)
         if (x - 2 >= mp.col_of[j] && x - 2 < mp.col_of[j + 1]) jx = j;
         if (y - 2 >= mp.col_of[j] && y - 2 < mp.col_of[j + 1]) jy = j;
       }
-      if (jx == jy) a = mp.B00[(x - 2) * q0 + (y - 2)] * scale;
+      if (jx == jy) a = mp.B00[(x - 2) * q0 + (y - 2)] - rec[mp.o_mmat + (x - 2) * q0 + (y - 2)];
     } else if (x >= ir && x < ii) {
       const int j = x - ir;
       if (y < 2) a = rec[mp.o_a21snp + 2 * j + y];
@@ -170,12 +172,53 @@ __global__ void __launch_bounds__(64)
       else if (y == x) a = rec[mp.o_a22 + j];
     } else if (x >= ii) {
       if (y >= 2 && y < ir) a = mp.A21ii[(x - ii) * n1 + (y - 2)] * scale;
-      else if (y == x) a = mp.B00[(n1 + x - ii) * q0 + (n1 + x - ii)] * scale;
+      else if (y == x) a = mp.B00[(n1 + x - ii) * q0 + (n1 + x - ii)] - rec[mp.o_mmat + (n1 + x - ii) * q0 + (n1 + x - ii)];
     }
     A[e] = a;
     Ai[e] = x == y ? 1.0 : 0.0;
   }
   gsync<LANES>();
+  // ---- missing calls: one Newton step takes the item-side estimates from the full sample to the
+  // retained subset.  The full-sample score vanishes, so the subset score is minus the missing
+  // people's; information in outer-product form (already down-dated in A).
+  if (n < mp.n_incl) {
+    double* dth = T;            // nt: the step, indexed like theta
+    double* blk = T + nt;       // scratch for one stage-1 block
+    for (int e = lane; e < nt; e += LANES) dth[e] = 0.0;
+    gsync<LANES>();
+    for (int j = 0; j < J; ++j) {
+      const int c0 = mp.col_of[j], d = mp.col_of[j + 1] - c0;
+      // exact full-sample information minus the missing people's outer products
+      for (int e = lane; e < d * d; e += LANES)
+        blk[e] = mp.H11[mp.h11_of[j] + e] - rec[mp.o_mmat + (c0 + e / d) * q0 + (c0 + e % d)];
+      gsync<LANES>();
+      if (warp_cholesky<LANES>(blk, d, lane) && lane == 0) {
+        double* x = dth + 2 + c0;
+        for (int i = 0; i < d; ++i) {
+          double v = -rec[mp.o_msum + c0 + i];
+          for (int k = 0; k < i; ++k) v -= blk[i * d + k] * x[k];
+          x[i] = v / blk[i * d + i];
+        }
+        for (int i = d - 1; i >= 0; --i) {
+          double v = x[i];
+          for (int k = i + 1; k < d; ++k) v -= blk[k * d + i] * x[k];
+          x[i] = v / blk[i * d + i];
+        }
+      }
+      gsync<LANES>();
+    }
+    // correlations follow: 0 = score + d score/d rho * step_rho + d score/d theta1 * step_theta1
+    for (int e = lane; e < J + npii; e += LANES) {
+      const int x = ir + e;
+      double v = e < J ? 0.0 : -rec[mp.o_msum + n1 + (e - J)];
+      for (int y = 2; y < ir; ++y) v -= A[x * nt + y] * dth[y];
+      dth[x] = v / A[x * nt + x];
+    }
+    gsync<LANES>();
+    for (int e = lane; e < nt; e += LANES) th[e] += dth[e];
+    gsync<LANES>();
+  }
+
   // ---- Ai = A^-1 by Gauss-Jordan with partial pivoting (A is block lower triangular, well conditioned)
   bool singular = false;
   for (int c = 0; c < nt; ++c) {

@@ -129,6 +129,46 @@ __global__ void __launch_bounds__(kT)
 #pragma unroll
   for (int j = 0; j < J; ++j) ordinal[j] = mp.n_cat[j] > 0;
 
+  // ---- people of the model whose call is missing for this SNP (naAction='omit' drops them from
+  // every statistic): their item-side score rows, summed and as outer products, let marg_fit.cu
+  // down-date the SNP-independent estimates and information to the retained subset.
+  if (n < mp.n_incl) {
+    double* Mm = dyn;                       // [q0p][q0p], row b owned by lane b / b - 32
+    double* msum = dyn + mp.q0p * mp.q0p;   // [q0p]
+    for (int k = tid; k < mp.q0p * mp.q0p + mp.q0p; k += kT) dyn[k] = 0.0;
+    __syncthreads();
+    if (warp == 0) {
+      const int halves = mp.q0p / 32;
+      for (int i0 = 0; i0 < n_src; i0 += 32) {
+        const int i = i0 + lane;
+        bool miss = false;
+        if (i < n_src && inc8[i]) {
+          double u;
+          miss = !std_geno(i, &u);
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, miss);
+        while (todo) {
+          const int src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const int64_t ip = i0 + src;
+          const double lo = mp.sc0[ip * mp.q0p + lane];
+          const double hi = halves > 1 ? mp.sc0[ip * mp.q0p + 32 + lane] : 0.0;
+          msum[lane] += lo;
+          if (halves > 1) msum[32 + lane] += hi;
+          for (int b2 = 0; b2 < mp.q0; ++b2) {
+            const double other = b2 < 32 ? __shfl_sync(0xffffffffu, lo, b2) : __shfl_sync(0xffffffffu, hi, b2 - 32);
+            Mm[lane * mp.q0p + b2] = fma(lo, other, Mm[lane * mp.q0p + b2]);
+            if (halves > 1) Mm[(32 + lane) * mp.q0p + b2] = fma(hi, other, Mm[(32 + lane) * mp.q0p + b2]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    for (int k = tid; k < mp.q0 * mp.q0; k += kT) out[mp.o_mmat + k] = Mm[(k / mp.q0) * mp.q0p + (k % mp.q0)];
+    for (int k = tid; k < mp.q0; k += kT) out[mp.o_msum + k] = msum[k];
+    __syncthreads();
+  }
+
   // ---- stage 2: rho_j <- rho_j + sum(psi) / sum(psi^2) until the score vanishes
   if (tid < J) rho_sh[tid] = 0.0;
   if (tid == 0) done_sh = 0;
@@ -301,7 +341,8 @@ void launch_marg_stats(gwsem_engine* e, const MargProgram& mp, const uint8_t* d_
                        int n_pad, double* d_summary) {
   if (n_snps <= 0) return;
   const int J = mp.J, D = 2 + J;
-  const size_t smem = sizeof(double) * std::max<size_t>((size_t)kT * (D + 2 * J), (size_t)8 * 64 * (D + 1));
+  const size_t smem = sizeof(double) * std::max<size_t>(std::max<size_t>((size_t)kT * (D + 2 * J), (size_t)8 * 64 * (D + 1)),
+                                                         (size_t)mp.q0p * mp.q0p + mp.q0p);
   e->prof_begin(kFamClassSums);
 #define GW_MARG(JJ)                                                                                                  \
   case JJ:                                                                                                           \

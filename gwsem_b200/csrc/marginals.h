@@ -18,6 +18,7 @@ struct MargItem {
   std::vector<double> beta;      // continuous: intercept + slopes; ordinal: slopes
   double var = 1.0;              // continuous residual variance (ML)
   int n_par = 0;                 // ordinal: C-1+K ; continuous: K+2
+  std::vector<double> hess;      // n_par x n_par: minus the exact second derivative of the log-likelihood at the estimate
   void fit(const std::vector<int>& rows, const std::vector<const double*>& X);
 };
 
@@ -51,6 +52,8 @@ struct MargProgram {
   const double* A21ii = nullptr;             // [npii][n1]
   const double* theta1 = nullptr;            // n1 stage-1 estimates of the items, in column order
   const double* rho_ii = nullptr;            // npii
+  const double* H11 = nullptr;               // exact stage-1 information of the items, blocks of n_par^2 back to back
+  int h11_of[kMargMaxItems + 1] = {0};       // offset of each item's block in H11
   // statistic vector layout (built on the host): kind 0 mean, 1 threshold, 2 slope, 3 variance, 4 covariance
   int n_stat = 0;
   const int32_t* stat_kind = nullptr;
@@ -59,6 +62,7 @@ struct MargProgram {
   const int32_t* stat_theta = nullptr;       // index into theta (snp 2 | items n1 | rho_j0 J | rho_ii)
   // summary record per SNP (doubles)
   int sum_stride = 0, o_rho = 0, o_a22 = 0, o_a21snp = 0, o_a21item = 0, o_bdd = 0, o_bd0 = 0;
+  int o_msum = 0, o_mmat = 0;  // missing-call people: sum of their item-side score rows, and of the outer products
 };
 
 }  // namespace gwsem

@@ -126,6 +126,15 @@ void MargItem::fit(const std::vector<int>& rows, const std::vector<const double*
     }
     var = ss / n;
     n_par = K + 2;
+    // exact information of (beta, var) at the MLE: X'X / var, n / (2 var^2); the cross term vanishes
+    hess.assign((size_t)n_par * n_par, 0.0);
+    for (int r : rows) {
+      xi[0] = 1;
+      for (int k = 0; k < K; ++k) xi[k + 1] = X[k][r];
+      for (int a = 0; a < d; ++a)
+        for (int b = 0; b < d; ++b) hess[(size_t)a * n_par + b] += xi[a] * xi[b] / var;
+    }
+    hess[(size_t)(n_par - 1) * n_par + (n_par - 1)] = n / (2 * var * var);
     return;
   }
   // ordered probit, Newton-Raphson with the exact Hessian
@@ -148,6 +157,7 @@ void MargItem::fit(const std::vector<int>& rows, const std::vector<const double*
     }
   }
   std::vector<double> g(d), H(d * d), j1(d), j0(d);
+  bool converged = false;
   for (int it = 0; it < 100; ++it) {
     std::fill(g.begin(), g.end(), 0.0);
     std::fill(H.begin(), H.end(), 0.0);
@@ -173,15 +183,21 @@ void MargItem::fit(const std::vector<int>& rows, const std::vector<const double*
         }
       }
     }
+    if (converged) {  // one more evaluation at the estimate: keep its exact information
+      hess = H;
+      break;
+    }
     std::vector<double> step = g;
-    if (!chol_solve(H, step, d)) fail("ordered probit regression failed (information matrix not positive definite)");
+    std::vector<double> Hc = H;
+    if (!chol_solve(Hc, step, d)) fail("ordered probit regression failed (information matrix not positive definite)");
     double mx = 0;
     for (int a = 0; a < d; ++a) {
       par[a] += step[a];
       mx = std::max(mx, std::fabs(step[a]));
     }
-    if (mx < 1e-12) break;
+    if (mx < 1e-12) converged = true;
   }
+  if (hess.empty()) hess = H;
   th.assign(par.begin(), par.begin() + C - 1);
   beta.assign(par.begin() + C - 1, par.end());
   n_par = d;

@@ -133,6 +133,8 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
   mp.o_a21item = o; o += mh.n1;
   mp.o_bdd = o; o += D * D;
   mp.o_bd0 = o; o += D * mh.q0;
+  mp.o_msum = o; o += mh.q0;
+  mp.o_mmat = o; o += mh.q0 * mh.q0;
   mp.sum_stride = o;
   mp.sc0 = up(pool, sc0, st);
   mp.z1 = up(pool, z1, st);
@@ -143,6 +145,15 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
   mp.A21ii = up(pool, mh.A21, st);
   mp.theta1 = up(pool, theta1, st);
   mp.rho_ii = up(pool, mh.rho, st);
+  {
+    std::vector<double> h11;
+    for (int j = 0; j < J; ++j) {
+      mp.h11_of[j] = (int)h11.size();
+      h11.insert(h11.end(), mh.items[j].hess.begin(), mh.items[j].hess.end());
+    }
+    mp.h11_of[J] = (int)h11.size();
+    mp.H11 = up(pool, h11, st);
+  }
   mp.stat_kind = up(pool, kind_, st);
   mp.stat_a = up(pool, a_, st);
   mp.stat_b = up(pool, b_, st);

@@ -84,3 +84,65 @@ def test_marginals_matches_oracle(engine, case):
     res2 = gm.fit_2bit(synth.pack_2bit(bed), plink1=True)
     assert np.array_equal(res2.est.view(np.uint64), res.est.view(np.uint64))
     gm.close()
+
+
+def test_marginals_with_missing_calls(engine):
+    """Missing calls drop people from every statistic (naAction='omit').  The device path takes the
+    item-side estimates from the full sample to the retained subset with one Newton step (exact
+    full-sample information, outer-product down-date) instead of re-estimating; at 1% missingness
+    that agrees with the oracle's full re-estimation to well under the SE-level tolerance."""
+    import marginals_oracle as mo
+    from gwsem_b200.engine import Model
+    n = 4000
+    ph = cohort(n, 21, 3, 3, [True, True, True])
+    items = ["i1", "i2", "i3"]
+    model = buildOneFac(ph, items, covariates=["pc1", "pc2", "pc3"])
+    flat = flatten(model)
+    data, ncat = model_columns(model)
+    codes = synth.simulate_hardcalls(n, 5, seed=9, maf_range=(0.2, 0.5), missing_rate=0.01)
+    geno = np.array([0.0, 1.0, 2.0, np.nan])[codes]
+    want = [mo.fit_snp_marginals(flat, data, g, ncat) for g in geno]
+    gm = Model(engine, flat, data, ncat)
+    res = gm.fit_2bit(synth.pack_2bit(codes))
+    for i, w in enumerate(want):
+        assert res.n_used[i] == w["n"] and res.catch_code[i] == 0 and res.status[i] == 0
+        se = np.sqrt(np.diag(w["vcov"]))
+        assert np.all(np.abs(res.est[i] - w["est"]) <= 2e-3 * np.maximum(np.abs(w["est"]), se))
+        assert np.allclose(np.sqrt(np.diag(res.vcov[i])), se, rtol=3e-3)
+    gm.close()
+
+
+def test_gwas_ordinal_one_factor_on_fixtures(engine, tmp_path):
+    """C1 shape: buildOneFac with ordinal items and covariates on the bundled example files, through
+    GWAS(): hardcalls (.bed) and dosages (.pgen, the generic double-column path)."""
+    import os
+    import marginals_oracle as mo
+    from conftest import EXTDATA, GOLDEN
+    from gwsem_b200 import GWAS
+    ps = pd.read_csv(os.path.join(EXTDATA, "example.psam"), sep="\t")
+    rng = np.random.default_rng(1)
+    ph = pd.DataFrame({"covar1": rng.normal(size=500), "covar2": rng.normal(size=500)})
+    for k in range(1, 5):
+        ph[f"i{k}"] = ps["phenotype"] * (0.4 + 0.1 * k) + rng.normal(size=500)
+    ph["i1"] = pd.Categorical(pd.qcut(ph["i1"], 3, labels=False), ordered=True)
+    ph["i2"] = pd.Categorical(pd.qcut(ph["i2"], 2, labels=False), ordered=True)
+    items = ["i1", "i2", "i3", "i4"]
+    model = buildOneFac(ph, items, covariates=["covar1", "covar2"])
+    flat = flatten(model)
+    data, ncat = model_columns(model)
+    for fname, gold_name in (("example.bed", "example_bed.npz"), ("example.pgen", "example_pgen.npz")):
+        out = str(tmp_path / "out.log")
+        GWAS(model, os.path.join(EXTDATA, fname), out, SNP=[1, 2, 3, 50, 120])
+        log = pd.read_csv(out, sep="\t", quoting=3, dtype={"catch1": str, "statusCode": str})
+        gold = np.load(os.path.join(GOLDEN, gold_name))
+        for row, snp in zip(log.to_dict("records"), [0, 1, 2, 49, 119]):
+            w = mo.fit_snp_marginals(flat, data, gold["geno"][snp], ncat)
+            if w["catch1"]:
+                assert isinstance(row["catch1"], str) and row["catch1"]
+                continue
+            assert row["statusCode"] == w["status"]
+            se = np.sqrt(np.diag(w["vcov"]))
+            loose = np.isnan(gold["geno"][snp]).any()          # missing calls: one-step down-date
+            for k, nme in enumerate(flat["par_names"]):
+                assert abs(row[nme] - w["est"][k]) <= (5e-2 if loose else 1e-4) * max(abs(w["est"][k]), se[k]), (fname, snp, nme)
+                assert row[f"V{nme}:{nme}"] == pytest.approx(w["vcov"][k, k], rel=5e-2 if loose else 2e-3)
