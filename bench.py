@@ -277,6 +277,13 @@ def run_gpu(args):
     alg_bytes_per_launch = ((N_PEOPLE + 3) // 4) * n_snps * args.steps / max(n_cs, 1)
     achieved = alg_bytes_per_launch / (ms_cs / max(n_cs, 1) / 1e3) / 1e9 if n_cs else None
     d2h = int(sum(getattr(hres, f).nbytes for f, _ in _lib.Result._fields_))
+    traffic = None   # DRAM bytes per launch from the committed ncu --set full capture, scaled to this launch size
+    tpath = os.path.join(ROOT, "profiles", "r01_class_sums_traffic.json")
+    if os.path.exists(tpath) and n_cs:
+        with open(tpath) as f:
+            t = json.load(f)
+        per_snp = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["snps_in_launch"] * (N_PEOPLE / t["n_people"])
+        traffic = per_snp * n_snps * args.steps / n_cs
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -288,7 +295,7 @@ def run_gpu(args):
                 "h2d_bytes_per_step": int(host_packed.numel()), "d2h_bytes_per_step": d2h},
         "gpu_launches": int(gpu_launches),
         "roofline": {"bound": "hbm", "kernel": "class_sums_kernel<8,3,...>", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                      "peak_source": peak_src, "launches_timed": n_cs,
                      "kernel_ms_share": {k: v[1] / ms for k, v in prof.items() if v[0]},
                      "note": "achieved = 25,000 B/SNP of packed genotypes x SNPs per launch / CUDA-event launch time; "

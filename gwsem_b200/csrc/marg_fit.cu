@@ -5,7 +5,7 @@
 //   statistics s = (means | thresholds, slopes, variances, covariances) by the delta method;
 //   a continuous variable contributes sd * rho to a covariance
 //   model-implied vector: RAM moments conditional on the exogenous covariates, ordinal rows
-//   standardised by the implied sd; damped Gauss-Newton with a central-difference Jacobian.
+//   standardised by the implied sd; damped Gauss-Newton with the analytic Jacobian.
 // Mirrors oracle/marginals_oracle.py (fit_snp_marginals).
 #include "common.h"
 #include "fit_device.cuh"
@@ -329,20 +329,58 @@ __global__ void __launch_bounds__(64)
     for (int e = 0; e < ns; ++e) f += resid[e] * resid[e];
     return f;
   };
-  auto jacobian = [&](double* thv) {  // central differences, h = 1e-6 max(1, |theta_k|) as the oracle
-    for (int k = 0; k < P; ++k) {
-      const double t0 = thv[k], h = 1e-6 * fmax(1.0, fabs(t0));
-      gsync<LANES>();
-      if (lane == 0) thv[k] = t0 + h;
-      gsync<LANES>();
-      implied_stats(fp, mp, ev, ws, sm, thv, sigp, lane);
-      if (lane == 0) thv[k] = t0 - h;
-      gsync<LANES>();
-      implied_stats(fp, mp, ev, ws, sm, thv, sig, lane);
-      for (int e = lane; e < ns; e += LANES) Jm[e * P + k] = (sigp[e] - sig[e]) / (2.0 * h);
-      if (lane == 0) thv[k] = t0;
-      gsync<LANES>();
+  // analytic Jacobian of the model-implied statistics (RAM derivatives chained through the
+  // standardisation of ordinal rows); evaluated at thv
+  auto jacobian = [&](double* thv) {
+    implied_stats(fp, mp, ev, ws, sm, thv, sig, lane);
+    const double *Z = sm + ws.Z, *C = sm + ws.C, *muv = sm + ws.T + nv;
+    for (int idx = lane; idx < ns * P; idx += LANES) {
+      const int e = idx / P, k = idx % P;
+      const int kind = mp.stat_kind[e], a = mp.stat_a[e], b = mp.stat_b[e];
+      const bool ord_a = a > 0 && mp.n_cat[a - 1] > 0;
+      const bool ord_b = kind == 4 && b > 0 && mp.n_cat[b - 1] > 0;
+      const int xa = kind == 2 ? fp.exo_latent[b] : 0;
+      double dCaa = 0.0, dCbb = 0.0, dCab = 0.0, dmu = 0.0, dZ = 0.0;
+      for (int ce = fp.par_cell_ptr[k]; ce < fp.par_cell_ptr[k + 1]; ++ce) {
+        const int c_id = fp.par_cells[ce];
+        const int m = fp.cell_mat[c_id], rr = fp.cell_row[c_id], cc = fp.cell_col[c_id];
+        if (m == 0) {
+          dCaa += 2.0 * Z[a * nv + rr] * C[cc * nv + a];
+          dmu += Z[a * nv + rr] * muv[cc];
+          if (kind == 2) dZ += Z[a * nv + rr] * Z[cc * nv + xa];
+          if (kind == 4) {
+            dCbb += 2.0 * Z[b * nv + rr] * C[cc * nv + b];
+            dCab += Z[a * nv + rr] * C[cc * nv + b] + Z[b * nv + rr] * C[cc * nv + a];
+          }
+        } else if (m == 1) {
+          dCaa += Z[a * nv + rr] * Z[a * nv + cc];
+          if (kind == 4) {
+            dCbb += Z[b * nv + rr] * Z[b * nv + cc];
+            dCab += Z[a * nv + rr] * Z[b * nv + cc];
+          }
+        } else {
+          dmu += Z[a * nv + cc];
+        }
+      }
+      const double Caa = C[a * nv + a];
+      const double sda = ord_a ? sqrt(Caa) : 1.0;
+      const double dsa = ord_a ? dCaa / (2.0 * sda * sda * sda) : 0.0;   // -d(1/sd_a)
+      double v;
+      if (kind == 0) v = dmu;
+      else if (kind == 1) {
+        const int par = fp.thr_par[e];
+        const double tau = par >= 0 ? thv[par] : fp.thr_val[e];
+        v = ((par == k ? 1.0 : 0.0) - dmu) / sda - (tau - muv[a]) * dsa;
+      } else if (kind == 2) v = dZ / sda - Z[a * nv + xa] * dsa;
+      else if (kind == 3) v = dCaa;
+      else {
+        const double Cbb = C[b * nv + b], sdb = ord_b ? sqrt(Cbb) : 1.0;
+        const double dsb = ord_b ? dCbb / (2.0 * sdb * sdb * sdb) : 0.0;
+        v = dCab / (sda * sdb) - C[a * nv + b] * (dsa / sdb + dsb / sda);
+      }
+      Jm[idx] = v;
     }
+    gsync<LANES>();
   };
   for (int k = lane; k < P; k += LANES) theta[k] = fp.par_start[k];
   gsync<LANES>();

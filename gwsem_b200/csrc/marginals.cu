@@ -26,27 +26,62 @@ __device__ __forceinline__ double rect_prob(double a1, double a0) {
 
 struct PairTerms {
   double psi;      // d loglik_i / d rho
+  double dpsi;     // d psi / d rho (exact, for Newton)
   double dl_du;    // d loglik2_i / d u (the standardised genotype)
   double dl_a;     // ordinal item: d/dz1 ; continuous item: d/dv
   double dl_b;     // ordinal item: d/dz0
 };
 
-__device__ __forceinline__ PairTerms pair_terms(bool ordinal, double rho, double u, double z1, double z0) {
+// Phi(z) - Phi(z - d) = phi(z) * P(z, d): Taylor in d with Hermite polynomials, |d| <= kTaylorMax
+constexpr double kTaylorMax = 0.125;
+__device__ __forceinline__ double phi_integral_poly(double z, double d) {
+  const double z2 = z * z;
+  double p = (z2 * z2 * z - 10.0 * z2 * z + 15.0 * z) * (1.0 / 720.0);
+  p = fma(p, d, (z2 * z2 - 6.0 * z2 + 3.0) * (1.0 / 120.0));
+  p = fma(p, d, (z2 * z - 3.0 * z) * (1.0 / 24.0));
+  p = fma(p, d, (z2 - 1.0) * (1.0 / 6.0));
+  p = fma(p, d, z * 0.5);
+  p = fma(p, d, 1.0);
+  return p * d;
+}
+
+// zz = {z1, z0, phi(z1), phi(z0), Phi(z1) - Phi(z0)} of the person for an ordinal item (the +-12
+// sentinels of the open categories make their phi vanish), {v, ...} for a continuous item.
+// rho-dependent scalars are hoisted by the caller: inv_s = 1/sqrt(1-rho^2).
+__device__ __forceinline__ PairTerms pair_terms(bool ordinal, double rho, double inv_s, double u, const double* zz) {
   PairTerms t;
   if (ordinal) {
-    const double s2 = 1.0 - rho * rho, s = sqrt(s2);
-    const double a1 = (z1 - rho * u) / s, a0 = (z0 - rho * u) / s;
-    const double f1 = dphi(a1), f0 = dphi(a0);   // the +-12 sentinels make the open ends vanish
-    const double pi = fmax(rect_prob(a1, a0), 1e-300);
-    t.psi = (f1 * (rho * z1 - u) - f0 * (rho * z0 - u)) / (s2 * s * pi);
-    t.dl_a = f1 / (s * pi);
-    t.dl_b = -f0 / (s * pi);
-    t.dl_du = -u - (rho / s) * (f1 - f0) / pi;
+    const double z1 = zz[0], z0 = zz[1];
+    const double a1 = (z1 - rho * u) * inv_s, a0 = (z0 - rho * u) * inv_s;
+    const double d1 = z1 - a1, d0 = z0 - a0;
+    double f1, f0, pi;
+    if (fabs(d1) <= kTaylorMax && fabs(d0) <= kTaylorMax) {
+      // phi(z - d) = phi(z) exp(z d - d^2/2);  Phi(z - d) = Phi(z) - phi(z) P(z, d)
+      f1 = zz[2] * exp(fma(z1, d1, -0.5 * d1 * d1));
+      f0 = zz[3] * exp(fma(z0, d0, -0.5 * d0 * d0));
+      pi = zz[4] - zz[2] * phi_integral_poly(z1, d1) + zz[3] * phi_integral_poly(z0, d0);
+    } else {
+      f1 = dphi(a1);
+      f0 = dphi(a0);
+      pi = rect_prob(a1, a0);
+    }
+    pi = fmax(pi, 1e-300);
+    const double inv_pi = 1.0 / pi, s3 = inv_s * inv_s * inv_s;
+    const double g1 = (rho * z1 - u) * s3, g0 = (rho * z0 - u) * s3;          // d a / d rho
+    const double h1 = z1 * s3 + 3.0 * rho * g1 * inv_s * inv_s, h0 = z0 * s3 + 3.0 * rho * g0 * inv_s * inv_s;
+    t.psi = (f1 * g1 - f0 * g0) * inv_pi;
+    t.dpsi = (f1 * (h1 - a1 * g1 * g1) - f0 * (h0 - a0 * g0 * g0)) * inv_pi - t.psi * t.psi;
+    t.dl_a = f1 * inv_s * inv_pi;
+    t.dl_b = -f0 * inv_s * inv_pi;
+    t.dl_du = -u - rho * inv_s * (f1 - f0) * inv_pi;
   } else {
-    const double v = z1, s2 = 1.0 - rho * rho;
-    t.psi = (rho * s2 + u * v * (1.0 + rho * rho) - rho * (u * u + v * v)) / (s2 * s2);
-    t.dl_du = -(u - rho * v) / s2;
-    t.dl_a = -(v - rho * u) / s2;
+    const double v = zz[0], s2 = 1.0 - rho * rho, is2 = 1.0 / s2;
+    const double num = rho * s2 + u * v * (1.0 + rho * rho) - rho * (u * u + v * v);
+    t.psi = num * is2 * is2;
+    const double dnum = 1.0 - 3.0 * rho * rho + 2.0 * rho * u * v - (u * u + v * v);
+    t.dpsi = dnum * is2 * is2 + 4.0 * rho * num * is2 * is2 * is2;
+    t.dl_du = -(u - rho * v) * is2;
+    t.dl_a = -(v - rho * u) * is2;
     t.dl_b = 0.0;
   }
   return t;
@@ -66,7 +101,7 @@ __device__ __forceinline__ double block_sum(double v, double* red, int tid) {
 
 // DOSAGE = false: hardcalls from the packed 2-bit row (class counts given);
 // DOSAGE = true: genotype column of doubles in file order (NaN = missing), moments taken here.
-template <int J, bool DOSAGE>
+template <int J, bool DOSAGE, int HALVES>
 __global__ void __launch_bounds__(kT)
     marg_stats_kernel(MargProgram mp, const uint8_t* __restrict__ rows, int64_t pitch, int n_src,
                       const uint8_t* __restrict__ inc8, const int32_t* __restrict__ counts, int plink1,
@@ -169,65 +204,74 @@ __global__ void __launch_bounds__(kT)
     __syncthreads();
   }
 
-  // ---- stage 2: rho_j <- rho_j + sum(psi) / sum(psi^2) until the score vanishes
+  // ---- stage 2: Newton on the score of every rho_j (exact second derivative; the outer-product
+  // information stands in when the curvature estimate is not negative)
   if (tid < J) rho_sh[tid] = 0.0;
   if (tid == 0) done_sh = 0;
   __syncthreads();
-  for (int iter = 0; iter < 40; ++iter) {
-    double s1[J], s2[J], rh[J];
+  for (int iter = 0; iter < 30; ++iter) {
+    double s1[J], s2[J], s3[J], rh[J], inv_s[J];
 #pragma unroll
-    for (int j = 0; j < J; ++j) { s1[j] = s2[j] = 0.0; rh[j] = rho_sh[j]; }
+    for (int j = 0; j < J; ++j) { s1[j] = s2[j] = s3[j] = 0.0; rh[j] = rho_sh[j]; inv_s[j] = rsqrt(1.0 - rh[j] * rh[j]); }
     for (int i = tid; i < n_src; i += kT) {
       double u;
       if (!std_geno(i, &u)) continue;
 #pragma unroll
       for (int j = 0; j < J; ++j) {
-        const PairTerms t = pair_terms(ordinal[j], rh[j], u, mp.z1[(int64_t)i * J + j], mp.z0[(int64_t)i * J + j]);
+        const PairTerms t = pair_terms(ordinal[j], rh[j], inv_s[j], u, mp.zz + ((int64_t)i * J + j) * 5);
         s1[j] += t.psi;
-        s2[j] = fma(t.psi, t.psi, s2[j]);
+        s2[j] += t.dpsi;
+        s3[j] = fma(t.psi, t.psi, s3[j]);
       }
     }
     double worst = 0.0;
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-      const double a = block_sum(s1[j], red, tid), b = block_sum(s2[j], red, tid);
-      double step = b > 0.0 ? a / b : 0.0;
+      const double a = block_sum(s1[j], red, tid), b = block_sum(s2[j], red, tid), c = block_sum(s3[j], red, tid);
+      double step = b < 0.0 ? -a / b : (c > 0.0 ? a / c : 0.0);
       step = fmax(-0.5, fmin(0.5, step));
       const double next = fmax(-0.99, fmin(0.99, rh[j] + step));
       worst = fmax(worst, fabs(next - rh[j]));
       if (tid == 0) rho_sh[j] = next;
     }
-    if (tid == 0 && worst < 1e-11) done_sh = 1;
+    if (tid == 0 && worst < 1e-8) done_sh = 1;   // quadratic convergence: the next step would be ~1e-16
     __syncthreads();
     if (done_sh) break;
   }
-  double rh[J];
+  double rh[J], inv_s[J];
 #pragma unroll
-  for (int j = 0; j < J; ++j) rh[j] = rho_sh[j];
+  for (int j = 0; j < J; ++j) { rh[j] = rho_sh[j]; inv_s[j] = rsqrt(1.0 - rh[j] * rh[j]); }
 
   // ---- Gamma pieces.  Phase 1 (thread = person): SNP-dependent score columns D = (mean, var, psi_j)
   // and the chain terms; phase 2 (lane = score column): D' * SC0 and the A21 rows.
   double* Dt = dyn;                    // [kT][D]
   double* DLt = dyn + kT * D;          // [kT][J][2]
+  int* catT = reinterpret_cast<int*>(dyn + kT * (D + 2 * J));  // [kT][J]
   double bdd[D * (D + 1) / 2], a21snp[2 * J];
 #pragma unroll
   for (int k = 0; k < D * (D + 1) / 2; ++k) bdd[k] = 0.0;
 #pragma unroll
   for (int k = 0; k < 2 * J; ++k) a21snp[k] = 0.0;
-  double acc[2][D + 1];  // per lane: columns lane, lane + 32; last slot is the A21 item entry
+  double acc[HALVES][D + 1];  // per lane: columns lane (, lane + 32); last slot is the A21 item entry
 #pragma unroll
-  for (int h = 0; h < 2; ++h)
+  for (int h = 0; h < HALVES; ++h)
 #pragma unroll
     for (int a = 0; a <= D; ++a) acc[h][a] = 0.0;
   // role of this lane's columns: which item's stage-1 block, and which entry of it
-  int col_item[2], col_sub[2];
+  int col_item[HALVES], col_sub[HALVES], col_x[HALVES];   // col_x: covariate read by a slope column, else -1
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
+  for (int h = 0; h < HALVES; ++h) {
     const int b = lane + 32 * h;
     col_item[h] = -1;
     col_sub[h] = 0;
+    col_x[h] = -1;
     for (int j = 0; j < J; ++j)
-      if (b >= mp.col_of[j] && b < mp.col_of[j + 1]) { col_item[h] = j; col_sub[h] = b - mp.col_of[j]; }
+      if (b >= mp.col_of[j] && b < mp.col_of[j + 1]) {
+        col_item[h] = j;
+        col_sub[h] = b - mp.col_of[j];
+        if (mp.n_cat[j] > 0) { if (col_sub[h] >= mp.n_cat[j] - 1) col_x[h] = col_sub[h] - (mp.n_cat[j] - 1); }
+        else if (col_sub[h] >= 1 && col_sub[h] <= mp.K) col_x[h] = col_sub[h] - 1;
+      }
   }
   for (int t0 = 0; t0 < n_src; t0 += kT) {
     const int i = t0 + tid;
@@ -241,10 +285,11 @@ __global__ void __launch_bounds__(kT)
         d[1] = (u * u - 1.0) / (2.0 * var);
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-          const PairTerms t = pair_terms(ordinal[j], rh[j], u, mp.z1[(int64_t)i * J + j], mp.z0[(int64_t)i * J + j]);
+          const PairTerms t = pair_terms(ordinal[j], rh[j], inv_s[j], u, mp.zz + ((int64_t)i * J + j) * 5);
           d[2 + j] = t.psi;
           DLt[(tid * J + j) * 2 + 0] = t.dl_a;
-          DLt[(tid * J + j) * 2 + 1] = t.dl_b;
+          DLt[(tid * J + j) * 2 + 1] = ordinal[j] ? t.dl_b : mp.zz[((int64_t)i * J + j) * 5];
+          catT[tid * J + j] = mp.cat[(int64_t)i * J + j];
           a21snp[2 * j + 0] += t.psi * (-t.dl_du / sd);
           a21snp[2 * j + 1] += t.psi * (-1.0 / (2.0 * var) - t.dl_du * u / (2.0 * var));
         }
@@ -261,36 +306,49 @@ __global__ void __launch_bounds__(kT)
 #pragma unroll
       for (int j = 0; j < J; ++j) DLt[(tid * J + j) * 2] = DLt[(tid * J + j) * 2 + 1] = 0.0;
     __syncthreads();
-    // phase 2: warp w takes people w*32 .. w*32+31 of the tile
-    for (int pp = 0; pp < 32; ++pp) {
-      const int p = warp * 32 + pp;
-      const int ip = t0 + p;
-      if (ip >= n_src) break;
-      const double* dp = Dt + p * D;
-      if (dp[0] == 0.0 && dp[1] == 0.0) continue;   // missing / excluded (warp uniform)
+    // phase 2: warp w takes people w*32 .. w*32+31 of the tile, four at a time so that the
+    // global loads of four score rows are in flight together (rows of missing people have D = 0)
+    for (int pp0 = 0; pp0 < 32; pp0 += 4) {
+      double sc[4][HALVES], xv[4][HALVES];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int b = lane + 32 * h;
-        if (b >= mp.q0p) continue;
-        const double sc = mp.sc0[(int64_t)ip * mp.q0p + b];
+      for (int k = 0; k < 4; ++k) {
+        const int ip = t0 + warp * 32 + pp0 + k;
+        const bool ok = ip < n_src;
 #pragma unroll
-        for (int a = 0; a < D; ++a) acc[h][a] = fma(dp[a], sc, acc[h][a]);
-        const int j = col_item[h];
-        if (j >= 0) {  // d loglik2 / d (stage-1 parameter b of item j) for the pair (snp, item j)
-          const double dla = DLt[(p * J + j) * 2], dlb = DLt[(p * J + j) * 2 + 1];
-          double v;
-          const int sub = col_sub[h];
-          if (mp.n_cat[j] > 0) {
-            const int C = mp.n_cat[j], cat = mp.cat[(int64_t)ip * J + j];
-            if (sub < C - 1) v = (cat == sub ? dla : 0.0) + (cat == sub + 1 ? dlb : 0.0);
-            else v = -mp.X[(int64_t)ip * mp.Kp + (sub - (C - 1))] * (dla + dlb);
-          } else {
-            const double sdj = mp.item_sd[j], vj = mp.z1[(int64_t)ip * J + j];
-            if (sub == 0) v = -dla / sdj;
-            else if (sub <= mp.K) v = -mp.X[(int64_t)ip * mp.Kp + (sub - 1)] * dla / sdj;
-            else v = -1.0 / (2.0 * sdj * sdj) - dla * vj / (2.0 * sdj * sdj);
+        for (int h = 0; h < HALVES; ++h) {
+          const int b = lane + 32 * h;
+          sc[k][h] = ok ? mp.sc0[(int64_t)ip * mp.q0p + b] : 0.0;
+          xv[k][h] = (ok && col_x[h] >= 0) ? mp.X[(int64_t)ip * mp.Kp + col_x[h]] : 0.0;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int p = warp * 32 + pp0 + k;
+        double dpr[D];
+#pragma unroll
+        for (int a = 0; a < D; ++a) dpr[a] = Dt[p * D + a];
+        const double* dp = dpr;
+#pragma unroll
+        for (int h = 0; h < HALVES; ++h) {
+#pragma unroll
+          for (int a = 0; a < D; ++a) acc[h][a] = fma(dp[a], sc[k][h], acc[h][a]);
+          const int j = col_item[h];
+          if (j >= 0) {  // d loglik2 / d (stage-1 parameter of item j) for the pair (snp, item j)
+            const double dla = DLt[(p * J + j) * 2], dlb = DLt[(p * J + j) * 2 + 1];
+            const int sub = col_sub[h];
+            double v;
+            if (mp.n_cat[j] > 0) {
+              const int cat = catT[p * J + j];
+              if (col_x[h] < 0) v = (cat == sub ? dla : 0.0) + (cat == sub + 1 ? dlb : 0.0);
+              else v = -xv[k][h] * (dla + dlb);
+            } else {  // continuous item: dlb carries the standardised residual
+              const double sdj = mp.item_sd[j];
+              if (sub == 0) v = -dla / sdj;
+              else if (col_x[h] >= 0) v = -xv[k][h] * dla / sdj;
+              else v = dla == 0.0 ? 0.0 : -1.0 / (2.0 * sdj * sdj) - dla * dlb / (2.0 * sdj * sdj);
+            }
+            acc[h][D] = fma(dp[2 + j], v, acc[h][D]);
           }
-          acc[h][D] = fma(dp[2 + j], v, acc[h][D]);
         }
       }
     }
@@ -320,11 +378,11 @@ __global__ void __launch_bounds__(kT)
   double* xw = dyn;  // [8][64][D+1]
   __syncthreads();
 #pragma unroll
-  for (int h = 0; h < 2; ++h)
+  for (int h = 0; h < HALVES; ++h)
 #pragma unroll
     for (int a = 0; a <= D; ++a) xw[((warp * 64) + lane + 32 * h) * (D + 1) + a] = acc[h][a];
   __syncthreads();
-  for (int e = tid; e < 64 * (D + 1); e += kT) {
+  for (int e = tid; e < 32 * HALVES * (D + 1); e += kT) {
     const int b = e / (D + 1), a = e % (D + 1);
     if (b >= mp.q0) continue;
     double v = 0.0;
@@ -341,25 +399,28 @@ void launch_marg_stats(gwsem_engine* e, const MargProgram& mp, const uint8_t* d_
                        int n_pad, double* d_summary) {
   if (n_snps <= 0) return;
   const int J = mp.J, D = 2 + J;
-  const size_t smem = sizeof(double) * std::max<size_t>(std::max<size_t>((size_t)kT * (D + 2 * J), (size_t)8 * 64 * (D + 1)),
+  const size_t smem = sizeof(double) * std::max<size_t>(std::max<size_t>((size_t)kT * (D + 3 * J), (size_t)8 * 64 * (D + 1)),
                                                          (size_t)mp.q0p * mp.q0p + mp.q0p);
   e->prof_begin(kFamClassSums);
-#define GW_MARG(JJ)                                                                                                  \
-  case JJ:                                                                                                           \
-    if (d_geno) {                                                                                                    \
-      GW_CUDA(cudaFuncSetAttribute(marg_stats_kernel<JJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      marg_stats_kernel<JJ, true><<<n_snps, kT, smem, e->stream>>>(mp, d_rows, pitch, n_src, d_inc8, d_counts, plink1, \
-                                                                    d_geno, n_pad, d_summary);                       \
-    } else {                                                                                                         \
-      GW_CUDA(cudaFuncSetAttribute(marg_stats_kernel<JJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      marg_stats_kernel<JJ, false><<<n_snps, kT, smem, e->stream>>>(mp, d_rows, pitch, n_src, d_inc8, d_counts, plink1, \
-                                                                     d_geno, n_pad, d_summary);                      \
-    }                                                                                                                \
+#define GW_MARG_L(JJ, DOS, HV)                                                                                      \
+  {                                                                                                                 \
+    GW_CUDA(cudaFuncSetAttribute(marg_stats_kernel<JJ, DOS, HV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    marg_stats_kernel<JJ, DOS, HV><<<n_snps, kT, smem, e->stream>>>(mp, d_rows, pitch, n_src, d_inc8, d_counts, plink1, \
+                                                                     d_geno, n_pad, d_summary);                     \
+  }
+#define GW_MARG(JJ)                                       \
+  case JJ:                                                \
+    if (d_geno) {                                         \
+      if (mp.q0p > 32) GW_MARG_L(JJ, true, 2) else GW_MARG_L(JJ, true, 1) \
+    } else {                                              \
+      if (mp.q0p > 32) GW_MARG_L(JJ, false, 2) else GW_MARG_L(JJ, false, 1) \
+    }                                                     \
     break;
   switch (J) {
     GW_MARG(1) GW_MARG(2) GW_MARG(3) GW_MARG(4) GW_MARG(5) GW_MARG(6) GW_MARG(7) GW_MARG(8)
     default: fail("marginals: %d items (1..%d supported)", J, kMargMaxItems);
   }
+#undef GW_MARG_L
 #undef GW_MARG
   GW_CUDA(cudaGetLastError());
   e->prof_end(kFamClassSums);

@@ -44,8 +44,7 @@ struct MargProgram {
   int col_of[kMargMaxItems + 1] = {0};
   double item_sd[kMargMaxItems] = {0};       // continuous items: residual sd
   const double* sc0 = nullptr;               // [n_pad][q0p] file order, zero rows for excluded people
-  const double* z1 = nullptr;                // [n_pad][J]
-  const double* z0 = nullptr;
+  const double* zz = nullptr;                // [n_pad][J][5]: z1, z0, phi(z1), phi(z0), Phi(z1)-Phi(z0) (continuous: v)
   const uint8_t* cat = nullptr;              // [n_pad][J]
   const double* X = nullptr;                 // [n_pad][Kp]
   const double* B00 = nullptr;               // [q0][q0]

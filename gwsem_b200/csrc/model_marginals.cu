@@ -57,16 +57,22 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
   }
   for (int j = 0; j <= J; ++j) mp.col_of[j] = mh.col_of[j];
   // person-major arrays in genotype-file order
-  std::vector<double> sc0((size_t)n_pad * mp.q0p, 0.0), z1((size_t)n_pad * J, 0.0), z0((size_t)n_pad * J, 0.0),
-      X((size_t)n_pad * mp.Kp, 0.0);
+  std::vector<double> sc0((size_t)n_pad * mp.q0p, 0.0), zz((size_t)n_pad * J * 5, 0.0), X((size_t)n_pad * mp.Kp, 0.0);
   std::vector<uint8_t> cat((size_t)n_pad * J, 0);
   for (int s = 0; s < n_src; ++s) {
     const int r = dest_of[s];
     if (r < 0 || !row_ok[r]) continue;
     for (int b = 0; b < mh.q0; ++b) sc0[(size_t)s * mp.q0p + b] = mh.sc0[(size_t)r * mh.q0 + b];
     for (int j = 0; j < J; ++j) {
-      z1[(size_t)s * J + j] = mh.z1[(size_t)r * J + j];
-      z0[(size_t)s * J + j] = mh.z0[(size_t)r * J + j];
+      double* e = &zz[((size_t)s * J + j) * 5];
+      e[0] = mh.z1[(size_t)r * J + j];
+      e[1] = mh.z0[(size_t)r * J + j];
+      if (mh.items[j].n_cat > 0) {
+        e[2] = 0.3989422804014327 * std::exp(-0.5 * e[0] * e[0]);
+        e[3] = 0.3989422804014327 * std::exp(-0.5 * e[1] * e[1]);
+        e[4] = 0.5 * (std::erfc(-e[0] * 0.7071067811865476) - std::erfc(-e[1] * 0.7071067811865476));
+        if (e[1] > 0) e[4] = 0.5 * (std::erfc(e[1] * 0.7071067811865476) - std::erfc(e[0] * 0.7071067811865476));
+      }
       if (mh.items[j].n_cat > 0) cat[(size_t)s * J + j] = (uint8_t)mh.items[j].values[r];
     }
     for (int k = 0; k < K; ++k) X[(size_t)s * mp.Kp + k] = exo_cols[k][r];
@@ -137,8 +143,7 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
   mp.o_mmat = o; o += mh.q0 * mh.q0;
   mp.sum_stride = o;
   mp.sc0 = up(pool, sc0, st);
-  mp.z1 = up(pool, z1, st);
-  mp.z0 = up(pool, z0, st);
+  mp.zz = up(pool, zz, st);
   mp.cat = up(pool, cat, st);
   mp.X = up(pool, X, st);
   mp.B00 = up(pool, mh.B00, st);

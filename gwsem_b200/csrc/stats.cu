@@ -69,7 +69,7 @@ __device__ __forceinline__ unsigned long long bed_to_plink2(unsigned long long w
 // mbarriers.  All 32 lanes read the same 32-person word of a genotype row (shared-memory
 // broadcast) and pick their own 2 bits; the adds are DFMAs with 0/1 weights.
 template <int S, int F, int WARPS, int TILE, int STAGES, bool PLINK1>
-__global__ void __launch_bounds__(WARPS * 32 + 32)
+__global__ void __launch_bounds__(WARPS * 32 + 32, (S * F <= 24 && WARPS <= 4) ? 3 : 1)
     class_sums_kernel(const uint8_t* __restrict__ packed, int64_t pitch, int n_snps, int n_src,
                       const uint8_t* __restrict__ inc8, const double* __restrict__ feat, int n_pad,
                       int feat_stride_out, double* __restrict__ sums) {
