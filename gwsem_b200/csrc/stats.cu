@@ -267,36 +267,45 @@ __global__ void __launch_bounds__(128)
   double acc[kMaxAcc];
 #pragma unroll
   for (int k = 0; k < kMaxAcc; ++k) acc[k] = 0.0;
-  for (int w0 = 0; w0 < n_words; w0 += 32) {
-    const int wi = w0 + lane;
-    unsigned long long m3 = 0;
-    if (wi < n_words) {
-      unsigned long long w = __ldg(&words[wi]);
-      if (PLINK1) w = bed_to_plink2(w);
-      const unsigned long long inc = incmask[wi];
-      const unsigned long long lo = w & 0x5555555555555555ull, hi = (w >> 1) & 0x5555555555555555ull;
-      c1 += __popcll(lo & ~hi & inc);
-      c2 += __popcll(hi & ~lo & inc);
-      m3 = lo & hi & inc;
-      c3 += __popcll(m3);
-      const unsigned long long rm = rowmask[wi];
-      r1 += __popcll(lo & ~hi & rm);
-      r2 += __popcll(hi & ~lo & rm);
-      r3 += __popcll(lo & hi & rm);
-    }
-    unsigned any = __ballot_sync(0xffffffffu, m3 != 0);
-    while (any) {
-      const int src = __ffs(any) - 1;
-      any &= any - 1;
-      unsigned long long bits = __shfl_sync(0xffffffffu, m3, src);
-      const int person0 = (w0 + src) << 5;
-      while (bits) {
-        const int person = person0 + ((__ffsll((long long)bits) - 1) >> 1);
-        bits &= bits - 1;
-        const double* f = featT + (int64_t)person * n_featm_pad;
+  constexpr int kUnroll = 4;  // 4 independent 8-byte loads per lane in flight
+  for (int wbase = 0; wbase < n_words; wbase += 32 * kUnroll) {
+    unsigned long long wv[kUnroll], iv[kUnroll], rv[kUnroll];
 #pragma unroll
-        for (int k = 0; k < kMaxAcc; ++k)
-          if (lane + 32 * k < n_featm) acc[k] += f[lane + 32 * k];
+    for (int k = 0; k < kUnroll; ++k) {
+      const int wi = wbase + 32 * k + lane;
+      const bool ok = wi < n_words;
+      wv[k] = ok ? __ldg(&words[wi]) : 0ull;
+      iv[k] = ok ? __ldg(&incmask[wi]) : 0ull;
+      rv[k] = ok ? __ldg(&rowmask[wi]) : 0ull;
+    }
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) {
+      const int w0 = wbase + 32 * k;
+      if (w0 >= n_words) break;
+      unsigned long long w = wv[k];
+      if (PLINK1) w = bed_to_plink2(w);
+      const unsigned long long lo = w & 0x5555555555555555ull, hi = (w >> 1) & 0x5555555555555555ull;
+      c1 += __popcll(lo & ~hi & iv[k]);
+      c2 += __popcll(hi & ~lo & iv[k]);
+      const unsigned long long m3 = lo & hi & iv[k];
+      c3 += __popcll(m3);
+      r1 += __popcll(lo & ~hi & rv[k]);
+      r2 += __popcll(hi & ~lo & rv[k]);
+      r3 += __popcll(lo & hi & rv[k]);
+      unsigned any = __ballot_sync(0xffffffffu, m3 != 0);
+      while (any) {
+        const int src = __ffs(any) - 1;
+        any &= any - 1;
+        unsigned long long bits = __shfl_sync(0xffffffffu, m3, src);
+        const int person0 = (w0 + src) << 5;
+        while (bits) {
+          const int person = person0 + ((__ffsll((long long)bits) - 1) >> 1);
+          bits &= bits - 1;
+          const double* f = featT + (int64_t)person * n_featm_pad;
+#pragma unroll
+          for (int q = 0; q < kMaxAcc; ++q)
+            if (lane + 32 * q < n_featm) acc[q] += f[lane + 32 * q];
+        }
       }
     }
   }
