@@ -62,7 +62,7 @@ gwsem_model::gwsem_model(gwsem_engine* e, const gwsem_model_spec* s) : engine(e)
     for (int r = 0; r < n_rows; ++r)
       if (!std::isfinite(col[r])) row_ok[r] = 0;
   if (fit_kind == 1) {
-    if (kind[0] != 1) fail("marginals: the first manifest variable must be the snp column (buildOneFac / buildOneFacRes / buildTwoFac layout)");
+    marg_mode = kind[0] == 1 ? 0 : 1;
     for (int v = 1; v < p; ++v)
       if (kind[v] != 0) fail("marginals: gxe product columns are not implemented yet");
     if (p - 1 > gwsem::kMargMaxItems) fail("marginals: at most %d items", gwsem::kMargMaxItems);
@@ -70,13 +70,23 @@ gwsem_model::gwsem_model(gwsem_engine* e, const gwsem_model_spec* s) : engine(e)
     exo_latent.assign(s->exo_latent, s->exo_latent + s->n_exo);
     exo_free.assign(s->exo_free, s->exo_free + (size_t)p * s->n_exo);
     for (int k = 0; k < s->n_exo; ++k) {
+      if (!s->exo_data[k]) {  // the genotype column as an exogenous predictor (buildItem, ordinal phenotype)
+        if (marg_mode != 1 || snp_exo >= 0) fail("marginals: unexpected exogenous covariate without data");
+        snp_exo = k;
+        exo_cols.emplace_back();
+        continue;
+      }
       exo_cols.emplace_back(s->exo_data[k], s->exo_data[k] + n_rows);
       for (int r = 0; r < n_rows; ++r)
         if (!std::isfinite(exo_cols[k][r])) row_ok[r] = 0;
     }
+    if (marg_mode == 1) {
+      if (kind[0] != 0 || p != 1 || snp_exo < 0 || n_categories[0] < 2)
+        fail("marginals with an exogenous snp is implemented for a single ordinal item (buildItem with an ordered factor)");
+    }
     for (int v = 0; v < p; ++v)
       for (int k = 0; k < s->n_exo; ++k)
-        if (exo_free[(size_t)v * s->n_exo + k] != (v > 0))
+        if (exo_free[(size_t)v * s->n_exo + k] != (marg_mode == 1 || v > 0))
           fail("marginals: every item must be regressed on every exogenous covariate and snp on none");
     thresholds.assign(s->thresholds, s->thresholds + 4 * (size_t)s->n_thresholds);
     q = p * (p + 1) / 2;

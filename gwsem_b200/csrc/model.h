@@ -6,6 +6,7 @@
 #include "fit_program.h"
 #include "kernels.h"
 #include "marginals.h"
+#include "probit.h"
 
 struct gwsem_model {
   gwsem_engine* engine;
@@ -40,6 +41,9 @@ struct gwsem_model {
 
   // WLS marginals (fit == 1)
   int fit_kind = 0;
+  int marg_mode = 0;   // 0: snp is a manifest variable; 1: snp is an exogenous predictor of one ordinal item
+  int snp_exo = -1;    // which exogenous covariate is the genotype column (mode 1)
+  gwsem::ProbitProgram pp;
   std::vector<int32_t> n_categories, exo_latent;
   std::vector<std::vector<double>> exo_cols;
   std::vector<uint8_t> exo_free;

@@ -26,6 +26,70 @@ const T* up(std::vector<DeviceBuffer<uint8_t>>& pool, const std::vector<T>& v, c
 
 void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
   cudaStream_t st = engine->stream;
+  if (marg_mode == 1) {
+    // one ordinal item regressed on snp + covariates: no-SNP probit fit as the Newton start
+    std::vector<int> rows;
+    for (int r = 0; r < n_rows; ++r)
+      if (row_ok[r]) rows.push_back(r);
+    const int C = n_categories[0];
+    MargItem it;
+    it.n_cat = C;
+    it.values = base[var_base[0]].data();
+    it.n_values = n_rows;
+    for (int r : rows) {
+      const double c = it.values[r];
+      if (c < 0 || c >= C || c != std::floor(c)) fail("marginals: the item holds a code outside 0..%d", C - 1);
+    }
+    std::vector<const double*> X;
+    std::vector<int> other;  // exogenous covariates besides the snp
+    for (int k = 0; k < (int)exo_cols.size(); ++k)
+      if (k != snp_exo) { X.push_back(exo_cols[k].data()); other.push_back(k); }
+    it.fit(rows, X);
+    const int K = (int)X.size();
+    pp = ProbitProgram();
+    pp.n_cat = C; pp.K = K; pp.Kp = std::max(K, 1); pp.P = P;
+    std::vector<uint8_t> cat(n_pad, 0);
+    std::vector<double> Xd((size_t)n_pad * pp.Kp, 0.0), theta0;
+    for (int s = 0; s < n_src; ++s) {
+      const int r = dest_of[s];
+      if (r < 0 || !row_ok[r]) continue;
+      cat[s] = (uint8_t)it.values[r];
+      for (int k = 0; k < K; ++k) Xd[(size_t)s * pp.Kp + k] = X[k][r];
+    }
+    theta0.insert(theta0.end(), it.th.begin(), it.th.end());
+    theta0.insert(theta0.end(), it.beta.begin(), it.beta.end());
+    // model parameter -> position in (thresholds, snp slope, covariate slopes); the item's variance must be 1
+    std::vector<int32_t> par_map(P, -1);
+    const int n_cells = (int)cells.size() / 5;
+    for (int c = 0; c < n_cells; ++c) {
+      const double* x = &cells[5 * (size_t)c];
+      const int mat = (int)x[0], rr = (int)x[1], cc = (int)x[2], par = (int)x[3];
+      if (mat == 1 && rr == 0 && cc == 0 && (par >= 0 || x[4] != 1.0)) fail("marginals: the ordinal item's variance must be fixed at 1");
+      if (mat == 0 && par >= 0) {
+        if (rr != 0) fail("marginals: unexpected free path in a single-item model");
+        int which = -1;
+        for (int k = 0; k < (int)exo_latent.size(); ++k)
+          if (exo_latent[k] == cc) which = k;
+        if (which < 0) fail("marginals: free path from a variable that is not an exogenous covariate");
+        if (which == snp_exo) par_map[par] = C - 1;
+        else par_map[par] = C + (int)(std::find(other.begin(), other.end(), which) - other.begin());
+      }
+      if (mat == 2 && par >= 0) fail("marginals: free means are not part of a single ordinal item model");
+    }
+    for (size_t t = 0; t < thresholds.size() / 4; ++t) {
+      const int par = (int)thresholds[4 * t + 2];
+      if (par < 0) fail("marginals: fixed thresholds are not implemented");
+      par_map[par] = (int)thresholds[4 * t + 1];
+    }
+    for (int k = 0; k < P; ++k)
+      if (par_map[k] < 0) fail("marginals: parameter %d is not a threshold or a slope of the item", k);
+    pp.cat = up(pool, cat, st);
+    pp.X = up(pool, Xd, st);
+    pp.theta0 = up(pool, theta0, st);
+    pp.par_map = up(pool, par_map, st);
+    pp.par_start = fp.par_start;
+    return;
+  }
   const int J = p - 1, K = (int)exo_cols.size();
   std::vector<int> rows;
   for (int r = 0; r < n_rows; ++r)
@@ -170,6 +234,19 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
 
 void gwsem_model::run_marginals(const uint8_t* d_packed, int64_t pitch, const double* d_geno, const double* d_maf_in,
                                 int n, int plink1, const gwsem_result& r) {
+  if (marg_mode == 1) {
+    const double* maf1 = d_maf_in;
+    if (!d_geno) {
+      d_counts.ensure(8 * (size_t)n);
+      d_miss.ensure(16);
+      d_mafs.ensure(n);
+      launch_count_missing(engine, d_packed, pitch, n, plink1, layout, d_featT, 0, 1, d_counts.p, d_miss.p);
+      launch_maf_from_counts(engine, d_counts.p, layout.n_kept, n, d_mafs.p);
+      maf1 = d_mafs.p;
+    }
+    launch_probit_snp(engine, pp, d_packed, pitch, n, n_src, layout.d_inc8, plink1, d_geno, n_pad, maf1, r);
+    return;
+  }
   d_summary.ensure((size_t)n * mp.sum_stride);
   const double* maf = d_maf_in;
   if (!d_geno) {

@@ -127,6 +127,8 @@ class Model:
         exo = list(flat["exo_pred"])
         exo_ptrs = (C.POINTER(C.c_double) * max(len(exo), 1))()
         for k, name in enumerate(exo):
+            if name == "snp" and "snp" not in data:
+                continue  # NULL: the genotype column itself (buildItem with an ordered phenotype)
             arr = np.ascontiguousarray(np.asarray(data[name], dtype=np.float64))
             self._keep.append(arr)
             exo_ptrs[k] = arr.ctypes.data_as(C.POINTER(C.c_double))

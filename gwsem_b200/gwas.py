@@ -141,9 +141,12 @@ def GWAS(model, snpData, out="out.log", *dots, SNP=None, startFrom=1, rowFilter=
     flat = flatten(model)
     if flat["fitfun"] != "WLS":
         raise NotImplementedError("fitfun='ML' is not implemented on the device yet; only WLS models run")
-    if flat["continuous_type"] == "marginals" and (flat["manifest"][0] != "snp" or model.gxe):
-        raise NotImplementedError("WLS marginals is implemented for models whose first manifest variable is snp and "
-                                  "that have no gxe terms (buildOneFac / buildOneFacRes / buildTwoFac)")
+    if flat["continuous_type"] == "marginals":
+        snp_exo_item = "snp" in flat["exo_pred"] and len(flat["manifest"]) == 1
+        if model.gxe or not (flat["manifest"][0] == "snp" or snp_exo_item):
+            raise NotImplementedError("WLS marginals is implemented for models whose first manifest variable is snp "
+                                      "(buildOneFac / buildOneFacRes / buildTwoFac) and for buildItem with one "
+                                      "ordered phenotype; gxe terms under marginals are not implemented")
     eng = _engine(device)
     data, n_categories = model_columns(model)
     with Source(snpData, method, src_rows) as src:

@@ -391,7 +391,9 @@ def fit_snp_marginals(flat, pheno_cols, snp, n_cats):
                fit=np.nan, n=0, iterations=0)
     names = flat["manifest"]
     cols = [snp if m == "snp" else pheno_cols[m] for m in names]
-    X = np.column_stack([pheno_cols[c] for c in flat["exo_pred"]]) if flat["exo_pred"] else np.zeros((len(snp), 0))
+    # buildItem with an ordered phenotype: `snp` itself is an exogenous predictor (R/model.R:560-576)
+    X = (np.column_stack([snp if c == "snp" else pheno_cols[c] for c in flat["exo_pred"]])
+         if flat["exo_pred"] else np.zeros((len(snp), 0)))
     keep = np.isfinite(np.column_stack(cols + [X])).all(1)
     cols = [c[keep] for c in cols]
     X = X[keep]
@@ -402,7 +404,11 @@ def fit_snp_marginals(flat, pheno_cols, snp, n_cats):
             out["catch1"] = f"{flat['name']}.data: '{m}' has observed variance less than {flat['min_variance']:g}"
             return out
     exo_free = flat["exo_free"] if flat["exo_free"] is not None else np.zeros((len(names), 0), bool)
-    st = marginals_stats(cols, kinds, [n_cats.get(m, 0) for m in names], X, exo_free)
+    try:
+        st = marginals_stats(cols, kinds, [n_cats.get(m, 0) for m in names], X, exo_free)
+    except np.linalg.LinAlgError:  # a stage-1 regression is not identified (e.g. a constant snp as predictor)
+        out["catch1"] = f"{flat['name']}.data: asymptotic covariance matrix is not positive definite"
+        return out
     n = st["n"]
     try:
         W = n * np.linalg.inv(st["nacov"])

@@ -150,3 +150,81 @@ def test_gwas_ordinal_one_factor_on_fixtures(engine, tmp_path):
             for k, nme in enumerate(flat["par_names"]):
                 assert abs(row[nme] - w["est"][k]) <= est_tol * max(abs(w["est"][k]), se[k]), (fname, snp, nme, n_miss)
                 assert row[f"V{nme}:{nme}"] == pytest.approx(w["vcov"][k, k], rel=var_tol), (fname, snp, nme, n_miss)
+
+
+def item_cohort(n, seed, cuts, n_cov):
+    rng = np.random.default_rng(seed)
+    ph = pd.DataFrame({"sex": rng.integers(0, 2, n).astype(float)})
+    for k in range(1, n_cov):
+        ph[f"pc{k}"] = rng.normal(size=n)
+    ystar = rng.normal(size=n) + 0.3 * ph["sex"].to_numpy() + sum(0.2 * ph[c].to_numpy() for c in ph.columns[1:])
+    ph["anx"] = pd.Categorical(np.searchsorted(cuts, ystar), ordered=True)
+    return ph
+
+
+@pytest.mark.parametrize("cuts,n_cov", [([-0.5, 0.6], 2), ([0.2], 0), ([-1.0, -0.2, 0.4, 1.1], 3)])
+def test_build_item_ordinal_matches_oracle(engine, cuts, n_cov):
+    """buildItem with an ordered phenotype (the README example, case/control when there are two
+    levels): snp is an exogenous predictor, so every SNP re-fits the ordered probit of the item on
+    snp + covariates.  People with a missing call are dropped exactly (no down-date here)."""
+    import marginals_oracle as mo
+    from gwsem_b200.engine import Model
+    from gwsem_b200.model import buildItem
+    n = 1500
+    ph = item_cohort(n, 3, cuts, n_cov)
+    covs = [c for c in ph.columns if c != "anx"][:n_cov] or None
+    model = buildItem(ph[["anx"] + (covs or [])], "anx", covariates=covs)
+    flat = flatten(model)
+    assert flat["continuous_type"] == "marginals" and flat["manifest"] == ["anx"] and flat["exo_pred"][0] == "snp"
+    data, ncat = model_columns(model)
+    codes = synth.simulate_hardcalls(n, 6, seed=5, maf_range=(0.15, 0.5))
+    codes[1, :60] = 3                              # missing calls
+    codes[2] = 0                                   # monomorphic: the probit on a constant snp is not identified
+    codes[4, ::7] = 3
+    geno = np.array([0.0, 1.0, 2.0, np.nan])[codes]
+    want = [mo.fit_snp_marginals(flat, data, g, ncat) for g in geno]
+    assert [bool(w["catch1"]) for w in want] == [False, False, True, False, False, False]
+    gm = Model(engine, flat, data, ncat)
+    res = gm.fit_2bit(synth.pack_2bit(codes))
+    compare(res, want, flat["par_names"])
+    assert np.allclose(res.maf[[0, 3, 5]], [min(g.mean() / 2, 1 - g.mean() / 2) for g in geno[[0, 3, 5]]])
+    bed = np.array([3, 2, 0, 1], np.uint8)[codes]
+    res2 = gm.fit_2bit(synth.pack_2bit(bed), plink1=True)
+    ok = res.catch_code == 0
+    assert np.array_equal(res2.est[ok].view(np.uint64), res.est[ok].view(np.uint64))
+    gm.close()
+
+
+def test_build_item_ordinal_gwas_on_fixtures(engine, tmp_path):
+    """The README's first example through GWAS(): hardcalls (.bed) and dosages (.pgen)."""
+    import os
+    import marginals_oracle as mo
+    from conftest import EXTDATA, GOLDEN
+    from gwsem_b200 import GWAS, loadResults, signif
+    from gwsem_b200.model import buildItem
+    ps = pd.read_csv(os.path.join(EXTDATA, "example.psam"), sep="\t")
+    rng = np.random.default_rng(4)
+    ph = pd.DataFrame({"sex": rng.integers(0, 2, 500).astype(float)})
+    ph["anxiety"] = pd.Categorical(pd.qcut(ps["phenotype"] + rng.normal(size=500), 3, labels=False), ordered=True)
+    model = buildItem(ph, "anxiety", covariates=["sex"])
+    flat = flatten(model)
+    data, ncat = model_columns(model)
+    pick = [1, 2, 3, 50, 120, 199]
+    for fname, gold_name in (("example.bed", "example_bed.npz"), ("example.pgen", "example_pgen.npz")):
+        out = str(tmp_path / "out.log")
+        GWAS(model, os.path.join(EXTDATA, fname), out, SNP=pick)
+        log = pd.read_csv(out, sep="\t", quoting=3, dtype={"catch1": str, "statusCode": str})
+        gold = np.load(os.path.join(GOLDEN, gold_name))
+        assert len(log) == len(pick)
+        for row, snp in zip(log.to_dict("records"), [s - 1 for s in pick]):
+            w = mo.fit_snp_marginals(flat, data, gold["geno"][snp], ncat)
+            if w["catch1"]:
+                assert isinstance(row["catch1"], str) and row["catch1"]
+                continue
+            assert row["statusCode"] == w["status"]
+            se = np.sqrt(np.diag(w["vcov"]))
+            for k, nme in enumerate(flat["par_names"]):
+                assert abs(row[nme] - w["est"][k]) <= EST_RTOL * max(abs(w["est"][k]), se[k]), (fname, snp, nme)
+                assert row[f"V{nme}:{nme}"] == pytest.approx(w["vcov"][k, k], rel=2 * SE_RTOL), (fname, snp, nme)
+        lr = signif(loadResults(out, "snp_to_anxiety"), "snp_to_anxiety")
+        assert np.isfinite(lr["P"]).sum() >= len(pick) - 1
