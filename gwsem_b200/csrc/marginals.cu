@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kT)
                       const uint8_t* __restrict__ inc8, const int32_t* __restrict__ counts, int plink1,
                       const double* __restrict__ geno, int n_pad, double* __restrict__ summary) {
   constexpr int D = 2 + J;
-  extern __shared__ double dyn[];
+  extern __shared__ __align__(16) double dyn[];
   __shared__ double red[kT / 32];
   __shared__ double rho_sh[J];
   __shared__ int done_sh;
@@ -209,19 +209,50 @@ __global__ void __launch_bounds__(kT)
   if (tid < J) rho_sh[tid] = 0.0;
   if (tid == 0) done_sh = 0;
   __syncthreads();
+  // Iteration 0 is at rho = 0, where psi = u r and d psi / d rho = (1 - u^2) q - u^2 r^2 with the
+  // person's generalised residual r = (phi(z0) - phi(z1)) / pi and q = (z1 phi(z1) - z0 phi(z0)) / pi:
+  // no exp, no Phi.  The loop stops once a step is below kNewtonStop (the error left is of the
+  // order of the square of that step); the Gamma pass below evaluates one more Newton step at no
+  // extra cost and applies it.
+  constexpr double kNewtonStop = 3e-4;
   for (int iter = 0; iter < 30; ++iter) {
     double s1[J], s2[J], s3[J], rh[J], inv_s[J];
 #pragma unroll
     for (int j = 0; j < J; ++j) { s1[j] = s2[j] = s3[j] = 0.0; rh[j] = rho_sh[j]; inv_s[j] = rsqrt(1.0 - rh[j] * rh[j]); }
-    for (int i = tid; i < n_src; i += kT) {
-      double u;
-      if (!std_geno(i, &u)) continue;
+    if (iter == 0) {
+      for (int i = tid; i < n_src; i += kT) {
+        double u;
+        if (!std_geno(i, &u)) continue;
 #pragma unroll
-      for (int j = 0; j < J; ++j) {
-        const PairTerms t = pair_terms(ordinal[j], rh[j], inv_s[j], u, mp.zz + ((int64_t)i * J + j) * 5);
-        s1[j] += t.psi;
-        s2[j] += t.dpsi;
-        s3[j] = fma(t.psi, t.psi, s3[j]);
+        for (int j = 0; j < J; ++j) {
+          const double* zz = mp.zz + ((int64_t)i * J + j) * 5;
+          double psi, dpsi;
+          if (ordinal[j]) {
+            const double ip = 1.0 / zz[4];
+            const double r = (zz[3] - zz[2]) * ip, q = (zz[0] * zz[2] - zz[1] * zz[3]) * ip;
+            psi = u * r;
+            dpsi = (1.0 - u * u) * q - psi * psi;
+          } else {
+            const double v = zz[0];
+            psi = u * v;
+            dpsi = 1.0 - (u * u + v * v);
+          }
+          s1[j] += psi;
+          s2[j] += dpsi;
+          s3[j] = fma(psi, psi, s3[j]);
+        }
+      }
+    } else {
+      for (int i = tid; i < n_src; i += kT) {
+        double u;
+        if (!std_geno(i, &u)) continue;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const PairTerms t = pair_terms(ordinal[j], rh[j], inv_s[j], u, mp.zz + ((int64_t)i * J + j) * 5);
+          s1[j] += t.psi;
+          s2[j] += t.dpsi;
+          s3[j] = fma(t.psi, t.psi, s3[j]);
+        }
       }
     }
     double worst = 0.0;
@@ -234,7 +265,7 @@ __global__ void __launch_bounds__(kT)
       worst = fmax(worst, fabs(next - rh[j]));
       if (tid == 0) rho_sh[j] = next;
     }
-    if (tid == 0 && worst < 1e-8) done_sh = 1;   // quadratic convergence: the next step would be ~1e-16
+    if (tid == 0 && iter > 0 && worst < kNewtonStop) done_sh = 1;
     __syncthreads();
     if (done_sh) break;
   }
@@ -242,12 +273,16 @@ __global__ void __launch_bounds__(kT)
 #pragma unroll
   for (int j = 0; j < J; ++j) { rh[j] = rho_sh[j]; inv_s[j] = rsqrt(1.0 - rh[j] * rh[j]); }
 
-  // ---- Gamma pieces.  Phase 1 (thread = person): SNP-dependent score columns D = (mean, var, psi_j)
-  // and the chain terms; phase 2 (lane = score column): D' * SC0 and the A21 rows.
-  double* Dt = dyn;                    // [kT][D]
-  double* DLt = dyn + kT * D;          // [kT][J][2]
-  int* catT = reinterpret_cast<int*>(dyn + kT * (D + 2 * J));  // [kT][J]
-  double bdd[D * (D + 1) / 2], a21snp[2 * J];
+  // ---- Gamma pieces.  Phase 1 (thread = person): the SNP-dependent score columns D = (mean, var,
+  // psi_j), and V[b] = psi_j * d loglik2 / d (stage-1 parameter b of item j), whose column sums are
+  // the A21 rows of the new correlations.  Phase 2 (lane = score column): D' * SC0 and sum V.
+  constexpr int DP = (D + 1) & ~1;                 // Dt row stride (16-byte rows for 128-bit loads)
+  const int vs = mp.n1 | 1;                        // V row stride, odd: conflict-free row writes
+  double* Dt = dyn;                                // [kT][DP]
+  double* Vt = dyn + kT * DP;                      // [kT][vs]
+  double bdd[D * (D + 1) / 2], a21snp[2 * J], ns1[J], ns2[J];  // sums of psi and d psi / d rho, for the closing Newton step
+#pragma unroll
+  for (int j = 0; j < J; ++j) ns1[j] = ns2[j] = 0.0;
 #pragma unroll
   for (int k = 0; k < D * (D + 1) / 2; ++k) bdd[k] = 0.0;
 #pragma unroll
@@ -257,98 +292,81 @@ __global__ void __launch_bounds__(kT)
   for (int h = 0; h < HALVES; ++h)
 #pragma unroll
     for (int a = 0; a <= D; ++a) acc[h][a] = 0.0;
-  // role of this lane's columns: which item's stage-1 block, and which entry of it
-  int col_item[HALVES], col_sub[HALVES], col_x[HALVES];   // col_x: covariate read by a slope column, else -1
-#pragma unroll
-  for (int h = 0; h < HALVES; ++h) {
-    const int b = lane + 32 * h;
-    col_item[h] = -1;
-    col_sub[h] = 0;
-    col_x[h] = -1;
-    for (int j = 0; j < J; ++j)
-      if (b >= mp.col_of[j] && b < mp.col_of[j + 1]) {
-        col_item[h] = j;
-        col_sub[h] = b - mp.col_of[j];
-        if (mp.n_cat[j] > 0) { if (col_sub[h] >= mp.n_cat[j] - 1) col_x[h] = col_sub[h] - (mp.n_cat[j] - 1); }
-        else if (col_sub[h] >= 1 && col_sub[h] <= mp.K) col_x[h] = col_sub[h] - 1;
-      }
-  }
+  const int K = mp.K;
   for (int t0 = 0; t0 < n_src; t0 += kT) {
     const int i = t0 + tid;
     double d[D];
 #pragma unroll
     for (int a = 0; a < D; ++a) d[a] = 0.0;
-    if (i < n_src) {
-      double u;
-      if (std_geno(i, &u)) {
-        d[0] = u / sd;
-        d[1] = (u * u - 1.0) / (2.0 * var);
+    double u;
+    const bool live = i < n_src && std_geno(i, &u);
+    double* vrow = Vt + tid * vs;
+    if (live) {
+      d[0] = u / sd;
+      d[1] = (u * u - 1.0) / (2.0 * var);
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-          const PairTerms t = pair_terms(ordinal[j], rh[j], inv_s[j], u, mp.zz + ((int64_t)i * J + j) * 5);
-          d[2 + j] = t.psi;
-          DLt[(tid * J + j) * 2 + 0] = t.dl_a;
-          DLt[(tid * J + j) * 2 + 1] = ordinal[j] ? t.dl_b : mp.zz[((int64_t)i * J + j) * 5];
-          catT[tid * J + j] = mp.cat[(int64_t)i * J + j];
-          a21snp[2 * j + 0] += t.psi * (-t.dl_du / sd);
-          a21snp[2 * j + 1] += t.psi * (-1.0 / (2.0 * var) - t.dl_du * u / (2.0 * var));
+      for (int j = 0; j < J; ++j) {
+        const double* zz = mp.zz + ((int64_t)i * J + j) * 5;
+        const PairTerms t = pair_terms(ordinal[j], rh[j], inv_s[j], u, zz);
+        d[2 + j] = t.psi;
+        ns1[j] += t.psi;
+        ns2[j] += t.dpsi;
+        a21snp[2 * j + 0] += t.psi * (-t.dl_du / sd);
+        a21snp[2 * j + 1] += t.psi * (-1.0 / (2.0 * var) - t.dl_du * u / (2.0 * var));
+        const double pa = t.psi * t.dl_a, pb = t.psi * t.dl_b;
+        double* vj = vrow + mp.col_of[j];
+        const double* xi = mp.X + (int64_t)i * mp.Kp;
+        if (ordinal[j]) {
+          const int nth = mp.n_cat[j] - 1, cat = mp.cat[(int64_t)i * J + j];
+          for (int c = 0; c < nth; ++c) vj[c] = (cat == c ? pa : 0.0) + (cat == c + 1 ? pb : 0.0);
+          const double ps = -(pa + pb);
+          for (int k = 0; k < K; ++k) vj[nth + k] = xi[k] * ps;
+        } else {  // continuous item: intercept, slopes, variance; zz[0] is the standardised residual
+          const double isd = 1.0 / mp.item_sd[j], ps = -pa * isd;
+          vj[0] = ps;
+          for (int k = 0; k < K; ++k) vj[1 + k] = xi[k] * ps;
+          vj[1 + K] = -(t.psi + pa * zz[0]) * (0.5 * isd * isd);
         }
-        int k = 0;
-#pragma unroll
-        for (int a = 0; a < D; ++a)
-#pragma unroll
-          for (int b = a; b < D; ++b) { bdd[k] = fma(d[a], d[b], bdd[k]); ++k; }
       }
+      int k = 0;
+#pragma unroll
+      for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int b = a; b < D; ++b) { bdd[k] = fma(d[a], d[b], bdd[k]); ++k; }
+    } else {
+      for (int b = 0; b < mp.n1; ++b) vrow[b] = 0.0;
     }
 #pragma unroll
-    for (int a = 0; a < D; ++a) Dt[tid * D + a] = d[a];
-    if (i >= n_src || (d[0] == 0.0 && d[1] == 0.0))
-#pragma unroll
-      for (int j = 0; j < J; ++j) DLt[(tid * J + j) * 2] = DLt[(tid * J + j) * 2 + 1] = 0.0;
+    for (int a = 0; a < D; ++a) Dt[tid * DP + a] = d[a];
+    if (DP > D) Dt[tid * DP + D] = 0.0;
     __syncthreads();
-    // phase 2: warp w takes people w*32 .. w*32+31 of the tile, four at a time so that the
-    // global loads of four score rows are in flight together (rows of missing people have D = 0)
+    // phase 2: warp w takes people w*32 .. w*32+31 of the tile, four at a time so that the global
+    // loads of four score rows are in flight together (SC0 is padded with zero rows to whole tiles;
+    // rows of missing and excluded people have D = 0 and V = 0)
+    const double* scw = mp.sc0 + (int64_t)(t0 + warp * 32) * mp.q0p + lane;
+    const double* dw = Dt + warp * 32 * DP;
+    const double* vw = Vt + warp * 32 * vs + lane;
     for (int pp0 = 0; pp0 < 32; pp0 += 4) {
-      double sc[4][HALVES], xv[4][HALVES];
+      double sc[4][HALVES];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int h = 0; h < HALVES; ++h) sc[k][h] = scw[(pp0 + k) * mp.q0p + 32 * h];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int ip = t0 + warp * 32 + pp0 + k;
-        const bool ok = ip < n_src;
+        const int p = pp0 + k;
+        double dpr[DP];
 #pragma unroll
-        for (int h = 0; h < HALVES; ++h) {
-          const int b = lane + 32 * h;
-          sc[k][h] = ok ? mp.sc0[(int64_t)ip * mp.q0p + b] : 0.0;
-          xv[k][h] = (ok && col_x[h] >= 0) ? mp.X[(int64_t)ip * mp.Kp + col_x[h]] : 0.0;
+        for (int a = 0; a < DP; a += 2) {
+          const double2 two = *reinterpret_cast<const double2*>(dw + p * DP + a);
+          dpr[a] = two.x;
+          dpr[a + 1] = two.y;
         }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int p = warp * 32 + pp0 + k;
-        double dpr[D];
-#pragma unroll
-        for (int a = 0; a < D; ++a) dpr[a] = Dt[p * D + a];
-        const double* dp = dpr;
 #pragma unroll
         for (int h = 0; h < HALVES; ++h) {
 #pragma unroll
-          for (int a = 0; a < D; ++a) acc[h][a] = fma(dp[a], sc[k][h], acc[h][a]);
-          const int j = col_item[h];
-          if (j >= 0) {  // d loglik2 / d (stage-1 parameter of item j) for the pair (snp, item j)
-            const double dla = DLt[(p * J + j) * 2], dlb = DLt[(p * J + j) * 2 + 1];
-            const int sub = col_sub[h];
-            double v;
-            if (mp.n_cat[j] > 0) {
-              const int cat = catT[p * J + j];
-              if (col_x[h] < 0) v = (cat == sub ? dla : 0.0) + (cat == sub + 1 ? dlb : 0.0);
-              else v = -xv[k][h] * (dla + dlb);
-            } else {  // continuous item: dlb carries the standardised residual
-              const double sdj = mp.item_sd[j];
-              if (sub == 0) v = -dla / sdj;
-              else if (col_x[h] >= 0) v = -xv[k][h] * dla / sdj;
-              else v = dla == 0.0 ? 0.0 : -1.0 / (2.0 * sdj * sdj) - dla * dlb / (2.0 * sdj * sdj);
-            }
-            acc[h][D] = fma(dp[2 + j], v, acc[h][D]);
-          }
+          for (int a = 0; a < D; ++a) acc[h][a] = fma(dpr[a], sc[k][h], acc[h][a]);
+          if (lane + 32 * h < mp.n1) acc[h][D] += vw[p * vs + 32 * h];
         }
       }
     }
@@ -358,7 +376,9 @@ __global__ void __launch_bounds__(kT)
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     const double a = block_sum(a21snp[2 * j], red, tid), b = block_sum(a21snp[2 * j + 1], red, tid);
-    if (tid == 0) { out[mp.o_a21snp + 2 * j] = a; out[mp.o_a21snp + 2 * j + 1] = b; out[mp.o_rho + j] = rh[j]; }
+    const double score = block_sum(ns1[j], red, tid), curv = block_sum(ns2[j], red, tid);
+    const double step = curv < 0.0 ? fmax(-kNewtonStop, fmin(kNewtonStop, -score / curv)) : 0.0;
+    if (tid == 0) { out[mp.o_a21snp + 2 * j] = a; out[mp.o_a21snp + 2 * j + 1] = b; out[mp.o_rho + j] = rh[j] + step; }
   }
   {
     int k = 0;
@@ -399,7 +419,7 @@ void launch_marg_stats(gwsem_engine* e, const MargProgram& mp, const uint8_t* d_
                        int n_pad, double* d_summary) {
   if (n_snps <= 0) return;
   const int J = mp.J, D = 2 + J;
-  const size_t smem = sizeof(double) * std::max<size_t>(std::max<size_t>((size_t)kT * (D + 3 * J), (size_t)8 * 64 * (D + 1)),
+  const size_t smem = sizeof(double) * std::max<size_t>(std::max<size_t>((size_t)kT * (((D + 1) & ~1) + (mp.n1 | 1)), (size_t)8 * 64 * (D + 1)),
                                                          (size_t)mp.q0p * mp.q0p + mp.q0p);
   e->prof_begin(kFamClassSums);
 #define GW_MARG_L(JJ, DOS, HV)                                                                                      \

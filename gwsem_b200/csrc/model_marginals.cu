@@ -121,7 +121,8 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
   }
   for (int j = 0; j <= J; ++j) mp.col_of[j] = mh.col_of[j];
   // person-major arrays in genotype-file order
-  std::vector<double> sc0((size_t)n_pad * mp.q0p, 0.0), zz((size_t)n_pad * J * 5, 0.0), X((size_t)n_pad * mp.Kp, 0.0);
+  std::vector<double> sc0((size_t)((n_pad + 255) / 256 * 256) * mp.q0p, 0.0),  // zero rows up to whole 256-person tiles
+       zz((size_t)n_pad * J * 5, 0.0), X((size_t)n_pad * mp.Kp, 0.0);
   std::vector<uint8_t> cat((size_t)n_pad * J, 0);
   for (int s = 0; s < n_src; ++s) {
     const int r = dest_of[s];
