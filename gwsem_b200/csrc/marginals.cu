@@ -24,6 +24,28 @@ __device__ __forceinline__ double rect_prob(double a1, double a0) {
   return a0 > 0.0 ? normcdf(-a0) - normcdf(-a1) : normcdf(a1) - normcdf(a0);
 }
 
+// 1/x to full double precision for normal x: 20-bit hardware estimate + two Newton steps
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  return fma(r, fma(-x, r, 1.0), r);
+}
+// exp(x): Taylor to x^9 when |x| <= 1/4 (truncation below 3e-13 relative), else the library call
+__device__ __forceinline__ double exp_small(double x) {
+  if (fabs(x) > 0.25) return exp(x);
+  double p = 1.0 / 362880.0;
+  p = fma(p, x, 1.0 / 40320.0);
+  p = fma(p, x, 1.0 / 5040.0);
+  p = fma(p, x, 1.0 / 720.0);
+  p = fma(p, x, 1.0 / 120.0);
+  p = fma(p, x, 1.0 / 24.0);
+  p = fma(p, x, 1.0 / 6.0);
+  p = fma(p, x, 0.5);
+  p = fma(p, x, 1.0);
+  return fma(p, x, 1.0);
+}
+
 struct PairTerms {
   double psi;      // d loglik_i / d rho
   double dpsi;     // d psi / d rho (exact, for Newton)
@@ -57,8 +79,9 @@ __device__ __forceinline__ PairTerms pair_terms(bool ordinal, double rho, double
     double f1, f0, pi;
     if (fabs(d1) <= kTaylorMax && fabs(d0) <= kTaylorMax) {
       // phi(z - d) = phi(z) exp(z d - d^2/2);  Phi(z - d) = Phi(z) - phi(z) P(z, d)
-      f1 = zz[2] * exp(fma(z1, d1, -0.5 * d1 * d1));
-      f0 = zz[3] * exp(fma(z0, d0, -0.5 * d0 * d0));
+      // (an open category's bound carries phi = 0 exactly: keep its argument out of the slow path)
+      f1 = zz[2] * exp_small(zz[2] == 0.0 ? 0.0 : fma(z1, d1, -0.5 * d1 * d1));
+      f0 = zz[3] * exp_small(zz[3] == 0.0 ? 0.0 : fma(z0, d0, -0.5 * d0 * d0));
       pi = zz[4] - zz[2] * phi_integral_poly(z1, d1) + zz[3] * phi_integral_poly(z0, d0);
     } else {
       f1 = dphi(a1);
@@ -66,7 +89,7 @@ __device__ __forceinline__ PairTerms pair_terms(bool ordinal, double rho, double
       pi = rect_prob(a1, a0);
     }
     pi = fmax(pi, 1e-300);
-    const double inv_pi = 1.0 / pi, s3 = inv_s * inv_s * inv_s;
+    const double inv_pi = fast_rcp(pi), s3 = inv_s * inv_s * inv_s;
     const double g1 = (rho * z1 - u) * s3, g0 = (rho * z0 - u) * s3;          // d a / d rho
     const double h1 = z1 * s3 + 3.0 * rho * g1 * inv_s * inv_s, h0 = z0 * s3 + 3.0 * rho * g0 * inv_s * inv_s;
     t.psi = (f1 * g1 - f0 * g0) * inv_pi;
@@ -209,12 +232,14 @@ __global__ void __launch_bounds__(kT)
   if (tid < J) rho_sh[tid] = 0.0;
   if (tid == 0) done_sh = 0;
   __syncthreads();
-  // Iteration 0 is at rho = 0, where psi = u r and d psi / d rho = (1 - u^2) q - u^2 r^2 with the
-  // person's generalised residual r = (phi(z0) - phi(z1)) / pi and q = (z1 phi(z1) - z0 phi(z0)) / pi:
-  // no exp, no Phi.  The loop stops once a step is below kNewtonStop (the error left is of the
-  // order of the square of that step); the Gamma pass below evaluates one more Newton step at no
-  // extra cost and applies it.
-  constexpr double kNewtonStop = 3e-4;
+  // Iteration 0 is at rho = 0, where the tetrachoric series gives the score and its first two
+  // derivatives without exp or Phi: with h_k = He_k(u) c_k and the person's
+  // c_k = (He_{k-1}(z0) phi(z0) - He_{k-1}(z1) phi(z1)) / pi (marginals_host side, mp.cc),
+  // psi = h1, psi' = h2 - h1^2, psi'' = h3 - 3 h1 h2 + 2 h1^3.  The root of that quadratic model is
+  // within O(rho^3) of the estimate; when it is below kSeriesMax the loop ends there, otherwise
+  // exact Newton passes follow until a step is below kNewtonStop.  The Gamma pass below evaluates
+  // one more exact Newton step at no extra cost and applies it.
+  constexpr double kNewtonStop = 3e-4, kSeriesMax = 0.04;
   for (int iter = 0; iter < 30; ++iter) {
     double s1[J], s2[J], s3[J], rh[J], inv_s[J];
 #pragma unroll
@@ -223,23 +248,25 @@ __global__ void __launch_bounds__(kT)
       for (int i = tid; i < n_src; i += kT) {
         double u;
         if (!std_geno(i, &u)) continue;
+        const double he2 = u * u - 1.0, he3 = u * (u * u - 3.0);
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-          const double* zz = mp.zz + ((int64_t)i * J + j) * 5;
-          double psi, dpsi;
+          const double* cc = mp.cc + ((int64_t)i * J + j) * 3;
+          double psi, dpsi, d2psi;
           if (ordinal[j]) {
-            const double ip = 1.0 / zz[4];
-            const double r = (zz[3] - zz[2]) * ip, q = (zz[0] * zz[2] - zz[1] * zz[3]) * ip;
-            psi = u * r;
-            dpsi = (1.0 - u * u) * q - psi * psi;
+            const double h1 = u * cc[0], h2 = he2 * cc[1], h3 = he3 * cc[2];
+            psi = h1;
+            dpsi = h2 - h1 * h1;
+            d2psi = h3 + h1 * (2.0 * h1 * h1 - 3.0 * h2);
           } else {
-            const double v = zz[0];
+            const double v = cc[0];
             psi = u * v;
             dpsi = 1.0 - (u * u + v * v);
+            d2psi = 6.0 * psi;
           }
           s1[j] += psi;
           s2[j] += dpsi;
-          s3[j] = fma(psi, psi, s3[j]);
+          s3[j] += d2psi;
         }
       }
     } else {
@@ -259,13 +286,20 @@ __global__ void __launch_bounds__(kT)
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       const double a = block_sum(s1[j], red, tid), b = block_sum(s2[j], red, tid), c = block_sum(s3[j], red, tid);
-      double step = b < 0.0 ? -a / b : (c > 0.0 ? a / c : 0.0);
+      double step;
+      if (iter == 0) {  // root of the quadratic model a + b rho + c rho^2 / 2 nearest to the Newton point
+        step = b < 0.0 ? -a / b : 0.0;
+        const double r1 = step, h = b < 0.0 ? c / (2.0 * b) : 0.0;
+        if (fabs(r1 * h) < 0.25) { step = r1 - h * r1 * r1; step = r1 - h * step * step; step = r1 - h * step * step; }
+      } else {
+        step = b < 0.0 ? -a / b : (c > 0.0 ? a / c : 0.0);
+      }
       step = fmax(-0.5, fmin(0.5, step));
       const double next = fmax(-0.99, fmin(0.99, rh[j] + step));
       worst = fmax(worst, fabs(next - rh[j]));
       if (tid == 0) rho_sh[j] = next;
     }
-    if (tid == 0 && iter > 0 && worst < kNewtonStop) done_sh = 1;
+    if (tid == 0 && worst < (iter == 0 ? kSeriesMax : kNewtonStop)) done_sh = 1;
     __syncthreads();
     if (done_sh) break;
   }
@@ -293,6 +327,7 @@ __global__ void __launch_bounds__(kT)
 #pragma unroll
     for (int a = 0; a <= D; ++a) acc[h][a] = 0.0;
   const int K = mp.K;
+  const double isd = 1.0 / sd, i2v = 1.0 / (2.0 * var);
   for (int t0 = 0; t0 < n_src; t0 += kT) {
     const int i = t0 + tid;
     double d[D];
@@ -302,8 +337,8 @@ __global__ void __launch_bounds__(kT)
     const bool live = i < n_src && std_geno(i, &u);
     double* vrow = Vt + tid * vs;
     if (live) {
-      d[0] = u / sd;
-      d[1] = (u * u - 1.0) / (2.0 * var);
+      d[0] = u * isd;
+        d[1] = (u * u - 1.0) * i2v;
 #pragma unroll
       for (int j = 0; j < J; ++j) {
         const double* zz = mp.zz + ((int64_t)i * J + j) * 5;
@@ -311,8 +346,8 @@ __global__ void __launch_bounds__(kT)
         d[2 + j] = t.psi;
         ns1[j] += t.psi;
         ns2[j] += t.dpsi;
-        a21snp[2 * j + 0] += t.psi * (-t.dl_du / sd);
-        a21snp[2 * j + 1] += t.psi * (-1.0 / (2.0 * var) - t.dl_du * u / (2.0 * var));
+        a21snp[2 * j + 0] -= t.psi * t.dl_du * isd;
+        a21snp[2 * j + 1] -= t.psi * fma(t.dl_du, u, 1.0) * i2v;
         const double pa = t.psi * t.dl_a, pb = t.psi * t.dl_b;
         double* vj = vrow + mp.col_of[j];
         const double* xi = mp.X + (int64_t)i * mp.Kp;
@@ -345,29 +380,33 @@ __global__ void __launch_bounds__(kT)
     // rows of missing and excluded people have D = 0 and V = 0)
     const double* scw = mp.sc0 + (int64_t)(t0 + warp * 32) * mp.q0p + lane;
     const double* dw = Dt + warp * 32 * DP;
-    const double* vw = Vt + warp * 32 * vs + lane;
+    const double* vw = Vt + warp * 32 * vs + lane;   // lanes beyond n1 read neighbouring rows; their sums are not used
+    const int q0p = mp.q0p;
     for (int pp0 = 0; pp0 < 32; pp0 += 4) {
       double sc[4][HALVES];
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < 4; ++k) {
 #pragma unroll
-        for (int h = 0; h < HALVES; ++h) sc[k][h] = scw[(pp0 + k) * mp.q0p + 32 * h];
+        for (int h = 0; h < HALVES; ++h) sc[k][h] = scw[32 * h];
+        scw += q0p;
+      }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int p = pp0 + k;
         double dpr[DP];
 #pragma unroll
         for (int a = 0; a < DP; a += 2) {
-          const double2 two = *reinterpret_cast<const double2*>(dw + p * DP + a);
+          const double2 two = *reinterpret_cast<const double2*>(dw + a);
           dpr[a] = two.x;
           dpr[a + 1] = two.y;
         }
+        dw += DP;
 #pragma unroll
         for (int h = 0; h < HALVES; ++h) {
 #pragma unroll
           for (int a = 0; a < D; ++a) acc[h][a] = fma(dpr[a], sc[k][h], acc[h][a]);
-          if (lane + 32 * h < mp.n1) acc[h][D] += vw[p * vs + 32 * h];
+          acc[h][D] += vw[32 * h];
         }
+        vw += vs;
       }
     }
     __syncthreads();
@@ -419,7 +458,7 @@ void launch_marg_stats(gwsem_engine* e, const MargProgram& mp, const uint8_t* d_
                        int n_pad, double* d_summary) {
   if (n_snps <= 0) return;
   const int J = mp.J, D = 2 + J;
-  const size_t smem = sizeof(double) * std::max<size_t>(std::max<size_t>((size_t)kT * (((D + 1) & ~1) + (mp.n1 | 1)), (size_t)8 * 64 * (D + 1)),
+  const size_t smem = sizeof(double) * std::max<size_t>(std::max<size_t>((size_t)kT * (((D + 1) & ~1) + (mp.n1 | 1)) + 64, (size_t)8 * 64 * (D + 1)),
                                                          (size_t)mp.q0p * mp.q0p + mp.q0p);
   e->prof_begin(kFamClassSums);
 #define GW_MARG_L(JJ, DOS, HV)                                                                                      \

@@ -45,6 +45,7 @@ struct MargProgram {
   double item_sd[kMargMaxItems] = {0};       // continuous items: residual sd
   const double* sc0 = nullptr;               // [n_pad][q0p] file order, zero rows for excluded people
   const double* zz = nullptr;                // [n_pad][J][5]: z1, z0, phi(z1), phi(z0), Phi(z1)-Phi(z0) (continuous: v)
+  const double* cc = nullptr;                // [n_pad][J][3]: tetrachoric-series coefficients c1..c3 (continuous: v)
   const uint8_t* cat = nullptr;              // [n_pad][J]
   const double* X = nullptr;                 // [n_pad][Kp]
   const double* B00 = nullptr;               // [q0][q0]

@@ -122,7 +122,7 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
   for (int j = 0; j <= J; ++j) mp.col_of[j] = mh.col_of[j];
   // person-major arrays in genotype-file order
   std::vector<double> sc0((size_t)((n_pad + 255) / 256 * 256) * mp.q0p, 0.0),  // zero rows up to whole 256-person tiles
-       zz((size_t)n_pad * J * 5, 0.0), X((size_t)n_pad * mp.Kp, 0.0);
+       zz((size_t)n_pad * J * 5, 0.0), cc((size_t)n_pad * J * 3, 0.0), X((size_t)n_pad * mp.Kp, 0.0);
   std::vector<uint8_t> cat((size_t)n_pad * J, 0);
   for (int s = 0; s < n_src; ++s) {
     const int r = dest_of[s];
@@ -137,6 +137,14 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
         e[3] = 0.3989422804014327 * std::exp(-0.5 * e[1] * e[1]);
         e[4] = 0.5 * (std::erfc(-e[0] * 0.7071067811865476) - std::erfc(-e[1] * 0.7071067811865476));
         if (e[1] > 0) e[4] = 0.5 * (std::erfc(e[1] * 0.7071067811865476) - std::erfc(e[0] * 0.7071067811865476));
+        if (e[0] >= 12.0) e[2] = 0.0;   // open categories: the sentinel bound carries no density
+        if (e[1] <= -12.0) e[3] = 0.0;
+        double* c = &cc[((size_t)s * J + j) * 3];
+        c[0] = (e[3] - e[2]) / e[4];
+        c[1] = (e[1] * e[3] - e[0] * e[2]) / e[4];
+        c[2] = ((e[1] * e[1] - 1.0) * e[3] - (e[0] * e[0] - 1.0) * e[2]) / e[4];
+      } else {
+        cc[((size_t)s * J + j) * 3] = e[0];
       }
       if (mh.items[j].n_cat > 0) cat[(size_t)s * J + j] = (uint8_t)mh.items[j].values[r];
     }
@@ -209,6 +217,7 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
   mp.sum_stride = o;
   mp.sc0 = up(pool, sc0, st);
   mp.zz = up(pool, zz, st);
+  mp.cc = up(pool, cc, st);
   mp.cat = up(pool, cat, st);
   mp.X = up(pool, X, st);
   mp.B00 = up(pool, mh.B00, st);
