@@ -42,7 +42,7 @@ __host__ __device__ inline WarpScratch scratch_layout(int p, int q, int nv, int 
 // A group of LANES threads (1 or 32) works on one SNP.
 template <int LANES>
 __device__ __forceinline__ void gsync() {
-  if (LANES > 1) gsync<LANES>();
+  if (LANES > 1) __syncwarp();
 }
 template <int LANES>
 __device__ __forceinline__ double gbcast(double v) {

@@ -29,6 +29,7 @@ struct FitProgram {
   const int32_t* par_cells = nullptr;
   const double* par_start = nullptr;
   const double* par_lbound = nullptr;
+  const double* par_warm = nullptr;  // marginals: estimates of a reference SNP, the iteration's starting point (else par_start)
   // marginals only: per statistic, the free threshold parameter (or -1 and its fixed value);
   // RAM index of each exogenous covariate's latent variable
   const int32_t* thr_par = nullptr;

@@ -26,15 +26,18 @@ __host__ __device__ inline MargScratch marg_layout(int nt, int ns, int P) {
   MargScratch m;
   int o = 0;
   auto take = [&](int n) { int at = o; o += n; return at; };
+  // Four large regions, each used twice: first for Muthen's A^-1 B A^-T, then by the fit.
+  //   A  -> acov -> Hc      B -> L (factor of the statistics' covariance)
+  //   Ai -> J               T -> H
+  auto big = [](int a, int b) { return a > b ? a : b; };
   m.th = take(nt);
-  m.A = take(nt * nt);
-  m.B = take(nt * nt);
-  m.Ai = take(nt * nt);
-  m.T = take(nt * nt);
+  m.A = m.Hc = take(big(nt * nt, P * P));
+  m.B = m.L = take(big(nt * nt, ns * ns));
+  m.Ai = m.J = take(big(nt * nt, ns * P));
+  m.T = m.H = take(big(nt * nt, P * P));
   m.s = take(ns);
   m.hidx = take(3 * ns);   // stored as doubles for simplicity
   m.hcoef = take(3 * ns);
-  m.L = take(ns * ns);
   m.scale = take(ns);
   m.theta = take(P);
   m.cand = take(P);
@@ -42,10 +45,7 @@ __host__ __device__ inline MargScratch marg_layout(int nt, int ns, int P) {
   m.sigp = take(ns);
   m.r = take(ns);
   m.rc = take(ns);
-  m.J = take(ns * P);
   m.g = take(P);
-  m.H = take(P * P);
-  m.Hc = take(P * P);
   m.delta = take(P);
   m.total = o;
   return m;
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(64)
     }
     gsync<LANES>();
   };
-  for (int k = lane; k < P; k += LANES) theta[k] = fp.par_start[k];
+  for (int k = lane; k < P; k += LANES) theta[k] = fp.par_warm ? fp.par_warm[k] : fp.par_start[k];
   gsync<LANES>();
   double F = objective(theta, r);
   double lam = 1e-4;
@@ -503,8 +503,7 @@ void launch_marg_fit(gwsem_engine* e, const FitProgram& fp, const MargProgram& m
                      const double* d_maf, const gwsem_result& d_res) {
   if (n_snps <= 0) return;
   const size_t per = marg_fit_scratch_doubles(fp, mp) * sizeof(double);
-  int warps = 2;
-  if (per * warps > 220 * 1024) warps = 1;
+  int warps = 1;
   if (per * warps > 227 * 1024) fail("marginals model too large for the per-SNP fit kernel (%zu bytes of scratch)", per);
   const size_t smem = per * warps;
   GW_CUDA(cudaFuncSetAttribute(marg_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -240,6 +240,33 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
   fp.thr_par = up(pool, tpar, st);
   fp.thr_val = up(pool, tval, st);
   fp.exo_latent = up(pool, exo_latent, st);
+
+  // Warm start.  The reference restarts every SNP from the model's start values so that a row does
+  // not depend on its neighbours (R/model.R:188); the same holds here with a start that is fixed
+  // per model: the estimates for a reference genotype column (codes 0,1,2,0,1,2,... down the file,
+  // unrelated to everybody's phenotype), fitted once from the model's own start values.  The item
+  // side of the solution barely moves between SNPs, so the per-SNP iteration starts next to it.
+  {
+    const int64_t rb = (n_pad / 4 + 15) / 16 * 16;
+    std::vector<uint8_t> ref(rb, 0);
+    for (int i = 0; i < n_src; ++i) ref[i >> 2] |= (uint8_t)((i % 3) << (2 * (i & 3)));
+    const uint8_t* d_ref = up(pool, ref, st);
+    DeviceBuffer<double> dd;
+    DeviceBuffer<int32_t> di;
+    dd.ensure((size_t)P + (size_t)P * P + 2);
+    di.ensure(5);
+    gwsem_result r;
+    r.est = dd.p; r.vcov = dd.p + P; r.fit = dd.p + P + (size_t)P * P; r.maf = r.fit + 1;
+    r.n_used = di.p; r.status = di.p + 1; r.catch_code = di.p + 2; r.catch_var = di.p + 3; r.iterations = di.p + 4;
+    fp.par_warm = nullptr;
+    run_marginals(d_ref, rb, nullptr, nullptr, 1, 0, r);
+    int32_t flags[5];
+    std::vector<double> warm(P);
+    GW_CUDA(cudaMemcpyAsync(flags, di.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    GW_CUDA(cudaMemcpyAsync(warm.data(), dd.p, P * sizeof(double), cudaMemcpyDeviceToHost, st));
+    GW_CUDA(cudaStreamSynchronize(st));
+    if (flags[1] == GWSEM_STATUS_OK && flags[2] == GWSEM_CATCH_NONE) fp.par_warm = up(pool, warm, st);
+  }
 }
 
 void gwsem_model::run_marginals(const uint8_t* d_packed, int64_t pitch, const double* d_geno, const double* d_maf_in,
