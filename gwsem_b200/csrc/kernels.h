@@ -52,6 +52,8 @@ void launch_marg_stats(gwsem_engine* e, const MargProgram& mp, const uint8_t* d_
                        int n_src, const uint8_t* d_inc8, const int32_t* d_counts, int plink1, const double* d_geno,
                        int n_pad, double* d_summary);
 void launch_maf_from_counts(gwsem_engine* e, const int32_t* d_counts, int n_kept, int n_snps, double* d_maf);
+// Jacobian of the model-implied statistics at two generic points (d_out[2][n_stat][P]): its zero pattern is structural
+void launch_marg_pattern(gwsem_engine* e, const FitProgram& fp, const MargProgram& mp, double* d_out);
 void launch_marg_fit(gwsem_engine* e, const FitProgram& fp, const MargProgram& mp, int n_snps, const double* d_summary,
                      const double* d_maf, const gwsem_result& d_res);
 

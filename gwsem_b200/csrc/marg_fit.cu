@@ -19,10 +19,10 @@ namespace {
 constexpr int LANES = 32;
 
 struct MargScratch {
-  int th, A, B, Ai, T, s, hidx, hcoef, L, scale, theta, cand, sig, sigp, r, rc, J, g, H, Hc, delta, total;
+  int th, A, B, Ai, T, s, hidx, hcoef, L, Lb, scale, theta, cand, sig, sigp, r, rc, J, g, H, Hc, delta, total;
 };
 
-__host__ __device__ inline MargScratch marg_layout(int nt, int ns, int P) {
+__host__ __device__ inline MargScratch marg_layout(int nt, int ns, int P, int nb_sep) {
   MargScratch m;
   int o = 0;
   auto take = [&](int n) { int at = o; o += n; return at; };
@@ -47,6 +47,7 @@ __host__ __device__ inline MargScratch marg_layout(int nt, int ns, int P) {
   m.rc = take(ns);
   m.g = take(P);
   m.delta = take(P);
+  m.Lb = take(nb_sep * nb_sep);  // factor of the b-block of the statistics' covariance (when rows are eliminated)
   m.total = o;
   return m;
 }
@@ -92,6 +93,84 @@ __device__ void implied_stats(const FitProgram& fp, const MargProgram& mp, Model
   gsync<LANES>();
 }
 
+// Analytic Jacobian of the model-implied statistics (RAM derivatives chained through the
+// standardisation of ordinal rows) at thv: out[i * n_c + c] = d sigma_{rows[i]} / d theta_{cols[c]}
+// (rows / cols null: all of them); `pairs`: out[i] = d sigma_{rows[i]} / d theta_{cols[i]}.
+__device__ void marg_jacobian(const FitProgram& fp, const MargProgram& mp, ModelEval<LANES>& ev, const WarpScratch& ws,
+                              double* sm, const double* thv, double* sig, double* out, const int32_t* rows, int n_r,
+                              const int32_t* cols, int n_c, bool pairs, int lane) {
+  const int nv = fp.nv;
+  implied_stats(fp, mp, ev, ws, sm, thv, sig, lane);
+  const double *Z = sm + ws.Z, *C = sm + ws.C, *muv = sm + ws.T + nv;
+  const int total = pairs ? n_r : n_r * n_c;
+  for (int idx = lane; idx < total; idx += LANES) {
+    const int ri = pairs ? idx : idx / n_c, ci = pairs ? idx : idx - ri * n_c;
+    const int e = rows ? rows[ri] : ri, k = cols ? cols[ci] : ci;
+    const int kind = mp.stat_kind[e], a = mp.stat_a[e], b = mp.stat_b[e];
+    const bool ord_a = a > 0 && mp.n_cat[a - 1] > 0;
+    const bool ord_b = kind == 4 && b > 0 && mp.n_cat[b - 1] > 0;
+    const int xa = kind == 2 ? fp.exo_latent[b] : 0;
+    double dCaa = 0.0, dCbb = 0.0, dCab = 0.0, dmu = 0.0, dZ = 0.0;
+    for (int ce = fp.par_cell_ptr[k]; ce < fp.par_cell_ptr[k + 1]; ++ce) {
+      const int c_id = fp.par_cells[ce];
+      const int m = fp.cell_mat[c_id], rr = fp.cell_row[c_id], cc = fp.cell_col[c_id];
+      if (m == 0) {
+        dCaa += 2.0 * Z[a * nv + rr] * C[cc * nv + a];
+        dmu += Z[a * nv + rr] * muv[cc];
+        if (kind == 2) dZ += Z[a * nv + rr] * Z[cc * nv + xa];
+        if (kind == 4) {
+          dCbb += 2.0 * Z[b * nv + rr] * C[cc * nv + b];
+          dCab += Z[a * nv + rr] * C[cc * nv + b] + Z[b * nv + rr] * C[cc * nv + a];
+        }
+      } else if (m == 1) {
+        dCaa += Z[a * nv + rr] * Z[a * nv + cc];
+        if (kind == 4) {
+          dCbb += Z[b * nv + rr] * Z[b * nv + cc];
+          dCab += Z[a * nv + rr] * Z[b * nv + cc];
+        }
+      } else {
+        dmu += Z[a * nv + cc];
+      }
+    }
+    const double Caa = C[a * nv + a];
+    const double sda = ord_a ? sqrt(Caa) : 1.0;
+    const double dsa = ord_a ? dCaa / (2.0 * sda * sda * sda) : 0.0;   // -d(1/sd_a)
+    double v;
+    if (kind == 0) v = dmu;
+    else if (kind == 1) {
+      const int par = fp.thr_par[e];
+      const double tau = par >= 0 ? thv[par] : fp.thr_val[e];
+      v = ((par == k ? 1.0 : 0.0) - dmu) / sda - (tau - muv[a]) * dsa;
+    } else if (kind == 2) v = dZ / sda - Z[a * nv + xa] * dsa;
+    else if (kind == 3) v = dCaa;
+    else {
+      const double Cbb = C[b * nv + b], sdb = ord_b ? sqrt(Cbb) : 1.0;
+      const double dsb = ord_b ? dCbb / (2.0 * sdb * sdb * sdb) : 0.0;
+      v = dCab / (sda * sdb) - C[a * nv + b] * (dsa / sdb + dsb / sda);
+    }
+    out[idx] = v;
+  }
+  gsync<LANES>();
+}
+
+// In-place inverse from the Cholesky factor: H (lower factor, n x n) -> out = (L L')^-1, column per lane
+__device__ void chol_inverse(const double* H, int n, double* out, int lane) {
+  for (int c = lane; c < n; c += LANES) {
+    double* x = out + c;
+    for (int i = 0; i < n; ++i) {
+      double v = (i == c) ? 1.0 : 0.0;
+      for (int k = 0; k < i; ++k) v -= H[i * n + k] * x[k * n];
+      x[i * n] = v / H[i * n + i];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+      double v = x[i * n];
+      for (int k = i + 1; k < n; ++k) v -= H[k * n + i] * x[k * n];
+      x[i * n] = v / H[i * n + i];
+    }
+  }
+  gsync<LANES>();
+}
+
 __global__ void __launch_bounds__(64)
     marg_fit_kernel(FitProgram fp, MargProgram mp, int n_snps, const double* __restrict__ summary,
                     const double* __restrict__ maf_in, gwsem_result res) {
@@ -102,7 +181,7 @@ __global__ void __launch_bounds__(64)
   const int J = mp.J, n1 = mp.n1, npii = mp.npii, q0 = mp.q0, D = 2 + J;
   const int nt = 2 + n1 + J + npii, ns = mp.n_stat, P = fp.P, nv = fp.nv;
   const WarpScratch ws = scratch_layout(fp.p, fp.q, nv, P, 1);
-  const MargScratch ms = marg_layout(nt, ns, P);
+  const MargScratch ms = marg_layout(nt, ns, P, mp.n_a > 0 ? mp.n_b : 0);
   double* sm = smem_d + (size_t)group * (ws.total + ms.total);
   double* mx = sm + ws.total;
   const double* rec = summary + (int64_t)snp * mp.sum_stride;
@@ -311,76 +390,42 @@ __global__ void __launch_bounds__(64)
     if (y > x) L[e] = L[y * ns + x];
   }
   gsync<LANES>();
-  if (!warp_cholesky<LANES>(L, ns, lane, gscale)) {
+  // ---- Fit.  Parameters that enter exactly one statistic (thresholds, covariate slopes: mp.elim_a_*)
+  // can reproduce any value of it, so minimising over them leaves the b-statistics' residuals
+  // weighted by the inverse of their own covariance block (a Schur complement of the full weight):
+  //   min_theta r' Gamma^-1 r  =  min_beta r_b' Gamma_bb^-1 r_b ,   r_a = Gamma_ab Gamma_bb^-1 r_b .
+  // The iteration runs on beta only (n_beta parameters, n_b statistics); the eliminated parameters
+  // follow in closed form and the full Jacobian is needed once, for the parameter covariance.
+  const int n_el = mp.n_a, nb = n_el > 0 ? mp.n_b : ns, nbeta = n_el > 0 ? mp.n_beta : P;
+  const int32_t* b_row = n_el > 0 ? mp.elim_b_row : nullptr;
+  const int32_t* b_par = n_el > 0 ? mp.elim_b_par : nullptr;
+  double* Lb = n_el > 0 ? mx + ms.Lb : L;
+  if (n_el > 0) {
+    for (int e = lane; e < nb * nb; e += LANES) Lb[e] = L[b_row[e / nb] * ns + b_row[e % nb]];
+    double* sc = mx + ms.sigp;  // pivot scales of the b block
+    for (int e = lane; e < nb; e += LANES) sc[e] = gscale[b_row[e]];
+    gsync<LANES>();
+    if (!warp_cholesky<LANES>(Lb, nb, lane, sc)) {
+      if (lane == 0) res.catch_code[snp] = GWSEM_CATCH_ACOV_NOT_PD;
+      return;
+    }
+  } else if (!warp_cholesky<LANES>(L, ns, lane, gscale)) {
     if (lane == 0) res.catch_code[snp] = GWSEM_CATCH_ACOV_NOT_PD;
     return;
   }
 
-  // ---- damped Gauss-Newton (same schedule as fit.cu / the oracle), numeric Jacobian
-  double *theta = mx + ms.theta, *cand = mx + ms.cand, *sig = mx + ms.sig, *sigp = mx + ms.sigp, *r = mx + ms.r;
+  // ---- damped Gauss-Newton on beta (same schedule as fit.cu / the oracle)
+  double *theta = mx + ms.theta, *cand = mx + ms.cand, *sig = mx + ms.sig, *r = mx + ms.r;
   double *rc = mx + ms.rc, *Jm = mx + ms.J, *g = mx + ms.g, *H = mx + ms.H, *Hc = mx + ms.Hc, *delta = mx + ms.delta;
   ModelEval<LANES> ev{fp, ws, sm, lane};
   auto objective = [&](const double* thv, double* resid) -> double {
     implied_stats(fp, mp, ev, ws, sm, thv, sig, lane);
-    for (int e = lane; e < ns; e += LANES) resid[e] = s[e] - sig[e];
+    for (int e = lane; e < nb; e += LANES) { const int row = b_row ? b_row[e] : e; resid[e] = s[row] - sig[row]; }
     gsync<LANES>();
-    warp_forward_solve<LANES>(L, ns, resid, 1, 1, lane);
+    warp_forward_solve<LANES>(Lb, nb, resid, 1, 1, lane);
     double f = 0.0;
-    for (int e = 0; e < ns; ++e) f += resid[e] * resid[e];
+    for (int e = 0; e < nb; ++e) f += resid[e] * resid[e];
     return f;
-  };
-  // analytic Jacobian of the model-implied statistics (RAM derivatives chained through the
-  // standardisation of ordinal rows); evaluated at thv
-  auto jacobian = [&](double* thv) {
-    implied_stats(fp, mp, ev, ws, sm, thv, sig, lane);
-    const double *Z = sm + ws.Z, *C = sm + ws.C, *muv = sm + ws.T + nv;
-    for (int idx = lane; idx < ns * P; idx += LANES) {
-      const int e = idx / P, k = idx % P;
-      const int kind = mp.stat_kind[e], a = mp.stat_a[e], b = mp.stat_b[e];
-      const bool ord_a = a > 0 && mp.n_cat[a - 1] > 0;
-      const bool ord_b = kind == 4 && b > 0 && mp.n_cat[b - 1] > 0;
-      const int xa = kind == 2 ? fp.exo_latent[b] : 0;
-      double dCaa = 0.0, dCbb = 0.0, dCab = 0.0, dmu = 0.0, dZ = 0.0;
-      for (int ce = fp.par_cell_ptr[k]; ce < fp.par_cell_ptr[k + 1]; ++ce) {
-        const int c_id = fp.par_cells[ce];
-        const int m = fp.cell_mat[c_id], rr = fp.cell_row[c_id], cc = fp.cell_col[c_id];
-        if (m == 0) {
-          dCaa += 2.0 * Z[a * nv + rr] * C[cc * nv + a];
-          dmu += Z[a * nv + rr] * muv[cc];
-          if (kind == 2) dZ += Z[a * nv + rr] * Z[cc * nv + xa];
-          if (kind == 4) {
-            dCbb += 2.0 * Z[b * nv + rr] * C[cc * nv + b];
-            dCab += Z[a * nv + rr] * C[cc * nv + b] + Z[b * nv + rr] * C[cc * nv + a];
-          }
-        } else if (m == 1) {
-          dCaa += Z[a * nv + rr] * Z[a * nv + cc];
-          if (kind == 4) {
-            dCbb += Z[b * nv + rr] * Z[b * nv + cc];
-            dCab += Z[a * nv + rr] * Z[b * nv + cc];
-          }
-        } else {
-          dmu += Z[a * nv + cc];
-        }
-      }
-      const double Caa = C[a * nv + a];
-      const double sda = ord_a ? sqrt(Caa) : 1.0;
-      const double dsa = ord_a ? dCaa / (2.0 * sda * sda * sda) : 0.0;   // -d(1/sd_a)
-      double v;
-      if (kind == 0) v = dmu;
-      else if (kind == 1) {
-        const int par = fp.thr_par[e];
-        const double tau = par >= 0 ? thv[par] : fp.thr_val[e];
-        v = ((par == k ? 1.0 : 0.0) - dmu) / sda - (tau - muv[a]) * dsa;
-      } else if (kind == 2) v = dZ / sda - Z[a * nv + xa] * dsa;
-      else if (kind == 3) v = dCaa;
-      else {
-        const double Cbb = C[b * nv + b], sdb = ord_b ? sqrt(Cbb) : 1.0;
-        const double dsb = ord_b ? dCbb / (2.0 * sdb * sdb * sdb) : 0.0;
-        v = dCab / (sda * sdb) - C[a * nv + b] * (dsa / sdb + dsb / sda);
-      }
-      Jm[idx] = v;
-    }
-    gsync<LANES>();
   };
   for (int k = lane; k < P; k += LANES) theta[k] = fp.par_warm ? fp.par_warm[k] : fp.par_start[k];
   gsync<LANES>();
@@ -389,50 +434,53 @@ __global__ void __launch_bounds__(64)
   int status = GWSEM_STATUS_ITERATION_LIMIT;
   int it = 0;
   const int max_iter = 200;
-  for (it = 1; it <= max_iter; ++it) {
-    jacobian(theta);
-    warp_forward_solve<LANES>(L, ns, Jm, P, P, lane);
-    for (int k = lane; k < P; k += LANES) {
+  for (it = 1; it <= max_iter && nbeta > 0; ++it) {
+    marg_jacobian(fp, mp, ev, ws, sm, theta, sig, Jm, b_row, nb, b_par, nbeta, false, lane);
+    warp_forward_solve<LANES>(Lb, nb, Jm, nbeta, nbeta, lane);
+    for (int k = lane; k < nbeta; k += LANES) {
       double v = 0.0;
-      for (int e = 0; e < ns; ++e) v += Jm[e * P + k] * r[e];
+      for (int e = 0; e < nb; ++e) v += Jm[e * nbeta + k] * r[e];
       g[k] = v;
     }
-    for (int idx = lane; idx < P * P; idx += LANES) {
-      const int a = idx / P, b = idx % P;
+    for (int idx = lane; idx < nbeta * nbeta; idx += LANES) {
+      const int a = idx / nbeta, b = idx % nbeta;
       double v = 0.0;
-      for (int e = 0; e < ns; ++e) v += Jm[e * P + a] * Jm[e * P + b];
+      for (int e = 0; e < nb; ++e) v += Jm[e * nbeta + a] * Jm[e * nbeta + b];
       H[idx] = v;
     }
     gsync<LANES>();
     bool improved = false;
     double Fc = F;
     for (int attempt = 0; attempt < 30; ++attempt) {
-      for (int idx = lane; idx < P * P; idx += LANES) {
-        const int a = idx / P, b = idx % P;
+      for (int idx = lane; idx < nbeta * nbeta; idx += LANES) {
+        const int a = idx / nbeta, b = idx % nbeta;
         double v = H[idx];
         if (a == b) v += lam * fmax(H[idx], 1e-12);
         Hc[idx] = v;
       }
       gsync<LANES>();
-      if (!warp_cholesky<LANES>(Hc, P, lane)) { lam *= 10; continue; }
+      if (!warp_cholesky<LANES>(Hc, nbeta, lane)) { lam *= 10; continue; }
       if (lane == 0) {
-        for (int i = 0; i < P; ++i) {
+        for (int i = 0; i < nbeta; ++i) {
           double v = g[i];
-          for (int k = 0; k < i; ++k) v -= Hc[i * P + k] * delta[k];
-          delta[i] = v / Hc[i * P + i];
+          for (int k = 0; k < i; ++k) v -= Hc[i * nbeta + k] * delta[k];
+          delta[i] = v / Hc[i * nbeta + i];
         }
-        for (int i = P - 1; i >= 0; --i) {
+        for (int i = nbeta - 1; i >= 0; --i) {
           double v = delta[i];
-          for (int k = i + 1; k < P; ++k) v -= Hc[k * P + i] * delta[k];
-          delta[i] = v / Hc[i * P + i];
+          for (int k = i + 1; k < nbeta; ++k) v -= Hc[k * nbeta + i] * delta[k];
+          delta[i] = v / Hc[i * nbeta + i];
         }
       }
       gsync<LANES>();
-      for (int k = lane; k < P; k += LANES) {
-        double c = theta[k] + delta[k];
+      for (int k = lane; k < P; k += LANES) cand[k] = theta[k];
+      gsync<LANES>();
+      for (int c = lane; c < nbeta; c += LANES) {
+        const int k = b_par ? b_par[c] : c;
+        double v = theta[k] + delta[c];
         const double lb = fp.par_lbound[k];
-        if (lb == lb && c < lb) c = lb;
-        cand[k] = c;
+        if (lb == lb && v < lb) v = lb;
+        cand[k] = v;
       }
       gsync<LANES>();
       Fc = objective(cand, rc);
@@ -441,24 +489,62 @@ __global__ void __launch_bounds__(64)
     }
     if (!improved) {
       double gmax = 0.0;
-      for (int k = 0; k < P; ++k) gmax = fmax(gmax, fabs(g[k]));
+      for (int k = 0; k < nbeta; ++k) gmax = fmax(gmax, fabs(g[k]));
       status = gmax < 1e-6 * (1 + F) ? GWSEM_STATUS_OK : GWSEM_STATUS_NONZERO_GRADIENT;
       break;
     }
     double step = 0.0;
-    for (int k = 0; k < P; ++k) step = fmax(step, fabs(cand[k] - theta[k]) / (fabs(theta[k]) + 1e-3));
+    for (int c = 0; c < nbeta; ++c) {
+      const int k = b_par ? b_par[c] : c;
+      step = fmax(step, fabs(cand[k] - theta[k]) / (fabs(theta[k]) + 1e-3));
+    }
     const double dF = F - Fc;
     gsync<LANES>();
     for (int k = lane; k < P; k += LANES) theta[k] = cand[k];
-    for (int e = lane; e < ns; e += LANES) r[e] = rc[e];
+    for (int e = lane; e < nb; e += LANES) r[e] = rc[e];
     gsync<LANES>();
     F = Fc;
     lam = fmax(lam / 10, 1e-12);
     if (step < 1e-10 || dF <= 1e-14 * (1 + F)) { status = GWSEM_STATUS_OK; break; }
   }
+  if (nbeta == 0) { status = GWSEM_STATUS_OK; it = 0; }
   if (it > max_iter) it = max_iter;
 
-  jacobian(theta);
+  if (n_el > 0) {
+    // eliminated parameters: r_a = Gamma_ab Gamma_bb^-1 r_b, then each one from its own statistic
+    // (r holds Lb^-1 r_b; back-substitution gives w = Gamma_bb^-1 r_b)
+    double* w = rc;
+    if (lane == 0)
+      for (int i = nb - 1; i >= 0; --i) {
+        double v = r[i];
+        for (int k = i + 1; k < nb; ++k) v -= Lb[k * nb + i] * w[k];
+        w[i] = v / Lb[i * nb + i];
+      }
+    gsync<LANES>();
+    double* target = mx + ms.sigp;  // n_el <= ns
+    for (int i = lane; i < n_el; i += LANES) {
+      const int row = mp.elim_a_row[i];
+      double ra = 0.0;
+      for (int j = 0; j < nb; ++j) ra += L[row * ns + b_row[j]] * w[j];   // L still holds Gamma
+      target[i] = s[row] - ra;
+    }
+    gsync<LANES>();
+    for (int round = 0; round < 2; ++round) {  // exact after one round when the statistic is linear in its parameter
+      marg_jacobian(fp, mp, ev, ws, sm, theta, sig, delta, mp.elim_a_row, n_el, mp.elim_a_par, n_el, true, lane);
+      for (int i = lane; i < n_el; i += LANES) {
+        const double d = delta[i];
+        if (d != 0.0) theta[mp.elim_a_par[i]] += (target[i] - sig[mp.elim_a_row[i]]) / d;
+      }
+      gsync<LANES>();
+    }
+    if (!warp_cholesky<LANES>(L, ns, lane, gscale)) {
+      if (lane == 0) res.catch_code[snp] = GWSEM_CATCH_ACOV_NOT_PD;
+      return;
+    }
+  }
+
+  // ---- parameter covariance (J' W J)^-1 from the full Jacobian at the estimate
+  marg_jacobian(fp, mp, ev, ws, sm, theta, sig, Jm, nullptr, ns, nullptr, P, false, lane);
   warp_forward_solve<LANES>(L, ns, Jm, P, P, lane);
   for (int idx = lane; idx < P * P; idx += LANES) {
     const int a = idx / P, b = idx % P;
@@ -468,20 +554,7 @@ __global__ void __launch_bounds__(64)
   }
   gsync<LANES>();
   if (warp_cholesky<LANES>(H, P, lane)) {
-    for (int c = lane; c < P; c += LANES) {
-      double* x = Hc + c;
-      for (int i = 0; i < P; ++i) {
-        double v = (i == c) ? 1.0 : 0.0;
-        for (int k = 0; k < i; ++k) v -= H[i * P + k] * x[k * P];
-        x[i * P] = v / H[i * P + i];
-      }
-      for (int i = P - 1; i >= 0; --i) {
-        double v = x[i * P];
-        for (int k = i + 1; k < P; ++k) v -= H[k * P + i] * x[k * P];
-        x[i * P] = v / H[i * P + i];
-      }
-    }
-    gsync<LANES>();
+    chol_inverse(H, P, Hc, lane);
     for (int idx = lane; idx < P * P; idx += LANES) vcov[idx] = Hc[idx];
   }
   for (int k = lane; k < P; k += LANES) est[k] = theta[k];
@@ -492,11 +565,40 @@ __global__ void __launch_bounds__(64)
   }
 }
 
+__global__ void __launch_bounds__(32) marg_pattern_kernel(FitProgram fp, MargProgram mp, double* __restrict__ out) {
+  extern __shared__ double smem_d[];
+  const int lane = threadIdx.x;
+  const int nt = 2 + mp.n1 + mp.J + mp.npii, ns = mp.n_stat, P = fp.P;
+  const WarpScratch ws = scratch_layout(fp.p, fp.q, fp.nv, P, 1);
+  const MargScratch ms = marg_layout(nt, ns, P, 0);
+  double *sm = smem_d, *mx = sm + ws.total;
+  double *theta = mx + ms.theta, *sig = mx + ms.sig, *Jm = mx + ms.J;
+  ModelEval<LANES> ev{fp, ws, sm, lane};
+  for (int rep = 0; rep < 2; ++rep) {
+    for (int k = lane; k < P; k += LANES)
+      theta[k] = rep == 0 ? fp.par_start[k] + 0.1 + 0.013 * k : fp.par_start[k] * 1.3 + 0.2 - 0.011 * k;
+    gsync<LANES>();
+    marg_jacobian(fp, mp, ev, ws, sm, theta, sig, Jm, nullptr, ns, nullptr, P, false, lane);
+    for (int e = lane; e < ns * P; e += LANES) out[rep * ns * P + e] = Jm[e];
+    gsync<LANES>();
+  }
+}
+
 }  // namespace
+
+void launch_marg_pattern(gwsem_engine* e, const FitProgram& fp, const MargProgram& mp, double* d_out) {
+  const int nt = 2 + mp.n1 + mp.J + mp.npii;
+  const size_t smem = ((size_t)scratch_layout(fp.p, fp.q, fp.nv, fp.P, 1).total + marg_layout(nt, mp.n_stat, fp.P, 0).total) * sizeof(double);
+  if (smem > 227 * 1024) fail("marginals model too large for the per-SNP fit kernel (%zu bytes of scratch)", smem);
+  GW_CUDA(cudaFuncSetAttribute(marg_pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  marg_pattern_kernel<<<1, 32, smem, e->stream>>>(fp, mp, d_out);
+  GW_CUDA(cudaGetLastError());
+  e->launches++;
+}
 
 size_t marg_fit_scratch_doubles(const FitProgram& fp, const MargProgram& mp) {
   const int nt = 2 + mp.n1 + mp.J + mp.npii;
-  return (size_t)scratch_layout(fp.p, fp.q, fp.nv, fp.P, 1).total + marg_layout(nt, mp.n_stat, fp.P).total;
+  return (size_t)scratch_layout(fp.p, fp.q, fp.nv, fp.P, 1).total + marg_layout(nt, mp.n_stat, fp.P, mp.n_a > 0 ? mp.n_b : 0).total;
 }
 
 void launch_marg_fit(gwsem_engine* e, const FitProgram& fp, const MargProgram& mp, int n_snps, const double* d_summary,

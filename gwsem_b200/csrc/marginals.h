@@ -60,6 +60,13 @@ struct MargProgram {
   const int32_t* stat_a = nullptr;           // manifest variable
   const int32_t* stat_b = nullptr;           // threshold index / covariate index / second variable
   const int32_t* stat_theta = nullptr;       // index into theta (snp 2 | items n1 | rho_j0 J | rho_ii)
+  // parameters that enter exactly one statistic are eliminated from the iteration (marg_fit.cu):
+  // pairs (elim_a_par[i], elim_a_row[i]); the iteration runs on parameters elim_b_par over rows elim_b_row
+  int n_a = 0, n_b = 0, n_beta = 0;
+  const int32_t* elim_a_par = nullptr;
+  const int32_t* elim_a_row = nullptr;
+  const int32_t* elim_b_par = nullptr;
+  const int32_t* elim_b_row = nullptr;
   // summary record per SNP (doubles)
   int sum_stride = 0, o_rho = 0, o_a22 = 0, o_a21snp = 0, o_a21item = 0, o_bdd = 0, o_bd0 = 0;
   int o_msum = 0, o_mmat = 0;  // missing-call people: sum of their item-side score rows, and of the outer products

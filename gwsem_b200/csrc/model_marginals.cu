@@ -241,6 +241,35 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
   fp.thr_val = up(pool, tval, st);
   fp.exo_latent = up(pool, exo_latent, st);
 
+  // Parameters that enter exactly one statistic (and are not bounded) leave the iteration: read
+  // the structural zero pattern of the Jacobian from two generic points.
+  {
+    const int ns = mp.n_stat;
+    DeviceBuffer<double> dj;
+    dj.ensure((size_t)2 * ns * P);
+    mp.n_a = 0;
+    launch_marg_pattern(engine, fp, mp, dj.p);
+    std::vector<double> jj((size_t)2 * ns * P);
+    GW_CUDA(cudaMemcpyAsync(jj.data(), dj.p, jj.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    GW_CUDA(cudaStreamSynchronize(st));
+    std::vector<int32_t> a_par, a_row, b_par, b_row;
+    std::vector<char> row_taken(ns, 0), par_gone(P, 0);
+    for (int k = 0; k < P; ++k) {
+      if (par_lbound[k] == par_lbound[k]) continue;
+      int only = -1, cnt = 0;
+      for (int e = 0; e < ns; ++e)
+        if (jj[(size_t)e * P + k] != 0.0 || jj[(size_t)(ns + e) * P + k] != 0.0) { only = e; ++cnt; }
+      if (cnt == 1 && !row_taken[only]) { row_taken[only] = 1; par_gone[k] = 1; a_par.push_back(k); a_row.push_back(only); }
+    }
+    for (int e = 0; e < ns; ++e) if (!row_taken[e]) b_row.push_back(e);
+    for (int k = 0; k < P; ++k) if (!par_gone[k]) b_par.push_back(k);
+    if (!a_par.empty()) {
+      mp.n_a = (int)a_par.size(); mp.n_b = (int)b_row.size(); mp.n_beta = (int)b_par.size();
+      mp.elim_a_par = up(pool, a_par, st); mp.elim_a_row = up(pool, a_row, st);
+      mp.elim_b_par = up(pool, b_par, st); mp.elim_b_row = up(pool, b_row, st);
+    }
+  }
+
   // Warm start.  The reference restarts every SNP from the model's start values so that a row does
   // not depend on its neighbours (R/model.R:188); the same holds here with a start that is fixed
   // per model: the estimates for a reference genotype column (codes 0,1,2,0,1,2,... down the file,
