@@ -125,7 +125,7 @@ __device__ __forceinline__ double block_sum(double v, double* red, int tid) {
 // DOSAGE = false: hardcalls from the packed 2-bit row (class counts given);
 // DOSAGE = true: genotype column of doubles in file order (NaN = missing), moments taken here.
 template <int J, bool DOSAGE, int HALVES>
-__global__ void __launch_bounds__(kT)
+__global__ void __launch_bounds__(kT, 2)
     marg_stats_kernel(MargProgram mp, const uint8_t* __restrict__ rows, int64_t pitch, int n_src,
                       const uint8_t* __restrict__ inc8, const int32_t* __restrict__ counts, int plink1,
                       const double* __restrict__ geno, int n_pad, double* __restrict__ summary) {
@@ -308,10 +308,12 @@ __global__ void __launch_bounds__(kT)
   for (int j = 0; j < J; ++j) { rh[j] = rho_sh[j]; inv_s[j] = rsqrt(1.0 - rh[j] * rh[j]); }
 
   // ---- Gamma pieces.  Phase 1 (thread = person): the SNP-dependent score columns D = (mean, var,
-  // psi_j), and V[b] = psi_j * d loglik2 / d (stage-1 parameter b of item j), whose column sums are
-  // the A21 rows of the new correlations.  Phase 2 (lane = score column): D' * SC0 and sum V.
+  // psi_j); the A21 rows of the new correlations, sum_i psi_j * d loglik2_i / d (stage-1 parameter
+  // of item j), accumulate in a row of shared memory private to the thread (a person touches two
+  // threshold entries and the K slopes of each item).  Phase 2 (lane = score column): D' * SC0.
   constexpr int DP = (D + 1) & ~1;                 // Dt row stride (16-byte rows for 128-bit loads)
-  const int vs = mp.n1 | 1;                        // V row stride, odd: conflict-free row writes
+  constexpr int Q0P = 32 * HALVES;                 // SC0 row stride
+  const int vs = mp.n1 | 1;                        // accumulator row stride, odd: conflict-free
   double* Dt = dyn;                                // [kT][DP]
   double* Vt = dyn + kT * DP;                      // [kT][vs]
   double bdd[D * (D + 1) / 2], a21snp[2 * J], ns1[J], ns2[J];  // sums of psi and d psi / d rho, for the closing Newton step
@@ -321,24 +323,23 @@ __global__ void __launch_bounds__(kT)
   for (int k = 0; k < D * (D + 1) / 2; ++k) bdd[k] = 0.0;
 #pragma unroll
   for (int k = 0; k < 2 * J; ++k) a21snp[k] = 0.0;
-  double acc[HALVES][D + 1];  // per lane: columns lane (, lane + 32); last slot is the A21 item entry
+  double acc[HALVES][D];  // per lane: columns lane (, lane + 32)
 #pragma unroll
   for (int h = 0; h < HALVES; ++h)
 #pragma unroll
-    for (int a = 0; a <= D; ++a) acc[h][a] = 0.0;
+    for (int a = 0; a < D; ++a) acc[h][a] = 0.0;
   const int K = mp.K;
   const double isd = 1.0 / sd, i2v = 1.0 / (2.0 * var);
+  double* vrow = Vt + tid * vs;
+  for (int b2 = 0; b2 < mp.n1; ++b2) vrow[b2] = 0.0;
   for (int t0 = 0; t0 < n_src; t0 += kT) {
     const int i = t0 + tid;
-    double d[D];
-#pragma unroll
-    for (int a = 0; a < D; ++a) d[a] = 0.0;
     double u;
     const bool live = i < n_src && std_geno(i, &u);
-    double* vrow = Vt + tid * vs;
     if (live) {
+      double d[D], ps[J];
       d[0] = u * isd;
-        d[1] = (u * u - 1.0) * i2v;
+      d[1] = (u * u - 1.0) * i2v;
 #pragma unroll
       for (int j = 0; j < J; ++j) {
         const double* zz = mp.zz + ((int64_t)i * J + j) * 5;
@@ -350,17 +351,25 @@ __global__ void __launch_bounds__(kT)
         a21snp[2 * j + 1] -= t.psi * fma(t.dl_du, u, 1.0) * i2v;
         const double pa = t.psi * t.dl_a, pb = t.psi * t.dl_b;
         double* vj = vrow + mp.col_of[j];
-        const double* xi = mp.X + (int64_t)i * mp.Kp;
         if (ordinal[j]) {
           const int nth = mp.n_cat[j] - 1, cat = mp.cat[(int64_t)i * J + j];
-          for (int c = 0; c < nth; ++c) vj[c] = (cat == c ? pa : 0.0) + (cat == c + 1 ? pb : 0.0);
-          const double ps = -(pa + pb);
-          for (int k = 0; k < K; ++k) vj[nth + k] = xi[k] * ps;
+          if (cat < nth) vj[cat] += pa;
+          if (cat > 0) vj[cat - 1] += pb;
+          ps[j] = -(pa + pb);
         } else {  // continuous item: intercept, slopes, variance; zz[0] is the standardised residual
-          const double isd = 1.0 / mp.item_sd[j], ps = -pa * isd;
-          vj[0] = ps;
-          for (int k = 0; k < K; ++k) vj[1 + k] = xi[k] * ps;
-          vj[1 + K] = -(t.psi + pa * zz[0]) * (0.5 * isd * isd);
+          const double isdj = 1.0 / mp.item_sd[j];
+          ps[j] = -pa * isdj;
+          vj[0] += ps[j];
+          vj[1 + K] -= (t.psi + pa * zz[0]) * (0.5 * isdj * isdj);
+        }
+      }
+      const double* xi = mp.X + (int64_t)i * mp.Kp;
+      for (int k = 0; k < K; ++k) {
+        const double x = xi[k];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          double* sl = vrow + mp.col_of[j] + (ordinal[j] ? mp.n_cat[j] - 1 : 1) + k;
+          *sl = fma(x, ps[j], *sl);
         }
       }
       int k = 0;
@@ -368,45 +377,39 @@ __global__ void __launch_bounds__(kT)
       for (int a = 0; a < D; ++a)
 #pragma unroll
         for (int b = a; b < D; ++b) { bdd[k] = fma(d[a], d[b], bdd[k]); ++k; }
-    } else {
-      for (int b = 0; b < mp.n1; ++b) vrow[b] = 0.0;
-    }
 #pragma unroll
-    for (int a = 0; a < D; ++a) Dt[tid * DP + a] = d[a];
+      for (int a = 0; a < D; ++a) Dt[tid * DP + a] = d[a];
+    } else {
+#pragma unroll
+      for (int a = 0; a < D; ++a) Dt[tid * DP + a] = 0.0;
+    }
     if (DP > D) Dt[tid * DP + D] = 0.0;
     __syncthreads();
     // phase 2: warp w takes people w*32 .. w*32+31 of the tile, four at a time so that the global
     // loads of four score rows are in flight together (SC0 is padded with zero rows to whole tiles;
-    // rows of missing and excluded people have D = 0 and V = 0)
-    const double* scw = mp.sc0 + (int64_t)(t0 + warp * 32) * mp.q0p + lane;
+    // rows of missing and excluded people have D = 0)
+    const double* scw = mp.sc0 + (int64_t)(t0 + warp * 32) * Q0P + lane;
     const double* dw = Dt + warp * 32 * DP;
-    const double* vw = Vt + warp * 32 * vs + lane;   // lanes beyond n1 read neighbouring rows; their sums are not used
-    const int q0p = mp.q0p;
+#pragma unroll 2
     for (int pp0 = 0; pp0 < 32; pp0 += 4) {
       double sc[4][HALVES];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 4; ++k)
 #pragma unroll
-        for (int h = 0; h < HALVES; ++h) sc[k][h] = scw[32 * h];
-        scw += q0p;
-      }
+        for (int h = 0; h < HALVES; ++h) sc[k][h] = scw[(pp0 + k) * Q0P + 32 * h];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         double dpr[DP];
 #pragma unroll
         for (int a = 0; a < DP; a += 2) {
-          const double2 two = *reinterpret_cast<const double2*>(dw + a);
+          const double2 two = *reinterpret_cast<const double2*>(dw + (pp0 + k) * DP + a);
           dpr[a] = two.x;
           dpr[a + 1] = two.y;
         }
-        dw += DP;
 #pragma unroll
-        for (int h = 0; h < HALVES; ++h) {
+        for (int h = 0; h < HALVES; ++h)
 #pragma unroll
           for (int a = 0; a < D; ++a) acc[h][a] = fma(dpr[a], sc[k][h], acc[h][a]);
-          acc[h][D] += vw[32 * h];
-        }
-        vw += vs;
       }
     }
     __syncthreads();
@@ -433,21 +436,29 @@ __global__ void __launch_bounds__(kT)
         }
       }
   }
+  // A21 rows: column sums of the threads' private rows
+  __syncthreads();
+  for (int b2 = warp; b2 < mp.n1; b2 += kT / 32) {
+    double v = 0.0;
+    for (int r = lane; r < kT; r += 32) v += Vt[r * vs + b2];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) out[mp.o_a21item + b2] = v;
+  }
   // lane-owned columns: sum the 8 warps through shared memory
-  double* xw = dyn;  // [8][64][D+1]
+  double* xw = dyn;  // [8][64][D]
   __syncthreads();
 #pragma unroll
   for (int h = 0; h < HALVES; ++h)
 #pragma unroll
-    for (int a = 0; a <= D; ++a) xw[((warp * 64) + lane + 32 * h) * (D + 1) + a] = acc[h][a];
+    for (int a = 0; a < D; ++a) xw[((warp * 64) + lane + 32 * h) * D + a] = acc[h][a];
   __syncthreads();
-  for (int e = tid; e < 32 * HALVES * (D + 1); e += kT) {
-    const int b = e / (D + 1), a = e % (D + 1);
-    if (b >= mp.q0) continue;
+  for (int e = tid; e < 32 * HALVES * D; e += kT) {
+    const int b2 = e / D, a = e % D;
+    if (b2 >= mp.q0) continue;
     double v = 0.0;
-    for (int w = 0; w < kT / 32; ++w) v += xw[(w * 64 + b) * (D + 1) + a];
-    if (a < D) out[mp.o_bd0 + a * mp.q0 + b] = v;
-    else if (b < mp.n1) out[mp.o_a21item + b] = v;
+    for (int w = 0; w < kT / 32; ++w) v += xw[(w * 64 + b2) * D + a];
+    out[mp.o_bd0 + a * mp.q0 + b2] = v;
   }
 }
 
