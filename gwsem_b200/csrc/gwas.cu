@@ -11,6 +11,9 @@
 #include <fstream>
 #include <map>
 #include <sstream>
+#include <charconv>
+#include <future>
+#include <thread>
 
 #include "common.h"
 #include "kernels.h"
@@ -41,6 +44,7 @@ struct Stager {
   int n_pad;
   int64_t pitch;  // canonical row pitch (bytes, multiple of 16, >= n_pad / 4)
   PinnedBuffer<uint8_t> h_bytes;
+  PinnedBuffer<uint8_t> h_fixed[2];  // fixed-width records: read ahead by a host thread (see read_fixed)
   DeviceBuffer<uint8_t> d_bytes, d_vt, d_rows;
   DeviceBuffer<uint64_t> d_off;
   DeviceBuffer<int32_t> d_base, d_err;
@@ -63,6 +67,63 @@ struct Stager {
     if (v >= s->n_variants)  // loader.cpp:369-372
       fail("%s: out of data (record %u requested but only %u in file)", s->kind == gwsem_source::kPgen ? "pgen" : "bgen", v + 1,
            s->n_variants);
+  }
+
+  bool fixed_width() const { return s->kind == gwsem_source::kPgen && (s->mode == 0x01 || s->mode == 0x02); }
+
+  // Fixed-width hardcall records (.bed, pgen mode 0x02): the record already is the canonical row.
+  // Reads variants[0..n) into pinned slot `slot`; runs of consecutive variants are one request,
+  // split over a few threads (page-cache copies scale with threads).  Host work only: runs on a
+  // helper thread while the device works on the previous batch.
+  void read_fixed(const uint32_t* variants, int n, int slot) {
+    for (int k = 0; k < n; ++k) check_index(variants[k]);
+    const int64_t row_bytes = ((int64_t)s->n_samples + 3) / 4;
+    struct Run { uint64_t off; uint8_t* dst; size_t len; };
+    std::vector<Run> runs;
+    const size_t piece = 8u << 20;
+    int k = 0;
+    while (k < n) {
+      int j = k + 1;
+      while (j < n && variants[j] == variants[j - 1] + 1) ++j;
+      uint64_t off0 = s->record_offset(variants[k]);
+      uint8_t* dst = h_fixed[slot].p + (size_t)k * row_bytes;
+      size_t len = (size_t)(j - k) * row_bytes;
+      while (len) {
+        const size_t take = std::min(len, piece);
+        runs.push_back({off0, dst, take});
+        off0 += take; dst += take; len -= take;
+      }
+      k = j;
+    }
+    const int threads = (int)std::min<size_t>(std::min(8u, std::max(1u, std::thread::hardware_concurrency())), runs.size());
+    std::vector<std::exception_ptr> err(std::max(threads, 1));
+    auto work = [&](int t) {
+      try {
+        for (size_t r = t; r < runs.size(); r += threads) s->read_at(runs[r].off, runs[r].dst, runs[r].len);
+      } catch (...) { err[t] = std::current_exception(); }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
+    if (threads > 0) work(0);
+    for (auto& th : pool) th.join();
+    for (auto& e2 : err) if (e2) std::rethrow_exception(e2);
+  }
+  void ensure_fixed(int max_rows) {  // on the calling thread: pinned allocation is a CUDA call
+    const int64_t row_bytes = ((int64_t)s->n_samples + 3) / 4;
+    for (auto& b : h_fixed) b.ensure((size_t)max_rows * row_bytes + 16);
+  }
+  void upload_fixed(int n, int slot) {
+    cudaStream_t st = e->stream;
+    const int64_t row_bytes = ((int64_t)s->n_samples + 3) / 4;
+    plink1 = s->mode == 0x01;
+    has_dosage = false;
+    d_rows.ensure((size_t)n * pitch + 16);
+    if (!rows_zeroed) {
+      GW_CUDA(cudaMemsetAsync(d_rows.p, 0, d_rows.n, st));
+      rows_zeroed = true;
+    }
+    GW_CUDA(cudaMemcpy2DAsync(d_rows.p, pitch, h_fixed[slot].p, row_bytes, row_bytes, n, cudaMemcpyHostToDevice, st));
+    n_rows_staged = n;
   }
 
   // PGEN / BED: leaves variants[k] decoded in row k of d_rows (+ d_dosage when has_dosage)
@@ -270,12 +331,33 @@ struct ContextFile {  // mxComputeLoadContext: line idx of .pvar / .bim (R/model
   }
 };
 
-void append_double(std::string& out, double v) {
+void append_double(std::string& out, double v) {  // as printf("%.15g"), NA for missing
   if (std::isnan(v)) { out += "NA"; return; }
   char buf[40];
-  snprintf(buf, sizeof(buf), "%.15g", v);
-  out += buf;
+  const auto r = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::general, 15);
+  out.append(buf, r.ptr);
 }
+
+// One batch of per-SNP results on the host, formatted into log rows by a pool of threads while
+// the next batch is staged and fitted.
+struct RowBatch {
+  int n = 0;
+  std::vector<uint32_t> variant;
+  std::vector<double> est, vcov, fit, maf;
+  std::vector<int32_t> n_used, status, catch_code, catch_var, iterations;
+  void resize(int rows, int P) {
+    n = rows;
+    variant.resize(rows);
+    est.resize((size_t)rows * P); vcov.resize((size_t)rows * P * P); fit.resize(rows); maf.resize(rows);
+    n_used.resize(rows); status.resize(rows); catch_code.resize(rows); catch_var.resize(rows); iterations.resize(rows);
+  }
+  gwsem_result view() {
+    gwsem_result h;
+    h.est = est.data(); h.vcov = vcov.data(); h.fit = fit.data(); h.maf = maf.data(); h.n_used = n_used.data();
+    h.status = status.data(); h.catch_code = catch_code.data(); h.catch_var = catch_var.data(); h.iterations = iterations.data();
+    return h;
+  }
+};
 
 }  // namespace gwsem
 
@@ -418,19 +500,95 @@ int gwsem_gwas_run(gwsem_model* m, gwsem_source* s, const gwsem_job* job, int64_
     Stager sg(e, s);
     const bool hard_file = s->kind == gwsem_source::kPgen && !s->any_dosage;
     int batch = job->batch_snps > 0 ? job->batch_snps
-                                    : (int)(hard_file ? std::min<int64_t>(1 << 15, std::max<int64_t>(64, (256ll << 20) / sg.pitch))
+                                    : (int)(hard_file ? std::min<int64_t>(1 << 15, std::max<int64_t>(64, (sg.fixed_width() ? 96ll << 20 : 256ll << 20) / sg.pitch))
                                                       : std::min<int64_t>(4096, std::max<int64_t>(16, (512ll << 20) / (8ll * sg.n_pad))));
-    std::vector<double> h_est, h_vcov, h_fit, h_maf;
-    std::vector<int32_t> h_n, h_status, h_catch, h_cvar, h_iter;
+    RowBatch rb[2];
+    std::future<void> pending;  // formatting + writing of the previous batch
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    // rows [k0, k1) of batch b as text
+    auto format_rows = [&](const RowBatch& b, int k0, int k1, const char* tbuf, std::string& line) {
+      for (int k = k0; k < k1; ++k) {
+        const bool caught = b.catch_code[k] != GWSEM_CATCH_NONE;
+        line += std::to_string(b.iterations[k] + 1);  // objective evaluations are not tracked separately
+        line += '\t';
+        line += std::to_string(b.iterations[k]);
+        line += '\t';
+        line += tbuf;
+        line += '\t';
+        line += std::to_string(b.variant[k] + 1);
+        for (int a = 0; a < P; ++a) { line += '\t'; append_double(line, b.est[(size_t)k * P + a]); }
+        line += '\t';
+        append_double(line, b.fit[k]);
+        line += "\tr'Wr\t";
+        line += std::to_string(b.n_used[k]);
+        line += '\t';
+        line += caught ? "NA" : status_text(b.status[k]);
+        for (auto& pr : vc) { line += '\t'; append_double(line, b.vcov[(size_t)k * P * P + (size_t)pr.first * P + pr.second]); }
+        if (s->kind == gwsem_source::kPgen) {
+          if (!ctx.lines.empty()) { line += '\t'; line += ctx.fields(b.variant[k]); }
+        } else {
+          const auto& bv = s->bgen[b.variant[k]];
+          line += '\t'; line += bv.snpid; line += '\t'; line += bv.rsid; line += '\t'; line += bv.chrom; line += '\t';
+          line += std::to_string(bv.pos); line += '\t'; line += bv.a2; line += '\t'; line += bv.a1;
+        }
+        char mbuf[32];
+        snprintf(mbuf, sizeof(mbuf), "\t%.8f\t", b.maf[k]);  // loader.cpp:404
+        line += mbuf;
+        if (b.catch_code[k] == GWSEM_CATCH_MIN_VARIANCE) {
+          char cbuf[256];
+          const char* var = (job->manifest_names && b.catch_var[k] >= 0) ? job->manifest_names[b.catch_var[k]] : "?";
+          snprintf(cbuf, sizeof(cbuf), "%s.data: '%s' has observed variance less than %g", job->model_name ? job->model_name : "model",
+                   var, m->min_variance);
+          line += cbuf;
+        } else if (b.catch_code[k] == GWSEM_CATCH_ACOV_NOT_PD) {
+          line += job->model_name ? job->model_name : "model";
+          line += ".data: asymptotic covariance matrix is not positive definite";
+        }
+        line += '\n';
+      }
+    };
+    auto write_batch = [&](const RowBatch& b) {
+      char tbuf[64];
+      time_t now = time(nullptr);
+      struct tm tmv;
+      localtime_r(&now, &tmv);
+      strftime(tbuf, sizeof(tbuf), "%b %d %Y %I:%M:%S %p", &tmv);
+      const int parts = (int)std::min<int64_t>(std::min(hw, 32u), std::max(1, b.n / 256));
+      std::vector<std::string> text(parts);
+      std::vector<std::thread> pool;
+      for (int t = 1; t < parts; ++t)
+        pool.emplace_back([&, t] { format_rows(b, (int)((int64_t)b.n * t / parts), (int)((int64_t)b.n * (t + 1) / parts), tbuf, text[t]); });
+      format_rows(b, 0, b.n / parts, tbuf, text[0]);
+      for (auto& th : pool) th.join();
+      for (auto& part : text)
+        if (fwrite(part.data(), 1, part.size(), fo) != part.size()) fail("write error on %s", job->out_path);
+    };
     DeviceBuffer<double> d_geno, d_maf;
     int64_t written = 0;
-    char tbuf[64];
+    // fixed-width files: a helper thread reads batch k+1 into pinned memory while batch k is on the device
+    const bool ahead = sg.fixed_width();
+    std::future<void> reading;
+    auto start_read = [&](size_t at) {
+      if (at >= todo.size()) return;
+      const int cnt = (int)std::min<size_t>(batch, todo.size() - at);
+      const int slot = (int)((at / batch) & 1);
+      reading = std::async(std::launch::async, [&sg, &todo, at, cnt, slot] { sg.read_fixed(&todo[at], cnt, slot); });
+    };
+    if (ahead) {
+      sg.ensure_fixed((int)std::min<size_t>(batch, todo.size()));
+      start_read(0);
+    }
     for (size_t t0 = 0; t0 < todo.size(); t0 += batch) {
       const int n = (int)std::min<size_t>(batch, todo.size() - t0);
       const uint32_t* v = &todo[t0];
       m->ensure_result_buffers(n);
       gwsem_result dres = m->device_result();
-      if (s->kind == gwsem_source::kPgen) {
+      if (ahead) {
+        reading.get();
+        sg.upload_fixed(n, (int)((t0 / batch) & 1));
+        start_read(t0 + batch);
+        m->fit_2bit_device(sg.d_rows.p, sg.pitch, n, sg.plink1, dres);
+      } else if (s->kind == gwsem_source::kPgen) {
         sg.stage_pgen(v, n);
         if (!sg.has_dosage) {
           m->fit_2bit_device(sg.d_rows.p, sg.pitch, n, sg.plink1, dres);
@@ -453,61 +611,16 @@ int gwsem_gwas_run(gwsem_model* m, gwsem_source* s, const gwsem_job* job, int64_
         sg.check_bgen_errors(n);
         m->fit_rows_device(d_geno.p, d_maf.p, n, dres);
       }
-      h_est.resize((size_t)n * P); h_vcov.resize((size_t)n * P * P); h_fit.resize(n); h_maf.resize(n);
-      h_n.resize(n); h_status.resize(n); h_catch.resize(n); h_cvar.resize(n); h_iter.resize(n);
-      gwsem_result h;
-      h.est = h_est.data(); h.vcov = h_vcov.data(); h.fit = h_fit.data(); h.maf = h_maf.data(); h.n_used = h_n.data();
-      h.status = h_status.data(); h.catch_code = h_catch.data(); h.catch_var = h_cvar.data(); h.iterations = h_iter.data();
-      m->download_result(h, dres, n, 0);
+      if (pending.valid()) pending.get();  // at most one batch in flight behind the device
+      RowBatch& cur = rb[(t0 / batch) & 1];
+      cur.resize(n, P);
+      std::copy(v, v + n, cur.variant.begin());
+      m->download_result(cur.view(), dres, n, 0);
       GW_CUDA(cudaStreamSynchronize(st));
-
-      time_t now = time(nullptr);
-      struct tm tmv;
-      localtime_r(&now, &tmv);
-      strftime(tbuf, sizeof(tbuf), "%b %d %Y %I:%M:%S %p", &tmv);
-      line.clear();
-      for (int k = 0; k < n; ++k) {
-        const bool caught = h_catch[k] != GWSEM_CATCH_NONE;
-        line += std::to_string(h_iter[k] + 1);  // objective evaluations are not tracked separately
-        line += '\t';
-        line += std::to_string(h_iter[k]);
-        line += '\t';
-        line += tbuf;
-        line += '\t';
-        line += std::to_string(v[k] + 1);
-        for (int a = 0; a < P; ++a) { line += '\t'; append_double(line, h_est[(size_t)k * P + a]); }
-        line += '\t';
-        append_double(line, h_fit[k]);
-        line += "\tr'Wr\t";
-        line += std::to_string(h_n[k]);
-        line += '\t';
-        line += caught ? "NA" : status_text(h_status[k]);
-        for (auto& pr : vc) { line += '\t'; append_double(line, h_vcov[(size_t)k * P * P + (size_t)pr.first * P + pr.second]); }
-        if (s->kind == gwsem_source::kPgen) {
-          if (!ctx.lines.empty()) { line += '\t'; line += ctx.fields(v[k]); }
-        } else {
-          const auto& bv = s->bgen[v[k]];
-          line += '\t'; line += bv.snpid; line += '\t'; line += bv.rsid; line += '\t'; line += bv.chrom; line += '\t';
-          line += std::to_string(bv.pos); line += '\t'; line += bv.a2; line += '\t'; line += bv.a1;
-        }
-        char mbuf[32];
-        snprintf(mbuf, sizeof(mbuf), "\t%.8f\t", h_maf[k]);  // loader.cpp:404
-        line += mbuf;
-        if (h_catch[k] == GWSEM_CATCH_MIN_VARIANCE) {
-          char cbuf[256];
-          const char* var = (job->manifest_names && h_cvar[k] >= 0) ? job->manifest_names[h_cvar[k]] : "?";
-          snprintf(cbuf, sizeof(cbuf), "%s.data: '%s' has observed variance less than %g", job->model_name ? job->model_name : "model",
-                   var, m->min_variance);
-          line += cbuf;
-        } else if (h_catch[k] == GWSEM_CATCH_ACOV_NOT_PD) {
-          line += job->model_name ? job->model_name : "model";
-          line += ".data: asymptotic covariance matrix is not positive definite";
-        }
-        line += '\n';
-      }
-      fwrite(line.data(), 1, line.size(), fo);
+      pending = std::async(std::launch::async, [&write_batch, &cur] { write_batch(cur); });
       written += n;
     }
+    if (pending.valid()) pending.get();
     fclose(fo);
     if (rows_written) *rows_written = written;
   });

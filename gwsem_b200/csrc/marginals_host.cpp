@@ -10,12 +10,35 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <exception>
+#include <thread>
+#include <vector>
 
 #include "common.h"
 
 namespace gwsem {
 
 namespace {
+
+// Runs body(chunk, begin, end) over a fixed partition of [0, n) into kChunks ranges on up to
+// kChunks host threads.  The partition does not depend on the machine, so sums that are combined
+// in chunk order are reproducible from run to run and from host to host.
+constexpr int kChunks = 32;
+template <typename Body>
+void for_chunks(int n, Body body) {
+  const int threads = (int)std::min<unsigned>(kChunks, std::max(1u, std::thread::hardware_concurrency()));
+  std::vector<std::thread> pool;
+  std::vector<std::exception_ptr> err(threads);
+  auto work = [&](int t) {
+    try {
+      for (int c = t; c < kChunks; c += threads) body(c, (int)((int64_t)n * c / kChunks), (int)((int64_t)n * (c + 1) / kChunks));
+    } catch (...) { err[t] = std::current_exception(); }
+  };
+  for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
+  work(0);
+  for (auto& th : pool) th.join();
+  for (auto& e : err) if (e) std::rethrow_exception(e);
+}
 
 constexpr double kZmax = 12.0;
 const double kInvSqrt2Pi = 0.3989422804014327;
@@ -159,29 +182,40 @@ void MargItem::fit(const std::vector<int>& rows, const std::vector<const double*
   std::vector<double> g(d), H(d * d), j1(d), j0(d);
   bool converged = false;
   for (int it = 0; it < 100; ++it) {
-    std::fill(g.begin(), g.end(), 0.0);
-    std::fill(H.begin(), H.end(), 0.0);
-    for (int r : rows) {
-      const int c = (int)values[r];
-      double eta = 0;
-      for (int k = 0; k < K; ++k) eta += par[C - 1 + k] * X[k][r];
-      const double z1 = (c < C - 1 ? par[c] : kZmax) - eta, z0 = (c > 0 ? par[c - 1] : -kZmax) - eta;
-      const double p1 = c < C - 1 ? phi(z1) : 0.0, p0 = c > 0 ? phi(z0) : 0.0;
-      const double pi = Phi(z1) - Phi(z0);
-      std::fill(j1.begin(), j1.end(), 0.0);
-      std::fill(j0.begin(), j0.end(), 0.0);
-      if (c < C - 1) j1[c] = 1;
-      if (c > 0) j0[c - 1] = 1;
-      for (int k = 0; k < K; ++k) j1[C - 1 + k] = j0[C - 1 + k] = -X[k][r];
-      const double d1 = -z1 * p1, d0 = -z0 * p0;
-      for (int a = 0; a < d; ++a) {
-        const double ga = (p1 * j1[a] - p0 * j0[a]) / pi;
-        g[a] += ga;
-        for (int b = 0; b < d; ++b) {
-          const double gb = (p1 * j1[b] - p0 * j0[b]) / pi;
-          H[a * d + b] += ga * gb - (d1 * j1[a] * j1[b] - d0 * j0[a] * j0[b]) / pi;
+    std::vector<double> gp((size_t)kChunks * d, 0.0), Hp((size_t)kChunks * d * d, 0.0);
+    for_chunks(n, [&](int chunk, int lo_i, int hi_i) {
+      double* gc = &gp[(size_t)chunk * d];
+      double* Hcn = &Hp[(size_t)chunk * d * d];
+      std::vector<double> j1(d), j0(d);
+      for (int ri = lo_i; ri < hi_i; ++ri) {
+        const int r = rows[ri];
+        const int c = (int)values[r];
+        double eta = 0;
+        for (int k = 0; k < K; ++k) eta += par[C - 1 + k] * X[k][r];
+        const double z1 = (c < C - 1 ? par[c] : kZmax) - eta, z0 = (c > 0 ? par[c - 1] : -kZmax) - eta;
+        const double p1 = c < C - 1 ? phi(z1) : 0.0, p0 = c > 0 ? phi(z0) : 0.0;
+        const double pi = Phi(z1) - Phi(z0);
+        std::fill(j1.begin(), j1.end(), 0.0);
+        std::fill(j0.begin(), j0.end(), 0.0);
+        if (c < C - 1) j1[c] = 1;
+        if (c > 0) j0[c - 1] = 1;
+        for (int k = 0; k < K; ++k) j1[C - 1 + k] = j0[C - 1 + k] = -X[k][r];
+        const double d1 = -z1 * p1, d0 = -z0 * p0;
+        for (int a = 0; a < d; ++a) {
+          const double ga = (p1 * j1[a] - p0 * j0[a]) / pi;
+          gc[a] += ga;
+          for (int b = 0; b < d; ++b) {
+            const double gb = (p1 * j1[b] - p0 * j0[b]) / pi;
+            Hcn[a * d + b] += ga * gb - (d1 * j1[a] * j1[b] - d0 * j0[a] * j0[b]) / pi;
+          }
         }
       }
+    });
+    std::fill(g.begin(), g.end(), 0.0);
+    std::fill(H.begin(), H.end(), 0.0);
+    for (int chunk = 0; chunk < kChunks; ++chunk) {
+      for (int a = 0; a < d; ++a) g[a] += gp[(size_t)chunk * d + a];
+      for (int e = 0; e < d * d; ++e) H[e] += Hp[(size_t)chunk * d * d + e];
     }
     if (converged) {  // one more evaluation at the estimate: keep its exact information
       hess = H;
@@ -299,8 +333,14 @@ void MarginalsHost::build(const std::vector<int>& rows) {
       return dd / P;
     };
     auto total = [&](double rh) {
+      double part[kChunks] = {0};
+      for_chunks((int)rows.size(), [&](int chunk, int lo_i, int hi_i) {
+        double sum = 0;
+        for (int ri = lo_i; ri < hi_i; ++ri) sum += person(rows[ri], rh, nullptr, nullptr);
+        part[chunk] = sum;
+      });
       double sum = 0;
-      for (int r : rows) sum += person(r, rh, nullptr, nullptr);
+      for (double v : part) sum += v;
       return sum;
     };
     double start = 0;
@@ -325,23 +365,35 @@ void MarginalsHost::build(const std::vector<int>& rows) {
         for (int k = 0; k < K; ++k) o[C - 1 + k] += sc * (-X[k][r]) * (dl[0] + dl[1]);
       }
     };
-    double dla[2], dlb[2];
-    for (int r : rows) {
-      dla[0] = dla[1] = dlb[0] = dlb[1] = 0;
-      const double sc = person(r, rh, dla, dlb);
-      sc0[(size_t)r * q0 + n1 + pk] = sc;
-      chain(a, ia, r, dla, sc, &A21[pk * (size_t)n1]);
-      chain(b, ib, r, dlb, sc, &A21[pk * (size_t)n1]);
-    }
+    std::vector<double> a21p((size_t)kChunks * n1, 0.0);
+    for_chunks((int)rows.size(), [&](int chunk, int lo_i, int hi_i) {
+      double dla[2], dlb[2];
+      for (int ri = lo_i; ri < hi_i; ++ri) {
+        const int r = rows[ri];
+        dla[0] = dla[1] = dlb[0] = dlb[1] = 0;
+        const double sc = person(r, rh, dla, dlb);
+        sc0[(size_t)r * q0 + n1 + pk] = sc;
+        chain(a, ia, r, dla, sc, &a21p[(size_t)chunk * n1]);
+        chain(b, ib, r, dlb, sc, &a21p[(size_t)chunk * n1]);
+      }
+    });
+    for (int chunk = 0; chunk < kChunks; ++chunk)
+      for (int e = 0; e < n1; ++e) A21[pk * (size_t)n1 + e] += a21p[(size_t)chunk * n1 + e];
   }
   // B00 = sum of outer products of the score rows
   B00.assign((size_t)q0 * q0, 0.0);
-  for (int r : rows) {
-    const double* sc = &sc0[(size_t)r * q0];
-    for (int a = 0; a < q0; ++a)
-      if (sc[a] != 0.0)
-        for (int b = 0; b < q0; ++b) B00[(size_t)a * q0 + b] += sc[a] * sc[b];
-  }
+  std::vector<double> bp((size_t)kChunks * q0 * q0, 0.0);
+  for_chunks((int)rows.size(), [&](int chunk, int lo_i, int hi_i) {
+    double* Bc = &bp[(size_t)chunk * q0 * q0];
+    for (int ri = lo_i; ri < hi_i; ++ri) {
+      const double* sc = &sc0[(size_t)rows[ri] * q0];
+      for (int a = 0; a < q0; ++a)
+        if (sc[a] != 0.0)
+          for (int b = 0; b < q0; ++b) Bc[(size_t)a * q0 + b] += sc[a] * sc[b];
+    }
+  });
+  for (int chunk = 0; chunk < kChunks; ++chunk)
+    for (size_t e = 0; e < (size_t)q0 * q0; ++e) B00[e] += bp[(size_t)chunk * q0 * q0 + e];
 }
 
 }  // namespace gwsem
