@@ -35,6 +35,10 @@ struct FitProgram {
   const int32_t* thr_par = nullptr;
   const double* thr_val = nullptr;
   const int32_t* exo_latent = nullptr;
+  // ML only: covariates (moment variables p .. p + n_exo - 1), which manifest variables are
+  // SNP-independent, whether the genotype is an exogenous covariate (and which one)
+  int n_exo = 0, snp_exo = 0, snp_exo_index = 0;
+  const int32_t* man_static = nullptr;
 };
 
 size_t fit_scratch_doubles(int p, int q, int nv, int P, int nf);

@@ -519,7 +519,7 @@ int gwsem_gwas_run(gwsem_model* m, gwsem_source* s, const gwsem_job* job, int64_
         for (int a = 0; a < P; ++a) { line += '\t'; append_double(line, b.est[(size_t)k * P + a]); }
         line += '\t';
         append_double(line, b.fit[k]);
-        line += "\tr'Wr\t";
+        line += m->fit_kind == 2 ? "\t-2lnL\t" : "\tr'Wr\t";
         line += std::to_string(b.n_used[k]);
         line += '\t';
         line += caught ? "NA" : status_text(b.status[k]);
@@ -536,7 +536,7 @@ int gwsem_gwas_run(gwsem_model* m, gwsem_source* s, const gwsem_job* job, int64_
         line += mbuf;
         if (b.catch_code[k] == GWSEM_CATCH_MIN_VARIANCE) {
           char cbuf[256];
-          const char* var = (job->manifest_names && b.catch_var[k] >= 0) ? job->manifest_names[b.catch_var[k]] : "?";
+          const char* var = b.catch_var[k] == -2 ? "snp" : (job->manifest_names && b.catch_var[k] >= 0) ? job->manifest_names[b.catch_var[k]] : "?";
           snprintf(cbuf, sizeof(cbuf), "%s.data: '%s' has observed variance less than %g", job->model_name ? job->model_name : "model",
                    var, m->min_variance);
           line += cbuf;

@@ -46,6 +46,10 @@ void launch_power_sums(gwsem_engine* e, const FitProgram& fp, const PeopleLayout
 void launch_fit_cumulants(gwsem_engine* e, const FitProgram& fp, int n_snps, const double* d_R, const int32_t* d_n,
                           const double* d_maf, const gwsem_result& d_res);
 
+// ML / FIML from the raw moment table (order-2 moment program over manifest variables + covariates)
+void launch_fit_ml(gwsem_engine* e, const FitProgram& fp, int n_snps, const double* d_R, const int32_t* d_n,
+                   const double* d_maf, const gwsem_result& d_res);
+
 // ---- marginals.cu / marg_fit.cu : WLS "marginals" path (ordinal items, exogenous covariates)
 struct MargProgram;
 void launch_marg_stats(gwsem_engine* e, const MargProgram& mp, const uint8_t* d_rows, int64_t pitch, int n_snps,

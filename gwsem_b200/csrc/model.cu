@@ -27,7 +27,7 @@ static const T* upload_vec(std::vector<DeviceBuffer<uint8_t>>& pool, const std::
 using namespace gwsem;
 
 gwsem_model::gwsem_model(gwsem_engine* e, const gwsem_model_spec* s) : engine(e) {
-  if (s->fit != 0 && s->fit != 1) fail("the ML fit function (fit=2) is not implemented on the device yet");
+  if (s->fit < 0 || s->fit > 2) fail("unknown fit function %d", s->fit);
   fit_kind = s->fit;
   nv = s->n_vars;
   p = s->n_manifest;
@@ -55,6 +55,37 @@ gwsem_model::gwsem_model(gwsem_engine* e, const gwsem_model_spec* s) : engine(e)
     }
     var_base[v] = it->second;
     if (kind[v] == 2) used_as_moderator[it->second] = true;
+  }
+  pm = p;
+  if (fit_kind == 2) {
+    // ML: the definition-variable covariates join the manifest variables as moment variables
+    // (second-order moments of [1, covariates, manifest] are the sufficient statistics).  A covariate
+    // without a data column is the genotype itself (buildItem's default exogenous = TRUE under ML).
+    moment_order = 2;
+    for (int v = 0; v < p; ++v)
+      if (s->n_categories && s->n_categories[v] > 0) fail("ML with ordinal items is not implemented (continuous manifest variables only)");
+    exo_latent.assign(s->exo_latent, s->exo_latent + s->n_exo);
+    for (int k = 0; k < s->n_exo; ++k) {
+      const double* col = s->exo_data[k];
+      if (!col) {
+        if (snp_exo >= 0) fail("ML: more than one exogenous covariate without data");
+        snp_exo = k;
+        kind.push_back(1);
+        var_base.push_back(-1);
+      } else {
+        auto it = base_of.find(col);
+        if (it == base_of.end()) {
+          it = base_of.emplace(col, (int)base.size()).first;
+          base.emplace_back(col, col + n_rows);
+          used_as_moderator.push_back(false);
+        }
+        kind.push_back(0);
+        var_base.push_back(it->second);
+      }
+    }
+    pm = p + s->n_exo;
+    for (int v = 0; v < p; ++v)
+      if (snp_exo >= 0 && kind[v] != 0) fail("ML: snp cannot be both a manifest variable and an exogenous covariate");
   }
   // naAction='omit' on the SNP-independent columns is static: drop those people once
   row_ok.assign(n_rows, 1);
@@ -99,8 +130,9 @@ gwsem_model::gwsem_model(gwsem_engine* e, const gwsem_model_spec* s) : engine(e)
     feature_monos.assign(1, {});
     return;
   }
-  // centre the pure phenotype columns (covariances are shift invariant; keeps moments well scaled)
-  for (size_t b = 0; b < base.size(); ++b) {
+  // centre the pure phenotype columns (covariances are shift invariant; keeps moments well scaled);
+  // not under ML, whose mean structure is in the data's own units
+  for (size_t b = 0; b < base.size() && fit_kind == 0; ++b) {
     if (used_as_moderator[b]) continue;
     long double sum = 0;
     long cnt = 0;
@@ -112,9 +144,11 @@ gwsem_model::gwsem_model(gwsem_engine* e, const gwsem_model_spec* s) : engine(e)
   build_program();
 }
 
-// Enumerate every multiset of <= 4 manifest variables; each is g^a times a monomial of base columns.
+// Enumerate every multiset of <= moment_order moment variables (manifest variables, plus the
+// covariates under ML); each is g^a times a monomial of base columns.  idx4 is indexed by the
+// sorted multiset padded with pm (= "none") in base pm + 1.
 void gwsem_model::build_program() {
-  const int p1 = p + 1;
+  const int p1 = pm + 1;
   q = p * (p + 1) / 2;
   std::map<std::vector<int>, int> mono_id;  // monomial (sorted base columns) -> provisional id
   std::vector<std::vector<int>> monos;
@@ -129,25 +163,33 @@ void gwsem_model::build_program() {
   };
   intern({});  // the constant
   struct Slot { int a, mono; };
-  std::vector<Slot> slot((size_t)p1 * p1 * p1 * p1, Slot{-1, -1});
-  int v[4];
-  for (v[0] = 0; v[0] <= p; ++v[0])
-    for (v[1] = v[0]; v[1] <= p; ++v[1])
-      for (v[2] = v[1]; v[2] <= p; ++v[2])
-        for (v[3] = v[2]; v[3] <= p; ++v[3]) {
-          if (v[0] == p) continue;  // empty multiset
-          int a = 0;
-          std::vector<int> m;
-          for (int k = 0; k < 4; ++k) {
-            if (v[k] == p) continue;
-            if (kind[v[k]] != 0) ++a;
-            if (var_base[v[k]] >= 0) m.push_back(var_base[v[k]]);
-          }
-          std::sort(m.begin(), m.end());
-          const int id = intern(m);
-          if (a >= 1) dense[id] = true;
-          slot[((v[0] * p1 + v[1]) * p1 + v[2]) * p1 + v[3]] = Slot{a, id};
-        }
+  size_t n_slots = 1;
+  for (int k = 0; k < moment_order; ++k) n_slots *= p1;
+  std::vector<Slot> slot(n_slots, Slot{-1, -1});
+  std::vector<int> v(moment_order, 0);
+  // odometer over non-decreasing tuples
+  while (true) {
+    if (v[0] != pm) {
+      int a = 0;
+      std::vector<int> m;
+      size_t at = 0;
+      for (int k = 0; k < moment_order; ++k) {
+        at = at * p1 + v[k];
+        if (v[k] == pm) continue;
+        if (kind[v[k]] != 0) ++a;
+        if (var_base[v[k]] >= 0) m.push_back(var_base[v[k]]);
+      }
+      std::sort(m.begin(), m.end());
+      const int id = intern(m);
+      if (a >= 1) dense[id] = true;
+      slot[at] = Slot{a, id};
+    }
+    int k = moment_order - 1;
+    while (k >= 0 && v[k] == pm) --k;
+    if (k < 0) break;
+    const int nv2 = v[k] + 1;
+    for (int j = k; j < moment_order; ++j) v[j] = nv2;
+  }
   // final order: constant, dense monomials, the rest
   std::vector<int> order(monos.size()), rank(monos.size());
   for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
@@ -262,6 +304,40 @@ void gwsem_model::prepare(const int32_t* row_filter, int src_rows) {
   if (fit_kind == 1) prepare_marginals(dest_of);
   GW_CUDA(cudaStreamSynchronize(st));
   prepared = true;
+  if (fit_kind == 2) prepare_ml();
+}
+
+// ML: covariate bookkeeping for the kernel, and the per-model warm start (see prepare_marginals:
+// the estimates for a reference genotype column, fitted once from the model's own start values).
+void gwsem_model::prepare_ml() {
+  cudaStream_t st = engine->stream;
+  std::vector<int32_t> man_static(p);
+  for (int i = 0; i < p; ++i) man_static[i] = kind[i] == 0;
+  fp.n_exo = (int)exo_latent.size();
+  fp.exo_latent = upload_vec(pool, exo_latent, st);
+  fp.man_static = upload_vec(pool, man_static, st);
+  fp.snp_exo = snp_exo >= 0;
+  fp.snp_exo_index = std::max(snp_exo, 0);
+  fp.par_warm = nullptr;
+  const int64_t rb = (n_pad / 4 + 15) / 16 * 16;
+  std::vector<uint8_t> ref(rb, 0);
+  for (int i = 0; i < n_src; ++i) ref[i >> 2] |= (uint8_t)((i % 3) << (2 * (i & 3)));
+  const uint8_t* d_ref = upload_vec(pool, ref, st);
+  DeviceBuffer<double> dd;
+  DeviceBuffer<int32_t> di;
+  dd.ensure((size_t)P + (size_t)P * P + 2);
+  di.ensure(5);
+  gwsem_result r;
+  r.est = dd.p; r.vcov = dd.p + P; r.fit = dd.p + P + (size_t)P * P; r.maf = r.fit + 1;
+  r.n_used = di.p; r.status = di.p + 1; r.catch_code = di.p + 2; r.catch_var = di.p + 3; r.iterations = di.p + 4;
+  fit_2bit_device(d_ref, rb, 1, 0, r);
+  int32_t flags[5];
+  std::vector<double> warm(P);
+  GW_CUDA(cudaMemcpyAsync(flags, di.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
+  GW_CUDA(cudaMemcpyAsync(warm.data(), dd.p, P * sizeof(double), cudaMemcpyDeviceToHost, st));
+  GW_CUDA(cudaStreamSynchronize(st));
+  if (flags[1] == GWSEM_STATUS_OK && flags[2] == GWSEM_CATCH_NONE) fp.par_warm = upload_vec(pool, warm, st);
+  GW_CUDA(cudaStreamSynchronize(st));
 }
 
 void gwsem_model::fit_2bit_device(const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
@@ -291,7 +367,8 @@ void gwsem_model::fit_2bit_device(const uint8_t* d_packed, int64_t pitch, int n_
     r.est += (size_t)s0 * P; r.vcov += (size_t)s0 * P * P; r.fit += s0; r.maf += s0; r.n_used += s0;
     r.status += s0; r.catch_code += s0; r.catch_var += s0; r.iterations += s0;
     launch_assemble_moments(engine, fp, layout, n, d_counts.p, d_sums.p, d_miss.p, d_R.p, d_nrows.p, d_mafs.p);
-    launch_fit_cumulants(engine, fp, n, d_R.p, d_nrows.p, d_mafs.p, r);
+    if (fit_kind == 2) launch_fit_ml(engine, fp, n, d_R.p, d_nrows.p, d_mafs.p, r);
+    else launch_fit_cumulants(engine, fp, n, d_R.p, d_nrows.p, d_mafs.p, r);
   }
 }
 
@@ -315,7 +392,8 @@ void gwsem_model::fit_rows_device(const double* d_geno, const double* d_maf, int
     gwsem_result r = d_res;
     r.est += (size_t)s0 * P; r.vcov += (size_t)s0 * P * P; r.fit += s0; r.maf += s0; r.n_used += s0;
     r.status += s0; r.catch_code += s0; r.catch_var += s0; r.iterations += s0;
-    launch_fit_cumulants(engine, fp, n, d_R.p, d_nrows.p, d_maf + s0, r);
+    if (fit_kind == 2) launch_fit_ml(engine, fp, n, d_R.p, d_nrows.p, d_maf + s0, r);
+    else launch_fit_cumulants(engine, fp, n, d_R.p, d_nrows.p, d_maf + s0, r);
   }
 }
 

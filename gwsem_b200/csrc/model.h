@@ -19,6 +19,8 @@ struct gwsem_model {
   std::vector<uint8_t> row_ok;            // complete phenotype row
   // moment program
   int nf = 0, nfd = 0, nfm = 0, nfm_pad = 0;
+  int pm = 0;             // moment variables: the manifest variables (+ the covariates under ML)
+  int moment_order = 4;   // 4: cumulants (fourth-order moments); 2: ML
   std::vector<std::vector<int>> feature_monos;
   std::vector<int32_t> idx4, stat_i, stat_j;
   // people axis / device state
@@ -39,8 +41,9 @@ struct gwsem_model {
   gwsem::DeviceBuffer<double> r_est, r_vcov, r_fit, r_maf;
   gwsem::DeviceBuffer<int32_t> r_n, r_status, r_catch, r_cvar, r_iter;
 
-  // WLS marginals (fit == 1)
+  // WLS marginals (fit == 1), ML (fit == 2)
   int fit_kind = 0;
+  void prepare_ml();
   int marg_mode = 0;   // 0: snp is a manifest variable; 1: snp is an exogenous predictor of one ordinal item
   int snp_exo = -1;    // which exogenous covariate is the genotype column (mode 1)
   gwsem::ProbitProgram pp;

@@ -139,16 +139,17 @@ def GWAS(model, snpData, out="out.log", *dots, SNP=None, startFrom=1, rowFilter=
     else:
         src_rows = n_rows
     flat = flatten(model)
+    data, n_categories = model_columns(model)
     if flat["fitfun"] != "WLS":
-        raise NotImplementedError("fitfun='ML' is not implemented on the device yet; only WLS models run")
-    if flat["continuous_type"] == "marginals":
+        if any(n_categories.get(m, 0) > 0 for m in flat["manifest"]):
+            raise NotImplementedError("fitfun='ML' with ordinal items is not implemented (continuous items only)")
+    elif flat["continuous_type"] == "marginals":
         snp_exo_item = "snp" in flat["exo_pred"] and len(flat["manifest"]) == 1
         if model.gxe or not (flat["manifest"][0] == "snp" or snp_exo_item):
             raise NotImplementedError("WLS marginals is implemented for models whose first manifest variable is snp "
                                       "(buildOneFac / buildOneFacRes / buildTwoFac) and for buildItem with one "
                                       "ordered phenotype; gxe terms under marginals are not implemented")
     eng = _engine(device)
-    data, n_categories = model_columns(model)
     with Source(snpData, method, src_rows) as src:
         gm = Model(eng, flat, data, n_categories)
         try:
