@@ -127,7 +127,7 @@ def test_ml_dosage_rows_and_gwas_log(engine, tmp_path):
     ph = pd.DataFrame({"pc1": rng.normal(size=500), "E": rng.integers(0, 2, 500).astype(float)})
     for k in range(1, 5):
         ph[f"i{k}"] = ps["phenotype"] * (0.4 + 0.1 * k) + 0.1 * ph["pc1"] + rng.normal(size=500)
-    model = buildTwoFac(ph, ["i1", "i2"], ["i3", "i4"], gxe="E", covariates=["pc1"], fitfun="ML")
+    model = buildOneFac(ph, ["i1", "i2", "i3", "i4"], gxe="E", covariates=["pc1"], fitfun="ML")
     flat = flatten(model)
     data, ncat = model_columns(model)
     pick = [1, 2, 77, 199]
