@@ -278,18 +278,44 @@ __global__ void __launch_bounds__(32)
   // ---- Newton iterations
   double *theta = sm + ms.theta, *cand = sm + ms.cand, *g = sm + ms.g, *g1 = sm + ms.g1, *g2 = sm + ms.g2;
   double *delta = sm + ms.delta, *H = sm + ms.H, *Hc = sm + ms.Hc;
-  for (int k = lane; k < P; k += LANES) theta[k] = fp.par_warm ? fp.par_warm[k] : fp.par_start[k];
-  gsync<LANES>();
+  // Start: the per-model warm start (or the model's start values), with the free mean and variance
+  // of every SNP-dependent manifest variable that nothing points at moved to this SNP's sample
+  // moments: they are what changes most from SNP to SNP (allele frequency).
+  auto load_start = [&](const double* from) {
+    for (int k = lane; k < P; k += LANES) theta[k] = from[k];
+    gsync<LANES>();
+    if (lane == 0) {
+      const double* b0 = mom;
+      for (int v = 0; v < p; ++v) {
+        if (fp.man_static[v]) continue;
+        bool target = false;
+        for (int e = 0; e < fp.n_cells; ++e)
+          if (fp.cell_mat[e] == 0 && fp.cell_row[e] == v && (fp.cell_par[e] >= 0 || fp.cell_val[e] != 0.0)) target = true;
+        if (target) continue;
+        const double m1 = b0[dw * dw + v] / n, m2 = b0[dw * dw + dw * p + v * p + v] / n;
+        for (int e = 0; e < fp.n_cells; ++e) {
+          const int par = fp.cell_par[e];
+          if (par < 0) continue;
+          if (fp.cell_mat[e] == 2 && fp.cell_col[e] == v) theta[par] = m1;
+          if (fp.cell_mat[e] == 1 && fp.cell_row[e] == v && fp.cell_col[e] == v) {
+            const double lb = fp.par_lbound[par];
+            theta[par] = (lb == lb) ? fmax(lb, m2 - m1 * m1) : m2 - m1 * m1;
+          }
+        }
+      }
+    }
+    gsync<LANES>();
+  };
+  load_start(fp.par_warm ? fp.par_warm : fp.par_start);
   double F = ml_eval(cx, theta, g);
   if (!isfinite(F) && fp.par_warm) {  // the warm start does not suit this SNP: the model's own start values
-    for (int k = lane; k < P; k += LANES) theta[k] = fp.par_start[k];
-    gsync<LANES>();
+    load_start(fp.par_start);
     F = ml_eval(cx, theta, g);
   }
   int status = GWSEM_STATUS_ITERATION_LIMIT, it = 0;
   const double n_all = cx.n_g[0] + cx.n_g[1];
   if (!isfinite(F)) status = GWSEM_STATUS_NONZERO_GRADIENT;
-  // Hessian of -2 lnL by differences of the gradient: forward during the iteration, central at the end
+  // Hessian of -2 lnL by differences of the analytic gradient (forward, relative step 1e-6; central on request)
   auto hessian = [&](bool central) {
     for (int k = 0; k < P; ++k) {
       const double t0 = theta[k];
@@ -320,7 +346,7 @@ __global__ void __launch_bounds__(32)
     gsync<LANES>();
   };
   const int max_iter = 100;
-  double lam = 0.0;
+  double lam = 0.0, last_step = 1.0;
   for (it = 1; it <= max_iter && isfinite(F); ++it) {
     hessian(false);
     bool improved = false;
@@ -362,6 +388,7 @@ __global__ void __launch_bounds__(32)
       double gmax = 0.0;
       for (int k = 0; k < P; ++k) gmax = fmax(gmax, fabs(g[k]));
       status = gmax < 1e-4 * n_all ? GWSEM_STATUS_OK : GWSEM_STATUS_NONZERO_GRADIENT;
+      last_step = 0.0;  // H was taken at this very point
       break;
     }
     double step = 0.0;
@@ -371,12 +398,15 @@ __global__ void __launch_bounds__(32)
     for (int k = lane; k < P; k += LANES) { theta[k] = cand[k]; g[k] = g1[k]; }
     gsync<LANES>();
     F = Fc;
+    last_step = step;
     lam = lam > 1e-8 ? lam / 10 : 0.0;
     if (step < 1e-9 || dF <= 1e-13 * (1 + fabs(F))) { status = GWSEM_STATUS_OK; break; }
   }
   if (it > max_iter) it = max_iter;
   if (isfinite(F)) {
-    hessian(true);
+    // H from the last iteration was taken one step before the estimate; that is the same matrix to
+    // O(step) relative.  Take it again at the estimate unless that step was tiny.
+    if (last_step > 1e-5) hessian(false);
     if (warp_cholesky<LANES>(H, P, lane)) {
       for (int c = lane; c < P; c += LANES) {
         double* x = Hc + c;
