@@ -106,10 +106,10 @@ typedef struct {
   int32_t n_rows;
   const int32_t* manifest_kind;       /* n_manifest: 0 data column, 1 snp, 2 snp * moderator */
   const double* const* manifest_data; /* n_manifest: column (kind 0), moderator (kind 2), NULL (kind 1) */
-  /* ---- WLS marginals only (fit == 1): ordinal items and exogenous covariates */
+  /* ---- WLS marginals (fit == 1) and ML (fit == 2): ordinal items and exogenous covariates */
   const int32_t* n_categories;        /* n_manifest: 0 continuous, C >= 2 ordinal; manifest_data then holds codes 0..C-1 */
   int32_t n_exo;                      /* exogenous covariates (definition variables, R/model.R:403-418) */
-  const double* const* exo_data;      /* n_exo columns of n_rows */
+  const double* const* exo_data;      /* n_exo columns of n_rows; NULL = the genotype itself (buildItem, exogenous = TRUE) */
   const int32_t* exo_latent;          /* n_exo: RAM index of the covariate's latent variable */
   const uint8_t* exo_free;            /* n_manifest x n_exo, row major: slope is a statistic */
   int32_t n_thresholds;
