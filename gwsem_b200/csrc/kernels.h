@@ -1,5 +1,7 @@
 // Internal launch interfaces between the engine's translation units.
 #pragma once
+#include <vector>
+
 #include "common.h"
 
 namespace gwsem {
@@ -24,6 +26,15 @@ struct PeopleLayout {
 // d_sums[snp][2][n_feat].  Launches one kernel per chunk of <= 8 features.
 void launch_class_sums(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
                        const PeopleLayout& pl, const double* d_feat, int n_feat, double* d_sums);
+
+// The same sums as an exact int8 tensor-core contraction (stats_imma.cu): features as four balanced
+// base-256 digits of round(h * 2^s_f), packed by imma_pack_features; d_inv_scale[f] = 2^-s_f.
+int imma_chunk_features(int n_feat);
+size_t imma_feature_bytes(int n_feat, int n_pad);
+void imma_pack_features(const std::vector<std::vector<int64_t>>& q, int n_pad, std::vector<int8_t>& out);
+void launch_class_sums_imma(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
+                            const PeopleLayout& pl, const int8_t* d_featq, const double* d_inv_scale, int n_feat,
+                            double* d_sums);
 
 // counts[snp][8] = {n_class1, n_class2, n_missing over included people; the same three over the
 // people kept by rowFilter (for MAF); 0; 0} and, for the missing class, sums of `n_featm`

@@ -240,13 +240,36 @@ void gwsem_model::prepare(const int32_t* row_filter, int src_rows) {
   const int nfm_pad = std::max(1, (nfm + 3) / 4 * 4);
   std::vector<double> feat((size_t)std::max(nfd, 1) * n_pad, 0.0), featT((size_t)n_pad * nfm_pad, 0.0), tot(nf, 0.0);
   std::vector<long double> acc(nf, 0.0L);
+  // Features that need class sums are rounded to a fixed-point grid 2^-s_f (|h| 2^s_f <= 2^30) and the
+  // rounded values are what every kernel sees: the class sums then are exact integer arithmetic on
+  // the tensor cores (stats_imma.cu) and agree with the totals and the missing-class sums bit for bit.
+  std::vector<double> scale(std::max(nfd, 1), 1.0), inv_scale(std::max(nfd, 1), 1.0);
+  for (int f = 1; f <= nfd; ++f) {
+    double mx = 0.0;
+    for (int s = 0; s < src_rows; ++s) {
+      if (!inc8[s]) continue;
+      double h = 1.0;
+      for (int b : feature_monos[f]) h *= base[b][dest_of[s]];
+      mx = std::max(mx, std::fabs(h));
+    }
+    int ex = 0;
+    if (mx > 0.0) { std::frexp(mx, &ex); }   // mx < 2^ex
+    scale[f - 1] = std::ldexp(1.0, 30 - ex);
+    inv_scale[f - 1] = std::ldexp(1.0, ex - 30);
+  }
+  std::vector<std::vector<int64_t>> fq(nfd, std::vector<int64_t>(n_pad, 0));
   for (int s = 0; s < src_rows; ++s) {
     if (!inc8[s]) continue;
     const int r = dest_of[s];
     for (int f = 1; f < nf; ++f) {
       double h = 1.0;
       for (int b : feature_monos[f]) h *= base[b][r];
-      if (f - 1 < nfd) feat[(size_t)(f - 1) * n_pad + s] = h;
+      if (f - 1 < nfd) {
+        const int64_t qv = std::llrint(h * scale[f - 1]);
+        fq[f - 1][s] = qv;
+        h = (double)qv * inv_scale[f - 1];
+        feat[(size_t)(f - 1) * n_pad + s] = h;
+      }
       featT[(size_t)s * nfm_pad + (f - 1)] = h;
       acc[f] += h;
     }
@@ -299,6 +322,12 @@ void gwsem_model::prepare(const int32_t* row_filter, int src_rows) {
   layout.d_rowmask = upload_vec(pool, rowmask, st);
   layout.n_kept = n_rows;
   d_feat = upload_vec(pool, feat, st);
+  if (nfd > 0) {
+    std::vector<int8_t> packed_q;
+    imma_pack_features(fq, n_pad, packed_q);
+    d_featq = upload_vec(pool, packed_q, st);
+    d_inv_scale = upload_vec(pool, inv_scale, st);
+  }
   d_featT = upload_vec(pool, featT, st);
   d_dest_of = upload_vec(pool, dest_of, st);
   if (fit_kind == 1) prepare_marginals(dest_of);
@@ -362,7 +391,9 @@ void gwsem_model::fit_2bit_device(const uint8_t* d_packed, int64_t pitch, int n_
       continue;
     }
     launch_count_missing(engine, rows, pitch, n, plink1, layout, d_featT, nfm, nfm_pad, d_counts.p, d_miss.p);
-    launch_class_sums(engine, rows, pitch, n, plink1, layout, d_feat, nfd, d_sums.p);
+    static const bool dfma = getenv("GWSEM_CS_DFMA") != nullptr;  // A/B aid: the FP64 class-sum kernel
+    if (dfma) launch_class_sums(engine, rows, pitch, n, plink1, layout, d_feat, nfd, d_sums.p);
+    else launch_class_sums_imma(engine, rows, pitch, n, plink1, layout, d_featq, d_inv_scale, nfd, d_sums.p);
     gwsem_result r = d_res;
     r.est += (size_t)s0 * P; r.vcov += (size_t)s0 * P * P; r.fit += s0; r.maf += s0; r.n_used += s0;
     r.status += s0; r.catch_code += s0; r.catch_var += s0; r.iterations += s0;

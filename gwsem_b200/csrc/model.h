@@ -30,6 +30,8 @@ struct gwsem_model {
   gwsem::PeopleLayout layout;
   const double* d_feat = nullptr;
   const double* d_featT = nullptr;
+  const int8_t* d_featq = nullptr;        // dense features as base-256 digits (stats_imma.cu)
+  const double* d_inv_scale = nullptr;    // 2^-s_f per dense feature
   const int32_t* d_dest_of = nullptr;
   std::vector<gwsem::DeviceBuffer<uint8_t>> pool;
   gwsem::DeviceBuffer<int32_t> d_counts;

@@ -1,0 +1,219 @@
+// Genotype-class sums as an exact integer contraction on the tensor cores.
+//
+//   sums[snp][class][f] = sum over people i with genotype class(i, snp) == class of h_f(i)
+//
+// is the product of a one-hot matrix A [2 * SNPs x people] with the feature matrix B [people x F].
+// The features are fixed-point integers (gwsem_model::prepare rounds every feature to a grid
+// 2^-s_f and the whole engine uses those rounded values), split into four balanced base-256 digits,
+// so B is int8, A is 0/1, and mma.sync m16n8k32 (s8 x s8 -> s32) accumulates exactly: no rounding
+// anywhere, and the result does not depend on summation order.  The digits' partial sums are
+// recombined in FP64 (each below 2^53).
+//
+// Why mma.sync and not tcgen05 here: tcgen05.mma reads A from shared memory (or TMEM), so the
+// one-hot expansion (16x the packed bytes) would have to be written to shared memory first, and
+// that store traffic is the bottleneck.  With mma.sync the A fragment is four registers per thread
+// that are built in place from two packed bytes with a nibble spread and four PRMT table look-ups
+// (PLINK 1 recoding is a different table: free).  The contraction is far from the tensor peak
+// either way; the bound is the packed-row stream from HBM and the integer ALU work of the expansion.
+//
+// Layout.  A warp owns MT m-tiles of 8 SNPs (rows 0-7: het class, rows 8-15: hom-ALT class).  Per
+// 32-person block it loads the 8-byte packed word of its SNP (lane>>2), builds the A fragments and
+// issues NT MMAs per m-tile against the B fragments (shared by the warp's m-tiles).  Packed rows and
+// the int8 feature block are staged in shared memory with cp.async, double buffered.
+#include "common.h"
+#include "kernels.h"
+
+namespace gwsem {
+
+namespace {
+
+constexpr int kGPad = 16;  // bytes of padding per staged genotype row (keeps 16-byte alignment): 8 rows -> 8 different bank groups
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void mma_s8(int (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// NT n-tiles of 8 columns (2 features each), MT m-tiles of 8 SNPs per warp, TILE people per stage.
+template <int NT, int MT, int WARPS, int TILE, bool PLINK1>
+__global__ void __launch_bounds__(WARPS * 32)
+    class_sums_imma_kernel(const uint8_t* __restrict__ rows, int64_t pitch, int n_snps, int n_blocks,
+                           const int8_t* __restrict__ Bq, const double* __restrict__ inv_scale, int f0, int n_feat,
+                           double* __restrict__ sums) {
+  constexpr int kSnps = WARPS * MT * 8;
+  constexpr int kGRow = TILE / 4 + kGPad;            // staged genotype row, bytes
+  constexpr int kBlocks = TILE / 32;                 // 32-person blocks per stage
+  constexpr int kBStage = kBlocks * NT * 8 * 32;     // staged feature bytes
+  constexpr int kGStage = kSnps * kGRow;
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t* Gs[2] = {smem, smem + kGStage + kBStage};
+  uint8_t* Bs[2] = {smem + kGStage, smem + 2 * kGStage + kBStage};
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int snp0 = blockIdx.x * kSnps;
+  const int n_tiles = (n_blocks + kBlocks - 1) / kBlocks;
+
+  auto load_stage = [&](int tile, int s) {
+    // genotype rows: kSnps x (TILE / 4) bytes in 16-byte pieces
+    constexpr int kPieces = TILE / 64;
+    for (int idx = tid; idx < kSnps * kPieces; idx += WARPS * 32) {
+      const int r = idx / kPieces, c = idx % kPieces;
+      const int64_t off = (int64_t)tile * (TILE / 4) + c * 16;
+      const bool ok = snp0 + r < n_snps && off + 16 <= pitch;
+      cp_async16(Gs[s] + r * kGRow + c * 16, rows + (ok ? (int64_t)(snp0 + r) * pitch + off : 0), ok);
+    }
+    // feature block: contiguous kBStage bytes
+    const int64_t base = (int64_t)tile * kBStage, limit = (int64_t)n_blocks * NT * 8 * 32;
+    for (int idx = tid; idx < kBStage / 16; idx += WARPS * 32) {
+      const int64_t off = base + (int64_t)idx * 16;
+      const bool ok = off + 16 <= limit;
+      cp_async16(Bs[s] + idx * 16, Bq + (ok ? off : 0), ok);
+    }
+    cp_async_commit();
+  };
+
+  int acc[MT][NT][4];
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[m][j][k] = 0;
+  // PRMT tables: byte index = 2-bit code; 1 where the code is the class
+  const unsigned tab1 = PLINK1 ? 0x00010000u : 0x00000100u;  // het: PLINK 2 code 1, PLINK 1 code 2
+  const unsigned tab2 = PLINK1 ? 0x00000001u : 0x00010000u;  // hom ALT: PLINK 2 code 2, PLINK 1 code 0
+  const unsigned pick = (unsigned)t | ((unsigned)(4 + t) << 4);  // bytes t of both words of the 64-bit block
+
+  load_stage(0, 0);
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const int s = tile & 1;
+    if (tile + 1 < n_tiles) {
+      load_stage(tile + 1, s ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const uint8_t* Gw = Gs[s] + (warp * MT * 8 + g) * kGRow;
+    const uint8_t* Bw = Bs[s] + g * 32 + t * 8;
+#pragma unroll 2
+    for (int kb = 0; kb < kBlocks; ++kb) {
+      uint2 bf[NT];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) bf[j] = *reinterpret_cast<const uint2*>(Bw + (kb * NT * 8 + j * 8) * 32);
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const uint2 w = *reinterpret_cast<const uint2*>(Gw + m * 8 * kGRow + kb * 8);
+        unsigned x = __byte_perm(w.x, w.y, pick);    // byte 0: people 4t..4t+3, byte 1: people 16+4t..
+        x = __byte_perm(x, 0u, 0x4140);              // 0x00HH00LL
+        x = (x | (x << 4)) & 0x0F0F0F0Fu;
+        x = (x | (x << 2)) & 0x33333333u;            // eight nibbles = eight 2-bit codes
+        const unsigned xh = x >> 16;
+        const unsigned a0 = __byte_perm(tab1, 0u, x), a1 = __byte_perm(tab2, 0u, x);
+        const unsigned a2 = __byte_perm(tab1, 0u, xh), a3 = __byte_perm(tab2, 0u, xh);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) mma_s8(acc[m][j], a0, a1, a2, a3, bf[j].x, bf[j].y);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- recombine the digits: a thread holds digits (0,1) or (2,3) of one feature per n-tile
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    const int snp = snp0 + (warp * MT + m) * 8 + g;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const double w = (t & 1) ? 65536.0 : 1.0;
+      double v1 = ((double)acc[m][j][0] + 256.0 * (double)acc[m][j][1]) * w;   // het
+      double v2 = ((double)acc[m][j][2] + 256.0 * (double)acc[m][j][3]) * w;   // hom ALT
+      v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+      v2 += __shfl_xor_sync(0xffffffffu, v2, 1);
+      const int f = f0 + 2 * j + (t >> 1);
+      if ((t & 1) == 0 && snp < n_snps && f < n_feat) {
+        const double sc = inv_scale[f];
+        sums[((int64_t)snp * 2 + 0) * n_feat + f] = v1 * sc;
+        sums[((int64_t)snp * 2 + 1) * n_feat + f] = v2 * sc;
+      }
+    }
+  }
+}
+
+template <int NT, int MT, int WARPS, int TILE>
+void launch_imma(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1, int n_blocks,
+                 const int8_t* Bq, const double* inv_scale, int f0, int n_feat, double* d_sums) {
+  constexpr int kSnps = WARPS * MT * 8;
+  const size_t smem = 2 * ((size_t)kSnps * (TILE / 4 + kGPad) + (size_t)(TILE / 32) * NT * 8 * 32);
+  const int grid = (n_snps + kSnps - 1) / kSnps;
+  if (plink1) {
+    auto k = class_sums_imma_kernel<NT, MT, WARPS, TILE, true>;
+    GW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, WARPS * 32, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums);
+  } else {
+    auto k = class_sums_imma_kernel<NT, MT, WARPS, TILE, false>;
+    GW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, WARPS * 32, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums);
+  }
+  GW_CUDA(cudaGetLastError());
+  e->launches++;
+}
+
+}  // namespace
+
+int imma_chunk_features(int n_feat) { return n_feat <= 4 ? 4 : 16; }
+
+// Host side of the digit layout: chunk c covers features [c * cf, (c + 1) * cf), cf = imma_chunk_features;
+// within a chunk: [block of 32 people][column = feature_in_chunk * 4 + digit][position], position of
+// person k in the block = 8 * ((k % 16) / 4) + 4 * (k / 16) + k % 4 (the two halves a thread needs are adjacent).
+size_t imma_feature_bytes(int n_feat, int n_pad) {
+  const int cf = imma_chunk_features(n_feat), chunks = (n_feat + cf - 1) / cf;
+  return (size_t)chunks * (n_pad / 32) * (cf * 4) * 32;
+}
+
+void imma_pack_features(const std::vector<std::vector<int64_t>>& q, int n_pad, std::vector<int8_t>& out) {
+  const int n_feat = (int)q.size(), cf = imma_chunk_features(n_feat), chunks = (n_feat + cf - 1) / cf;
+  const int n_blocks = n_pad / 32, ncol = cf * 4;
+  out.assign(imma_feature_bytes(n_feat, n_pad), 0);
+  for (int f = 0; f < n_feat; ++f) {
+    const int c = f / cf, fi = f % cf;
+    int8_t* base = out.data() + (size_t)c * n_blocks * ncol * 32;
+    for (int i = 0; i < n_pad; ++i) {
+      int64_t v = q[f][i];
+      const int blk = i / 32, k = i % 32, pos = 8 * ((k % 16) / 4) + 4 * (k / 16) + k % 4;
+      for (int d = 0; d < 4; ++d) {
+        const int64_t digit = ((v + 128) & 255) - 128;  // balanced digit in [-128, 127]
+        base[((size_t)blk * ncol + fi * 4 + d) * 32 + pos] = (int8_t)digit;
+        v = (v - digit) >> 8;
+      }
+      if (v != 0) fail("feature %d does not fit four balanced base-256 digits", f);
+    }
+  }
+}
+
+void launch_class_sums_imma(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
+                            const PeopleLayout& pl, const int8_t* d_featq, const double* d_inv_scale, int n_feat,
+                            double* d_sums) {
+  if (n_snps <= 0 || n_feat <= 0) return;
+  if (pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(d_packed) & 15))
+    fail("packed genotype rows must be 16-byte aligned with a pitch that is a multiple of 16 (pitch=%lld)",
+         (long long)pitch);
+  const int n_blocks = pl.n_pad / 32, cf = imma_chunk_features(n_feat);
+  e->prof_begin(kFamClassSums);
+  for (int f0 = 0, c = 0; f0 < n_feat; f0 += cf, ++c) {
+    const int8_t* Bq = d_featq + (size_t)c * n_blocks * (cf * 4) * 32;
+    if (cf == 4) launch_imma<2, 4, 4, 1024>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums);
+    else launch_imma<8, 2, 4, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums);
+  }
+  e->prof_end(kFamClassSums);
+}
+
+}  // namespace gwsem
