@@ -324,7 +324,9 @@ void gwsem_model::prepare(const int32_t* row_filter, int src_rows) {
   d_feat = upload_vec(pool, feat, st);
   if (nfd > 0) {
     std::vector<int8_t> packed_q;
-    imma_pack_features(fq, n_pad, packed_q);
+    std::vector<uint8_t> kept8(n_pad, 0);
+    for (int s2 = 0; s2 < src_rows; ++s2) kept8[s2] = dest_of[s2] >= 0;
+    imma_pack_features(fq, n_pad, inc8, kept8, packed_q);
     d_featq = upload_vec(pool, packed_q, st);
     d_inv_scale = upload_vec(pool, inv_scale, st);
   }
@@ -390,10 +392,12 @@ void gwsem_model::fit_2bit_device(const uint8_t* d_packed, int64_t pitch, int n_
       run_marginals(rows, pitch, nullptr, nullptr, n, plink1, r);
       continue;
     }
-    launch_count_missing(engine, rows, pitch, n, plink1, layout, d_featT, nfm, nfm_pad, d_counts.p, d_miss.p);
+    static const bool dfma_first = getenv("GWSEM_CS_DFMA") != nullptr;
+    const bool light = !dfma_first && imma_has_counts(nfd);
+    launch_count_missing(engine, rows, pitch, n, plink1, layout, d_featT, nfm, nfm_pad, d_counts.p, d_miss.p, light);
     static const bool dfma = getenv("GWSEM_CS_DFMA") != nullptr;  // A/B aid: the FP64 class-sum kernel
     if (dfma) launch_class_sums(engine, rows, pitch, n, plink1, layout, d_feat, nfd, d_sums.p);
-    else launch_class_sums_imma(engine, rows, pitch, n, plink1, layout, d_featq, d_inv_scale, nfd, d_sums.p);
+    else launch_class_sums_imma(engine, rows, pitch, n, plink1, layout, d_featq, d_inv_scale, nfd, d_sums.p, d_counts.p);
     gwsem_result r = d_res;
     r.est += (size_t)s0 * P; r.vcov += (size_t)s0 * P * P; r.fit += s0; r.maf += s0; r.n_used += s0;
     r.status += s0; r.catch_code += s0; r.catch_var += s0; r.iterations += s0;

@@ -251,7 +251,10 @@ void launch_class_sums(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, 
 // person-major features over the missing class.  Lanes scan 32-person words; a word with
 // missing calls is handled by the whole warp (lane f accumulates feature f, f+32, ...), people
 // in index order, so the result does not depend on scheduling.
-template <bool PLINK1>
+// LIGHT: the het / hom-ALT counts come from the tensor-core class-sum kernel (indicator columns,
+// stats_imma.cu); only the missing class is counted here, and words without a missing call cost
+// three logic operations.
+template <bool PLINK1, bool LIGHT>
 __global__ void __launch_bounds__(128)
     count_missing_kernel(const uint8_t* __restrict__ packed, int64_t pitch, int n_snps, int n_pad,
                          const unsigned long long* __restrict__ incmask,
@@ -285,13 +288,18 @@ __global__ void __launch_bounds__(128)
       unsigned long long w = wv[k];
       if (PLINK1) w = bed_to_plink2(w);
       const unsigned long long lo = w & 0x5555555555555555ull, hi = (w >> 1) & 0x5555555555555555ull;
-      c1 += __popcll(lo & ~hi & iv[k]);
-      c2 += __popcll(hi & ~lo & iv[k]);
       const unsigned long long m3 = lo & hi & iv[k];
-      c3 += __popcll(m3);
-      r1 += __popcll(lo & ~hi & rv[k]);
-      r2 += __popcll(hi & ~lo & rv[k]);
-      r3 += __popcll(lo & hi & rv[k]);
+      if (LIGHT) {
+        const unsigned long long m3r = lo & hi & rv[k];
+        if (m3r) { c3 += __popcll(m3); r3 += __popcll(m3r); }
+      } else {
+        c1 += __popcll(lo & ~hi & iv[k]);
+        c2 += __popcll(hi & ~lo & iv[k]);
+        c3 += __popcll(m3);
+        r1 += __popcll(lo & ~hi & rv[k]);
+        r2 += __popcll(hi & ~lo & rv[k]);
+        r3 += __popcll(lo & hi & rv[k]);
+      }
       unsigned any = __ballot_sync(0xffffffffu, m3 != 0);
       while (any) {
         const int src = __ffs(any) - 1;
@@ -319,9 +327,14 @@ __global__ void __launch_bounds__(128)
     r3 += __shfl_xor_sync(0xffffffffu, r3, o);
   }
   if (lane == 0) {
-    int4* o = reinterpret_cast<int4*>(counts + 8 * (int64_t)row);
-    o[0] = make_int4(c1, c2, c3, r1);
-    o[1] = make_int4(r2, r3, 0, 0);
+    if (LIGHT) {
+      counts[8 * (int64_t)row + 2] = c3;
+      counts[8 * (int64_t)row + 5] = r3;
+    } else {
+      int4* o = reinterpret_cast<int4*>(counts + 8 * (int64_t)row);
+      o[0] = make_int4(c1, c2, c3, r1);
+      o[1] = make_int4(r2, r3, 0, 0);
+    }
   }
 #pragma unroll
   for (int k = 0; k < kMaxAcc; ++k)
@@ -330,19 +343,19 @@ __global__ void __launch_bounds__(128)
 
 void launch_count_missing(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
                           const PeopleLayout& pl, const double* d_featT, int n_featm, int n_featm_pad,
-                          int32_t* d_counts, double* d_miss) {
+                          int32_t* d_counts, double* d_miss, bool light) {
   if (n_snps <= 0) return;
   if (n_featm > 256) fail("too many missing-class features (%d > 256)", n_featm);
   if (pitch % 8 != 0 || pitch * 4 < pl.n_pad) fail("pitch %lld too small for %d padded people", (long long)pitch, pl.n_pad);
   const int warps = 4;
   const int grid = (n_snps + warps - 1) / warps;
   e->prof_begin(kFamCountMissing);
-  if (plink1)
-    count_missing_kernel<true><<<grid, warps * 32, 0, e->stream>>>(d_packed, pitch, n_snps, pl.n_pad, pl.d_incmask,
-                                                                   pl.d_rowmask, d_featT, n_featm, n_featm_pad, d_counts, d_miss);
-  else
-    count_missing_kernel<false><<<grid, warps * 32, 0, e->stream>>>(d_packed, pitch, n_snps, pl.n_pad, pl.d_incmask,
-                                                                    pl.d_rowmask, d_featT, n_featm, n_featm_pad, d_counts, d_miss);
+#define GW_CM(P1, LT)                                                                                              \
+  count_missing_kernel<P1, LT><<<grid, warps * 32, 0, e->stream>>>(d_packed, pitch, n_snps, pl.n_pad, pl.d_incmask, \
+                                                                   pl.d_rowmask, d_featT, n_featm, n_featm_pad, d_counts, d_miss)
+  if (plink1) { if (light) GW_CM(true, true); else GW_CM(true, false); }
+  else { if (light) GW_CM(false, true); else GW_CM(false, false); }
+#undef GW_CM
   GW_CUDA(cudaGetLastError());
   e->prof_end(kFamCountMissing);
   e->launches++;

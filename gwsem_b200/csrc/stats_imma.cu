@@ -50,7 +50,8 @@ template <int NT, int MT, int WARPS, int TILE, bool PLINK1>
 __global__ void __launch_bounds__(WARPS * 32)
     class_sums_imma_kernel(const uint8_t* __restrict__ rows, int64_t pitch, int n_snps, int n_blocks,
                            const int8_t* __restrict__ Bq, const double* __restrict__ inv_scale, int f0, int n_feat,
-                           double* __restrict__ sums) {
+                           double* __restrict__ sums, unsigned tab1, unsigned tab2, int32_t* __restrict__ counts,
+                           int count_slot) {
   constexpr int kSnps = WARPS * MT * 8;
   constexpr int kGRow = TILE / 4 + kGPad;            // staged genotype row, bytes
   constexpr int kBlocks = TILE / 32;                 // 32-person blocks per stage
@@ -89,9 +90,8 @@ __global__ void __launch_bounds__(WARPS * 32)
     for (int j = 0; j < NT; ++j)
 #pragma unroll
       for (int k = 0; k < 4; ++k) acc[m][j][k] = 0;
-  // PRMT tables: byte index = 2-bit code; 1 where the code is the class
-  const unsigned tab1 = PLINK1 ? 0x00010000u : 0x00000100u;  // het: PLINK 2 code 1, PLINK 1 code 2
-  const unsigned tab2 = PLINK1 ? 0x00000001u : 0x00010000u;  // hom ALT: PLINK 2 code 2, PLINK 1 code 0
+  // PRMT tables (kernel arguments, so that they stay in registers): byte index = 2-bit code, 1 where
+  // the code is the class.  het: PLINK 2 code 1, PLINK 1 code 2; hom ALT: PLINK 2 code 2, PLINK 1 code 0
   const unsigned pick = (unsigned)t | ((unsigned)(4 + t) << 4);  // bytes t of both words of the 64-bit block
 
   load_stage(0, 0);
@@ -139,6 +139,12 @@ __global__ void __launch_bounds__(WARPS * 32)
       v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
       v2 += __shfl_xor_sync(0xffffffffu, v2, 1);
       const int f = f0 + 2 * j + (t >> 1);
+      if (counts && 2 * j + (t >> 1) == count_slot && (t & 1) == 0 && snp < n_snps) {
+        // indicator columns: digit columns 0 / 1 of this slot = included / kept people
+        int32_t* c = counts + 8 * (int64_t)snp;
+        c[0] = acc[m][j][0]; c[3] = acc[m][j][1];   // het: included, kept
+        c[1] = acc[m][j][2]; c[4] = acc[m][j][3];   // hom ALT
+      }
       if ((t & 1) == 0 && snp < n_snps && f < n_feat) {
         const double sc = inv_scale[f];
         sums[((int64_t)snp * 2 + 0) * n_feat + f] = v1 * sc;
@@ -150,18 +156,19 @@ __global__ void __launch_bounds__(WARPS * 32)
 
 template <int NT, int MT, int WARPS, int TILE>
 void launch_imma(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1, int n_blocks,
-                 const int8_t* Bq, const double* inv_scale, int f0, int n_feat, double* d_sums) {
+                 const int8_t* Bq, const double* inv_scale, int f0, int n_feat, double* d_sums, int32_t* d_counts,
+                 int count_slot) {
   constexpr int kSnps = WARPS * MT * 8;
   const size_t smem = 2 * ((size_t)kSnps * (TILE / 4 + kGPad) + (size_t)(TILE / 32) * NT * 8 * 32);
   const int grid = (n_snps + kSnps - 1) / kSnps;
   if (plink1) {
     auto k = class_sums_imma_kernel<NT, MT, WARPS, TILE, true>;
     GW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, WARPS * 32, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums);
+    k<<<grid, WARPS * 32, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums, 0x00010000u, 0x00000001u, d_counts, count_slot);
   } else {
     auto k = class_sums_imma_kernel<NT, MT, WARPS, TILE, false>;
     GW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, WARPS * 32, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums);
+    k<<<grid, WARPS * 32, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums, 0x00000100u, 0x00010000u, d_counts, count_slot);
   }
   GW_CUDA(cudaGetLastError());
   e->launches++;
@@ -179,7 +186,10 @@ size_t imma_feature_bytes(int n_feat, int n_pad) {
   return (size_t)chunks * (n_pad / 32) * (cf * 4) * 32;
 }
 
-void imma_pack_features(const std::vector<std::vector<int64_t>>& q, int n_pad, std::vector<int8_t>& out) {
+bool imma_has_counts(int n_feat) { return n_feat > 0 && n_feat % imma_chunk_features(n_feat) != 0; }
+
+void imma_pack_features(const std::vector<std::vector<int64_t>>& q, int n_pad, const std::vector<uint8_t>& inc8,
+                        const std::vector<uint8_t>& kept, std::vector<int8_t>& out) {
   const int n_feat = (int)q.size(), cf = imma_chunk_features(n_feat), chunks = (n_feat + cf - 1) / cf;
   const int n_blocks = n_pad / 32, ncol = cf * 4;
   out.assign(imma_feature_bytes(n_feat, n_pad), 0);
@@ -197,11 +207,20 @@ void imma_pack_features(const std::vector<std::vector<int64_t>>& q, int n_pad, s
       if (v != 0) fail("feature %d does not fit four balanced base-256 digits", f);
     }
   }
+  if (imma_has_counts(n_feat)) {  // indicators in the free slot after the last feature
+    const int c = n_feat / cf, fi = n_feat % cf;
+    int8_t* base = out.data() + (size_t)c * n_blocks * ncol * 32;
+    for (int i = 0; i < n_pad; ++i) {
+      const int blk = i / 32, k = i % 32, pos = 8 * ((k % 16) / 4) + 4 * (k / 16) + k % 4;
+      base[((size_t)blk * ncol + fi * 4 + 0) * 32 + pos] = inc8[i] ? 1 : 0;
+      base[((size_t)blk * ncol + fi * 4 + 1) * 32 + pos] = kept[i] ? 1 : 0;
+    }
+  }
 }
 
 void launch_class_sums_imma(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
                             const PeopleLayout& pl, const int8_t* d_featq, const double* d_inv_scale, int n_feat,
-                            double* d_sums) {
+                            double* d_sums, int32_t* d_counts) {
   if (n_snps <= 0 || n_feat <= 0) return;
   if (pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(d_packed) & 15))
     fail("packed genotype rows must be 16-byte aligned with a pitch that is a multiple of 16 (pitch=%lld)",
@@ -210,8 +229,24 @@ void launch_class_sums_imma(gwsem_engine* e, const uint8_t* d_packed, int64_t pi
   e->prof_begin(kFamClassSums);
   for (int f0 = 0, c = 0; f0 < n_feat; f0 += cf, ++c) {
     const int8_t* Bq = d_featq + (size_t)c * n_blocks * (cf * 4) * 32;
-    if (cf == 4) launch_imma<2, 4, 4, 1024>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums);
-    else launch_imma<8, 2, 4, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums);
+    // the chunk that holds the indicator columns also writes the class counts
+    const bool last = f0 + cf >= n_feat;
+    int32_t* d_cnt = (last && d_counts && imma_has_counts(n_feat)) ? d_counts : nullptr;
+    const int count_slot = n_feat % cf;
+    if (cf == 4) {
+      static const int variant = getenv("GWSEM_IMMA_VARIANT") ? atoi(getenv("GWSEM_IMMA_VARIANT")) : 0;  // tuning aid
+      switch (variant) {  //          NT MT WARPS TILE
+        case 1: launch_imma<2, 2, 8, 1024>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        case 2: launch_imma<2, 4, 4, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        case 3: launch_imma<2, 2, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        case 4: launch_imma<2, 2, 4, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        case 5: launch_imma<2, 4, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        case 6: launch_imma<2, 2, 8, 256>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        case 7: launch_imma<2, 1, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        default: launch_imma<2, 4, 4, 1024>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+      }
+    }
+    else launch_imma<8, 2, 4, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot);
   }
   e->prof_end(kFamClassSums);
 }
