@@ -278,7 +278,7 @@ def run_gpu(args):
     achieved = alg_bytes_per_launch / (ms_cs / max(n_cs, 1) / 1e3) / 1e9 if n_cs else None
     d2h = int(sum(getattr(hres, f).nbytes for f, _ in _lib.Result._fields_))
     traffic = None   # DRAM bytes per launch from the committed ncu --set full capture, scaled to this launch size
-    tpath = os.path.join(ROOT, "profiles", "r01_class_sums_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01_class_sums_imma_traffic.json")
     if os.path.exists(tpath) and n_cs:
         with open(tpath) as f:
             t = json.load(f)
@@ -294,12 +294,13 @@ def run_gpu(args):
         "e2e": {"value": total_snps / (ms_e2e / 1e3), "unit": UNIT,
                 "h2d_bytes_per_step": int(host_packed.numel()), "d2h_bytes_per_step": d2h},
         "gpu_launches": int(gpu_launches),
-        "roofline": {"bound": "hbm", "kernel": "class_sums_kernel<8,3,...>", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "class_sums_imma_kernel<2,4,4,1024>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                      "peak_source": peak_src, "launches_timed": n_cs,
                      "kernel_ms_share": {k: v[1] / ms for k, v in prof.items() if v[0]},
                      "note": "achieved = 25,000 B/SNP of packed genotypes x SNPs per launch / CUDA-event launch time; "
-                             "the kernel is FP64-pipe bound (DESIGN.md), so the HBM fraction is low by construction"},
+                             "exact int8 tensor-core contraction; the limiter is the integer ALU work of expanding 2-bit codes "
+                             "into one-hot A fragments (ncu: alu pipe), not HBM -- see DESIGN.md section 3"},
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu:
