@@ -33,6 +33,33 @@ N_SNPS = 100_000
 METRIC = "SNPs/sec per model (buildItem WLS, 100k people)"
 UNIT = "SNPs/s"
 WORKLOAD = "C2: buildItem, 1 continuous phenotype, WLS cumulants, synthetic 100k people x 100k SNPs pgen (mode 0x02) per GPU"
+KERNEL = "class_sums_imma_kernel<2,4,4,1024>"
+NOTE = ("achieved = 25,000 B/SNP of packed genotypes x SNPs per launch / CUDA-event launch time; "
+        "exact int8 tensor-core contraction; the limiter is the integer ALU work of expanding 2-bit codes "
+        "into one-hot A fragments (ncu: alu pipe), not HBM -- see DESIGN.md section 3")
+WHICH = "c2"
+
+
+def use_workload(name):
+    """--workload c3: the configuration BASELINE.json's target is quoted on (buildOneFac WLS, 3 ordinal items +
+    5 PCs, 50k people).  The default stays configs[1] (c2) as the bench contract asks."""
+    global N_PEOPLE, N_SNPS, METRIC, WORKLOAD, KERNEL, NOTE, WHICH
+    WHICH = name
+    if name == "c3":
+        N_PEOPLE, N_SNPS = 50_000, 32_768
+        METRIC = "SNPs/sec per model (buildOneFac WLS, 3 ordinal items + 5 PCs, 50k people)"
+        WORKLOAD = ("C3: buildOneFac, 3 ordinal items (3/4/5 levels) + 5 PC covariates, WLS marginals, synthetic 50k people "
+                    "x 32,768 SNPs of packed hardcalls per step per GPU (the 1M-SNP file streams through in such batches)")
+        KERNEL = "marg_stats_kernel<3,false,1>"
+        NOTE = ("achieved = 12,500 B/SNP of packed genotypes x SNPs per launch / CUDA-event launch time; the kernel is "
+                "FP64-issue bound (polyserial scores per person), so the HBM fraction is low by construction")
+
+
+def build_model(ph):
+    from gwsem_b200.model import buildItem, buildOneFac
+    if WHICH == "c3":
+        return buildOneFac(ph, ["i1", "i2", "i3"], covariates=[f"pc{k + 1}" for k in range(5)])
+    return buildItem(ph, "y")
 
 
 def measured_peaks():
@@ -90,6 +117,16 @@ def phenotype(n, seed=2001):
     import numpy as np
     import pandas as pd
     rng = np.random.default_rng(seed)
+    if WHICH == "c3":   # F ~ N(0,1) + sum 0.1 PC; items cut into 3/4/5 levels
+        K = 5
+        X = rng.normal(size=(n, K))
+        F = rng.normal(size=n) + X @ np.full(K, 0.1)
+        ph = pd.DataFrame({f"pc{k + 1}": X[:, k] for k in range(K)})
+        cuts = [[-.43, .43], [-.67, 0, .67], [-.84, -.25, .25, .84]]
+        for j, lam in enumerate([.8, .7, .6]):
+            ystar = lam * F + X @ (rng.normal(size=K) * 0.1) + rng.normal(size=n)
+            ph[f"i{j + 1}"] = pd.Categorical(np.searchsorted(cuts[j], ystar), ordered=True)
+        return ph
     return pd.DataFrame({"y": rng.normal(size=n)})
 
 
@@ -97,20 +134,25 @@ def phenotype(n, seed=2001):
 
 def _cpu_worker(args):
     """decode with the reference's pgenlib (oracle/_ref), fit with the numpy restatement"""
-    path, lo, hi = args
+    path, lo, hi, which = args
+    use_workload(which)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import fit_oracle as fo
     from oracle_lib import RefPgen
-    from gwsem_b200.model import buildItem, flatten
+    from gwsem_b200.gwas import model_columns
+    from gwsem_b200.model import flatten
     ph = phenotype(N_PEOPLE)
-    flat = flatten(buildItem(ph, "y"))
-    cols = {"y": ph["y"].to_numpy()}
+    model = build_model(ph)
+    flat = flatten(model)
+    cols, ncat = model_columns(model)
+    if which == "c3":
+        import marginals_oracle as mo
     r = RefPgen(path)
     ok = 0
     for i in range(lo, hi):
         g, _ = r.load_row(i)
-        out = fo.fit_snp_cumulants(flat, cols, g)
+        out = mo.fit_snp_marginals(flat, cols, g, ncat) if which == "c3" else fo.fit_snp_cumulants(flat, cols, g)
         ok += out["status"] == "OK"
     return ok
 
@@ -126,11 +168,11 @@ def cpu_baseline(sample_snps, cores, repeats=1):
     synth.write_pgen_fixed(path, codes)
     del codes
     bounds = np.linspace(0, sample_snps, cores + 1).astype(int)
-    jobs = [(path, int(bounds[k]), int(bounds[k + 1])) for k in range(cores)]
+    jobs = [(path, int(bounds[k]), int(bounds[k + 1]), WHICH) for k in range(cores)]
     ctx = mp.get_context("spawn")
     best = None
     with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(path, 0, 1)] * cores)  # import + warm up
+        pool.map(_cpu_worker, [(path, 0, 1, WHICH)] * cores)  # import + warm up
         for _ in range(repeats):
             t0 = time.perf_counter()
             pool.map(_cpu_worker, jobs)
@@ -138,7 +180,8 @@ def cpu_baseline(sample_snps, cores, repeats=1):
             best = dt if best is None else min(best, dt)
     os.remove(path)
     os.rmdir(tmp)
-    kind = "reference decode (vendored pgenlib via oracle/_ref) + numpy port of the OpenMx WLS fit (oracle/fit_oracle.py)"
+    kind = ("reference decode (vendored pgenlib via oracle/_ref) + numpy port of the OpenMx WLS fit ("
+            + ("oracle/marginals_oracle.py" if WHICH == "c3" else "oracle/fit_oracle.py") + ")")
     return sample_snps / best, f"{sample_snps} SNPs x {N_PEOPLE} people of the same synthetic cohort; {kind}"
 
 
@@ -147,7 +190,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = 256 * cores
+    sample = (2 if WHICH == "c3" else 256) * cores
     vals = []
     for _ in range(max(1, args.warmup > 0)):
         cpu_baseline(max(cores, sample // 8), cores)
@@ -174,7 +217,8 @@ def run_gpu(args):
     import torch.distributed as dist
     from gwsem_b200 import _lib, synth
     from gwsem_b200.engine import Engine, FitResult, Model
-    from gwsem_b200.model import buildItem, flatten
+    from gwsem_b200.gwas import model_columns
+    from gwsem_b200.model import flatten
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -186,9 +230,12 @@ def run_gpu(args):
 
     n_snps = args.snps
     ph = phenotype(N_PEOPLE)
-    flat = flatten(buildItem(ph, "y"))
+    sem = build_model(ph)
+    flat = flatten(sem)
     eng = Engine(local)
-    model = Model(eng, flat, {"y": ph["y"].to_numpy()})
+    cols, ncat = model_columns(sem)
+    model = Model(eng, flat, cols, ncat)
+    model.set_row_filter(None, N_PEOPLE)
     P = model.P
     stream = torch.cuda.Stream(device=dev)
     eng.set_stream(stream.cuda_stream)
@@ -279,7 +326,7 @@ def run_gpu(args):
     d2h = int(sum(getattr(hres, f).nbytes for f, _ in _lib.Result._fields_))
     traffic = None   # DRAM bytes per launch from the committed ncu --set full capture, scaled to this launch size
     tpath = os.path.join(ROOT, "profiles", "r01_class_sums_imma_traffic.json")
-    if os.path.exists(tpath) and n_cs:
+    if os.path.exists(tpath) and n_cs and WHICH == "c2":
         with open(tpath) as f:
             t = json.load(f)
         per_snp = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["snps_in_launch"] * (N_PEOPLE / t["n_people"])
@@ -289,23 +336,21 @@ def run_gpu(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "n_people": N_PEOPLE, "snps_per_step_per_gpu": n_snps,
-                   "l2": "inputs (2.5 GB of packed genotypes per GPU) are larger than L2; no flush needed",
+                   "l2": f"inputs ({(N_PEOPLE + 3) // 4 * n_snps / 1e9:.2f} GB of packed genotypes per GPU) are larger than L2; no flush needed",
                    "status_ok_fraction": ok_frac, "e2e_results_identical_to_device_path": e2e_ok},
         "e2e": {"value": total_snps / (ms_e2e / 1e3), "unit": UNIT,
                 "h2d_bytes_per_step": int(host_packed.numel()), "d2h_bytes_per_step": d2h},
         "gpu_launches": int(gpu_launches),
-        "roofline": {"bound": "hbm", "kernel": "class_sums_imma_kernel<2,4,4,1024>", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": KERNEL, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                      "peak_source": peak_src, "launches_timed": n_cs,
                      "kernel_ms_share": {k: v[1] / ms for k, v in prof.items() if v[0]},
-                     "note": "achieved = 25,000 B/SNP of packed genotypes x SNPs per launch / CUDA-event launch time; "
-                             "exact int8 tensor-core contraction; the limiter is the integer ALU work of expanding 2-bit codes "
-                             "into one-hot A fragments (ncu: alu pipe), not HBM -- see DESIGN.md section 3"},
+                     "note": NOTE},
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        v, desc = cpu_baseline(args.cpu_sample, cores)
+        v, desc = cpu_baseline(args.cpu_sample if WHICH == "c2" else 2 * cores, cores)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -318,10 +363,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gwsem_b200", choices=["gwsem_b200", "reference"])
-    ap.add_argument("--snps", type=int, default=N_SNPS, help="SNPs per step per GPU (default: the named workload)")
+    ap.add_argument("--snps", type=int, default=0, help="SNPs per step per GPU (default: the named workload)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
+                    help="c2 = BASELINE.json configs[1] (the contract's default); c3 = configs[2], the target's model")
     ap.add_argument("--cpu-sample", type=int, default=1024)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    use_workload(args.workload)
+    if not args.snps:
+        args.snps = N_SNPS
     if args.impl == "reference":
         run_reference(args)
     else:
