@@ -18,6 +18,18 @@ namespace {
 
 constexpr int LANES = 32;
 
+// The RAM evaluation (ModelEval) needs only these pieces of the cumulants kernel's scratch layout.
+__host__ __device__ inline WarpScratch marg_ws(int p, int nv) {
+  WarpScratch w{};
+  int o = 0;
+  auto take = [&](int n) { int at = o; o += n; return at; };
+  w.A = take(nv * nv); w.S = take(nv * nv); w.Z = take(nv * nv); w.C = take(nv * nv);
+  w.T = take(nv * nv > 2 * nv ? nv * nv : 2 * nv);
+  w.sig = take(p * (p + 1) / 2);
+  w.total = o;
+  return w;
+}
+
 struct MargScratch {
   int th, A, B, Ai, T, s, hidx, hcoef, L, Lb, scale, theta, cand, sig, sigp, r, rc, J, g, H, Hc, delta, total;
 };
@@ -180,7 +192,7 @@ __global__ void __launch_bounds__(64)
   if (snp >= n_snps) return;
   const int J = mp.J, n1 = mp.n1, npii = mp.npii, q0 = mp.q0, D = 2 + J;
   const int nt = 2 + n1 + J + npii, ns = mp.n_stat, P = fp.P, nv = fp.nv;
-  const WarpScratch ws = scratch_layout(fp.p, fp.q, nv, P, 1);
+  const WarpScratch ws = marg_ws(fp.p, nv);
   const MargScratch ms = marg_layout(nt, ns, P, mp.n_a > 0 ? mp.n_b : 0);
   double* sm = smem_d + (size_t)group * (ws.total + ms.total);
   double* mx = sm + ws.total;
@@ -569,7 +581,7 @@ __global__ void __launch_bounds__(32) marg_pattern_kernel(FitProgram fp, MargPro
   extern __shared__ double smem_d[];
   const int lane = threadIdx.x;
   const int nt = 2 + mp.n1 + mp.J + mp.npii, ns = mp.n_stat, P = fp.P;
-  const WarpScratch ws = scratch_layout(fp.p, fp.q, fp.nv, P, 1);
+  const WarpScratch ws = marg_ws(fp.p, fp.nv);
   const MargScratch ms = marg_layout(nt, ns, P, 0);
   double *sm = smem_d, *mx = sm + ws.total;
   double *theta = mx + ms.theta, *sig = mx + ms.sig, *Jm = mx + ms.J;
@@ -588,7 +600,7 @@ __global__ void __launch_bounds__(32) marg_pattern_kernel(FitProgram fp, MargPro
 
 void launch_marg_pattern(gwsem_engine* e, const FitProgram& fp, const MargProgram& mp, double* d_out) {
   const int nt = 2 + mp.n1 + mp.J + mp.npii;
-  const size_t smem = ((size_t)scratch_layout(fp.p, fp.q, fp.nv, fp.P, 1).total + marg_layout(nt, mp.n_stat, fp.P, 0).total) * sizeof(double);
+  const size_t smem = ((size_t)marg_ws(fp.p, fp.nv).total + marg_layout(nt, mp.n_stat, fp.P, 0).total) * sizeof(double);
   if (smem > 227 * 1024) fail("marginals model too large for the per-SNP fit kernel (%zu bytes of scratch)", smem);
   GW_CUDA(cudaFuncSetAttribute(marg_pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   marg_pattern_kernel<<<1, 32, smem, e->stream>>>(fp, mp, d_out);
@@ -598,7 +610,7 @@ void launch_marg_pattern(gwsem_engine* e, const FitProgram& fp, const MargProgra
 
 size_t marg_fit_scratch_doubles(const FitProgram& fp, const MargProgram& mp) {
   const int nt = 2 + mp.n1 + mp.J + mp.npii;
-  return (size_t)scratch_layout(fp.p, fp.q, fp.nv, fp.P, 1).total + marg_layout(nt, mp.n_stat, fp.P, mp.n_a > 0 ? mp.n_b : 0).total;
+  return (size_t)marg_ws(fp.p, fp.nv).total + marg_layout(nt, mp.n_stat, fp.P, mp.n_a > 0 ? mp.n_b : 0).total;
 }
 
 void launch_marg_fit(gwsem_engine* e, const FitProgram& fp, const MargProgram& mp, int n_snps, const double* d_summary,

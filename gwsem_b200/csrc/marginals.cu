@@ -487,7 +487,7 @@ void launch_marg_stats(gwsem_engine* e, const MargProgram& mp, const uint8_t* d_
     }                                                     \
     break;
   switch (J) {
-    GW_MARG(1) GW_MARG(2) GW_MARG(3) GW_MARG(4) GW_MARG(5) GW_MARG(6) GW_MARG(7) GW_MARG(8)
+    GW_MARG(1) GW_MARG(2) GW_MARG(3) GW_MARG(4) GW_MARG(5) GW_MARG(6) GW_MARG(7) GW_MARG(8) GW_MARG(9) GW_MARG(10)
     default: fail("marginals: %d items (1..%d supported)", J, kMargMaxItems);
   }
 #undef GW_MARG_L

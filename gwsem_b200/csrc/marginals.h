@@ -7,7 +7,7 @@
 
 namespace gwsem {
 
-constexpr int kMargMaxItems = 8;
+constexpr int kMargMaxItems = 10;
 
 struct MargItem {
   int n_cat = 0;                 // 0 = continuous, else ordinal with codes 0..n_cat-1

@@ -50,6 +50,9 @@ CASES = {
     "continuous_with_covariates": dict(n_items=4, n_cov=2, ordinal=[False] * 4, build="onefacres"),
     "ordinal_no_covariates": dict(n_items=3, n_cov=0, ordinal=[True, True, True], build="onefac"),
     "twofac_ordinal": dict(n_items=6, n_cov=1, ordinal=[True, False, True, True, False, True], build="twofac"),
+    # reference tests/testthat/test-covariate.R:68-75: exogenous = FALSE turns the covariates into manifest
+    # variables, so 2 ordinal + 5 continuous items + 2 covariates are nine "items" besides snp
+    "endogenous_covariates": dict(n_items=7, n_cov=2, ordinal=[True, True] + [False] * 5, build="onefac_endo"),
 }
 
 
@@ -64,6 +67,8 @@ def test_marginals_matches_oracle(engine, case):
     covs = [f"pc{k + 1}" for k in range(cfg["n_cov"])] or None
     if cfg["build"] == "onefac":
         model = buildOneFac(ph, items, covariates=covs)
+    elif cfg["build"] == "onefac_endo":
+        model = buildOneFac(ph, items, covariates=covs, exogenous=False)
     elif cfg["build"] == "onefacres":
         model = buildOneFacRes(ph, items, covariates=covs)
     else:
