@@ -191,39 +191,66 @@ __global__ void __launch_bounds__(kT, 2)
   // every statistic): their item-side score rows, summed and as outer products, let marg_fit.cu
   // down-date the SNP-independent estimates and information to the retained subset.
   if (n < mp.n_incl) {
-    double* Mm = dyn;                       // [q0p][q0p], row b owned by lane b / b - 32
-    double* msum = dyn + mp.q0p * mp.q0p;   // [q0p]
-    for (int k = tid; k < mp.q0p * mp.q0p + mp.q0p; k += kT) dyn[k] = 0.0;
-    __syncthreads();
-    if (warp == 0) {
-      const int halves = mp.q0p / 32;
-      for (int i0 = 0; i0 < n_src; i0 += 32) {
-        const int i = i0 + lane;
+    // All warps scan for missing calls (ascending order: deterministic sums); the score rows of the
+    // people found are staged eight at a time and every thread owns a few entries of the sums.
+    constexpr int kCap = 4096;                        // people scanned per round
+    constexpr int kMaxOwn = (64 * 64 + 64 + kT - 1) / kT;
+    double* rowbuf = dyn;                             // [8][q0p]
+    int* list = reinterpret_cast<int*>(dyn + 8 * 64); // kCap entries
+    __shared__ int warp_cnt[kT / 32];
+    const int q0 = mp.q0, q0p = mp.q0p, n_el = q0 * q0 + q0;
+    double macc[kMaxOwn];
+#pragma unroll
+    for (int k = 0; k < kMaxOwn; ++k) macc[k] = 0.0;
+    for (int base = 0; base < n_src; base += kCap) {
+      int cnt = 0;
+      for (int s0 = base; s0 < min(n_src, base + kCap); s0 += kT) {
+        const int i = s0 + tid;
         bool miss = false;
         if (i < n_src && inc8[i]) {
           double u;
           miss = !std_geno(i, &u);
         }
-        unsigned todo = __ballot_sync(0xffffffffu, miss);
-        while (todo) {
-          const int src = __ffs(todo) - 1;
-          todo &= todo - 1;
-          const int64_t ip = i0 + src;
-          const double lo = mp.sc0[ip * mp.q0p + lane];
-          const double hi = halves > 1 ? mp.sc0[ip * mp.q0p + 32 + lane] : 0.0;
-          msum[lane] += lo;
-          if (halves > 1) msum[32 + lane] += hi;
-          for (int b2 = 0; b2 < mp.q0; ++b2) {
-            const double other = b2 < 32 ? __shfl_sync(0xffffffffu, lo, b2) : __shfl_sync(0xffffffffu, hi, b2 - 32);
-            Mm[lane * mp.q0p + b2] = fma(lo, other, Mm[lane * mp.q0p + b2]);
-            if (halves > 1) Mm[(32 + lane) * mp.q0p + b2] = fma(hi, other, Mm[(32 + lane) * mp.q0p + b2]);
+        const unsigned bal = __ballot_sync(0xffffffffu, miss);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int before = cnt;
+        for (int w = 0; w < warp; ++w) before += warp_cnt[w];
+        if (miss) list[before + __popc(bal & ((1u << lane) - 1u))] = i;
+#pragma unroll
+        for (int w = 0; w < kT / 32; ++w) cnt += warp_cnt[w];
+        __syncthreads();
+      }
+      for (int c0 = 0; c0 < cnt; c0 += 8) {
+        const int who = c0 + warp;
+        for (int b2 = lane; b2 < q0p; b2 += 32)
+          rowbuf[warp * q0p + b2] = who < cnt ? mp.sc0[(int64_t)list[who] * q0p + b2] : 0.0;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kMaxOwn; ++k) {
+          const int e = tid + k * kT;
+          if (e < n_el) {
+            double v = 0.0;
+            if (e < q0 * q0) {
+              const int r1 = e / q0, r2 = e - r1 * q0;
+#pragma unroll
+              for (int w = 0; w < 8; ++w) v = fma(rowbuf[w * q0p + r1], rowbuf[w * q0p + r2], v);
+            } else {
+#pragma unroll
+              for (int w = 0; w < 8; ++w) v += rowbuf[w * q0p + (e - q0 * q0)];
+            }
+            macc[k] += v;
           }
         }
+        __syncthreads();
       }
     }
-    __syncthreads();
-    for (int k = tid; k < mp.q0 * mp.q0; k += kT) out[mp.o_mmat + k] = Mm[(k / mp.q0) * mp.q0p + (k % mp.q0)];
-    for (int k = tid; k < mp.q0; k += kT) out[mp.o_msum + k] = msum[k];
+#pragma unroll
+    for (int k = 0; k < kMaxOwn; ++k) {
+      const int e = tid + k * kT;
+      if (e < q0 * q0) out[mp.o_mmat + e] = macc[k];
+      else if (e < n_el) out[mp.o_msum + (e - q0 * q0)] = macc[k];
+    }
     __syncthreads();
   }
 
@@ -470,7 +497,7 @@ void launch_marg_stats(gwsem_engine* e, const MargProgram& mp, const uint8_t* d_
   if (n_snps <= 0) return;
   const int J = mp.J, D = 2 + J;
   const size_t smem = sizeof(double) * std::max<size_t>(std::max<size_t>((size_t)kT * (((D + 1) & ~1) + (mp.n1 | 1)) + 64, (size_t)8 * 64 * (D + 1)),
-                                                         (size_t)mp.q0p * mp.q0p + mp.q0p);
+                                                         (size_t)8 * 64 + 4096 / 2);
   e->prof_begin(kFamClassSums);
 #define GW_MARG_L(JJ, DOS, HV)                                                                                      \
   {                                                                                                                 \
