@@ -33,7 +33,7 @@ N_SNPS = 100_000
 METRIC = "SNPs/sec per model (buildItem WLS, 100k people)"
 UNIT = "SNPs/s"
 WORKLOAD = "C2: buildItem, 1 continuous phenotype, WLS cumulants, synthetic 100k people x 100k SNPs pgen (mode 0x02) per GPU"
-KERNEL = "class_sums_imma_kernel<2,4,4,1024>"
+KERNEL = "class_sums_imma_kernel<2,4,4,512>"
 NOTE = ("achieved = 25,000 B/SNP of packed genotypes x SNPs per launch / CUDA-event launch time; "
         "exact int8 tensor-core contraction; the limiter is the integer ALU work of expanding 2-bit codes "
         "into one-hot A fragments (ncu: alu pipe), not HBM -- see DESIGN.md section 3")

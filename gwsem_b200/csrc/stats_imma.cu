@@ -38,6 +38,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// prmt.b32 as is (the __byte_perm intrinsic first masks the selector to three bits per nibble; the
+// selectors built below never have bit 3 set)
+__device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) {
+  unsigned d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
 __device__ __forceinline__ void mma_s8(int (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -58,8 +66,7 @@ __global__ void __launch_bounds__(WARPS * 32)
   constexpr int kBStage = kBlocks * NT * 8 * 32;     // staged feature bytes
   constexpr int kGStage = kSnps * kGRow;
   extern __shared__ __align__(16) uint8_t smem[];
-  uint8_t* Gs[2] = {smem, smem + kGStage + kBStage};
-  uint8_t* Bs[2] = {smem + kGStage, smem + 2 * kGStage + kBStage};
+  constexpr int kStage = kGStage + kBStage;   // stage s: genotype rows at s * kStage, feature block after them
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int snp0 = blockIdx.x * kSnps;
   const int n_tiles = (n_blocks + kBlocks - 1) / kBlocks;
@@ -71,14 +78,14 @@ __global__ void __launch_bounds__(WARPS * 32)
       const int r = idx / kPieces, c = idx % kPieces;
       const int64_t off = (int64_t)tile * (TILE / 4) + c * 16;
       const bool ok = snp0 + r < n_snps && off + 16 <= pitch;
-      cp_async16(Gs[s] + r * kGRow + c * 16, rows + (ok ? (int64_t)(snp0 + r) * pitch + off : 0), ok);
+      cp_async16(smem + s * kStage + r * kGRow + c * 16, rows + (ok ? (int64_t)(snp0 + r) * pitch + off : 0), ok);
     }
     // feature block: contiguous kBStage bytes
     const int64_t base = (int64_t)tile * kBStage, limit = (int64_t)n_blocks * NT * 8 * 32;
     for (int idx = tid; idx < kBStage / 16; idx += WARPS * 32) {
       const int64_t off = base + (int64_t)idx * 16;
       const bool ok = off + 16 <= limit;
-      cp_async16(Bs[s] + idx * 16, Bq + (ok ? off : 0), ok);
+      cp_async16(smem + s * kStage + kGStage + idx * 16, Bq + (ok ? off : 0), ok);
     }
     cp_async_commit();
   };
@@ -90,8 +97,8 @@ __global__ void __launch_bounds__(WARPS * 32)
     for (int j = 0; j < NT; ++j)
 #pragma unroll
       for (int k = 0; k < 4; ++k) acc[m][j][k] = 0;
-  // PRMT tables (kernel arguments, so that they stay in registers): byte index = 2-bit code, 1 where
-  // the code is the class.  het: PLINK 2 code 1, PLINK 1 code 2; hom ALT: PLINK 2 code 2, PLINK 1 code 0
+  // PRMT tables (kernel arguments tab1 / tab2): byte index = 2-bit code, 1 where the code is the class.
+  // het: PLINK 2 code 1, PLINK 1 code 2; hom ALT: PLINK 2 code 2, PLINK 1 code 0.
   const unsigned pick = (unsigned)t | ((unsigned)(4 + t) << 4);  // bytes t of both words of the 64-bit block
 
   load_stage(0, 0);
@@ -104,8 +111,8 @@ __global__ void __launch_bounds__(WARPS * 32)
       cp_async_wait<0>();
     }
     __syncthreads();
-    const uint8_t* Gw = Gs[s] + (warp * MT * 8 + g) * kGRow;
-    const uint8_t* Bw = Bs[s] + g * 32 + t * 8;
+    const uint8_t* Gw = smem + s * kStage + (warp * MT * 8 + g) * kGRow;
+    const uint8_t* Bw = smem + s * kStage + kGStage + g * 32 + t * 8;
 #pragma unroll 2
     for (int kb = 0; kb < kBlocks; ++kb) {
       uint2 bf[NT];
@@ -116,11 +123,13 @@ __global__ void __launch_bounds__(WARPS * 32)
         const uint2 w = *reinterpret_cast<const uint2*>(Gw + m * 8 * kGRow + kb * 8);
         unsigned x = __byte_perm(w.x, w.y, pick);    // byte 0: people 4t..4t+3, byte 1: people 16+4t..
         x = __byte_perm(x, 0u, 0x4140);              // 0x00HH00LL
-        x = (x | (x << 4)) & 0x0F0F0F0Fu;
-        x = (x | (x << 2)) & 0x33333333u;            // eight nibbles = eight 2-bit codes
+        // spread with multiply-adds (FMA pipe) instead of shift-or-mask (ALU pipe, the busy one):
+        // a byte 16 h + l becomes 256 h + l, then a nibble 4 c1 + c0 becomes 16 c1 + c0
+        x = (x & 0x00F000F0u) * 15u + x;             // 0x0H0H0L0L
+        x = (x & 0x0C0C0C0Cu) * 3u + x;              // eight nibbles = eight 2-bit codes
         const unsigned xh = x >> 16;
-        const unsigned a0 = __byte_perm(tab1, 0u, x), a1 = __byte_perm(tab2, 0u, x);
-        const unsigned a2 = __byte_perm(tab1, 0u, xh), a3 = __byte_perm(tab2, 0u, xh);
+        const unsigned a0 = prmt(tab1, 0u, x), a1 = prmt(tab2, 0u, x);
+        const unsigned a2 = prmt(tab1, 0u, xh), a3 = prmt(tab2, 0u, xh);
 #pragma unroll
         for (int j = 0; j < NT; ++j) mma_s8(acc[m][j], a0, a1, a2, a3, bf[j].x, bf[j].y);
       }
@@ -237,13 +246,14 @@ void launch_class_sums_imma(gwsem_engine* e, const uint8_t* d_packed, int64_t pi
       static const int variant = getenv("GWSEM_IMMA_VARIANT") ? atoi(getenv("GWSEM_IMMA_VARIANT")) : 0;  // tuning aid
       switch (variant) {  //          NT MT WARPS TILE
         case 1: launch_imma<2, 2, 8, 1024>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        case 2: launch_imma<2, 4, 4, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        case 2: launch_imma<2, 4, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
         case 3: launch_imma<2, 2, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
         case 4: launch_imma<2, 2, 4, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
         case 5: launch_imma<2, 4, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
         case 6: launch_imma<2, 2, 8, 256>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
         case 7: launch_imma<2, 1, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        default: launch_imma<2, 4, 4, 1024>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        case 8: launch_imma<2, 4, 4, 1024>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        default: launch_imma<2, 4, 4, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
       }
     }
     else launch_imma<8, 2, 4, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot);
