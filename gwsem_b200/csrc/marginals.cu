@@ -69,9 +69,11 @@ __device__ __forceinline__ double phi_integral_poly(double z, double d) {
 
 // zz = {z1, z0, phi(z1), phi(z0), Phi(z1) - Phi(z0)} of the person for an ordinal item (the +-12
 // sentinels of the open categories make their phi vanish), {v, ...} for a continuous item.
-// rho-dependent scalars are hoisted by the caller: inv_s = 1/sqrt(1-rho^2).
-__device__ __forceinline__ PairTerms pair_terms(bool ordinal, double rho, double inv_s, double u, const double* zz) {
+// The rho-dependent scalars come from shared memory (pc = {rho, 1/sqrt(1-rho^2), its cube, 3 rho / (1-rho^2)}):
+// kept in registers the compiler re-derived them, rsqrt included, for every person.
+__device__ __forceinline__ PairTerms pair_terms(bool ordinal, const double* pc, double u, const double* zz) {
   PairTerms t;
+  const double rho = pc[0], inv_s = pc[1];
   if (ordinal) {
     const double z1 = zz[0], z0 = zz[1];
     const double a1 = (z1 - rho * u) * inv_s, a0 = (z0 - rho * u) * inv_s;
@@ -89,9 +91,9 @@ __device__ __forceinline__ PairTerms pair_terms(bool ordinal, double rho, double
       pi = rect_prob(a1, a0);
     }
     pi = fmax(pi, 1e-300);
-    const double inv_pi = fast_rcp(pi), s3 = inv_s * inv_s * inv_s;
+    const double inv_pi = fast_rcp(pi), s3 = pc[2], r3 = pc[3];
     const double g1 = (rho * z1 - u) * s3, g0 = (rho * z0 - u) * s3;          // d a / d rho
-    const double h1 = z1 * s3 + 3.0 * rho * g1 * inv_s * inv_s, h0 = z0 * s3 + 3.0 * rho * g0 * inv_s * inv_s;
+    const double h1 = fma(r3, g1, z1 * s3), h0 = fma(r3, g0, z0 * s3);
     t.psi = (f1 * g1 - f0 * g0) * inv_pi;
     t.dpsi = (f1 * (h1 - a1 * g1 * g1) - f0 * (h0 - a0 * g0 * g0)) * inv_pi - t.psi * t.psi;
     t.dl_a = f1 * inv_s * inv_pi;
@@ -133,6 +135,7 @@ __global__ void __launch_bounds__(kT, 2)
   extern __shared__ __align__(16) double dyn[];
   __shared__ double red[kT / 32];
   __shared__ double rho_sh[J];
+  __shared__ double pc_sh[J][4];
   __shared__ int done_sh;
   const int snp = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* out = summary + (int64_t)snp * mp.sum_stride;
@@ -268,9 +271,14 @@ __global__ void __launch_bounds__(kT, 2)
   // one more exact Newton step at no extra cost and applies it.
   constexpr double kNewtonStop = 3e-4, kSeriesMax = 0.04;
   for (int iter = 0; iter < 30; ++iter) {
-    double s1[J], s2[J], s3[J], rh[J], inv_s[J];
+    double s1[J], s2[J], s3[J], rh[J];
 #pragma unroll
-    for (int j = 0; j < J; ++j) { s1[j] = s2[j] = s3[j] = 0.0; rh[j] = rho_sh[j]; inv_s[j] = rsqrt(1.0 - rh[j] * rh[j]); }
+    for (int j = 0; j < J; ++j) { s1[j] = s2[j] = s3[j] = 0.0; rh[j] = rho_sh[j]; }
+    if (tid < J) {
+      const double r = rho_sh[tid], is = rsqrt(1.0 - r * r);
+      pc_sh[tid][0] = r; pc_sh[tid][1] = is; pc_sh[tid][2] = is * is * is; pc_sh[tid][3] = 3.0 * r * is * is;
+    }
+    __syncthreads();
     if (iter == 0) {
       for (int i = tid; i < n_src; i += kT) {
         double u;
@@ -302,7 +310,7 @@ __global__ void __launch_bounds__(kT, 2)
         if (!std_geno(i, &u)) continue;
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-          const PairTerms t = pair_terms(ordinal[j], rh[j], inv_s[j], u, mp.zz + ((int64_t)i * J + j) * 5);
+          const PairTerms t = pair_terms(ordinal[j], pc_sh[j], u, mp.zz + ((int64_t)i * J + j) * 5);
           s1[j] += t.psi;
           s2[j] += t.dpsi;
           s3[j] = fma(t.psi, t.psi, s3[j]);
@@ -330,9 +338,14 @@ __global__ void __launch_bounds__(kT, 2)
     __syncthreads();
     if (done_sh) break;
   }
-  double rh[J], inv_s[J];
+  double rh[J];
 #pragma unroll
-  for (int j = 0; j < J; ++j) { rh[j] = rho_sh[j]; inv_s[j] = rsqrt(1.0 - rh[j] * rh[j]); }
+  for (int j = 0; j < J; ++j) rh[j] = rho_sh[j];
+  if (tid < J) {
+    const double r = rho_sh[tid], is = rsqrt(1.0 - r * r);
+    pc_sh[tid][0] = r; pc_sh[tid][1] = is; pc_sh[tid][2] = is * is * is; pc_sh[tid][3] = 3.0 * r * is * is;
+  }
+  __syncthreads();
 
   // ---- Gamma pieces.  Phase 1 (thread = person): the SNP-dependent score columns D = (mean, var,
   // psi_j); the A21 rows of the new correlations, sum_i psi_j * d loglik2_i / d (stage-1 parameter
@@ -370,7 +383,7 @@ __global__ void __launch_bounds__(kT, 2)
 #pragma unroll
       for (int j = 0; j < J; ++j) {
         const double* zz = mp.zz + ((int64_t)i * J + j) * 5;
-        const PairTerms t = pair_terms(ordinal[j], rh[j], inv_s[j], u, zz);
+        const PairTerms t = pair_terms(ordinal[j], pc_sh[j], u, zz);
         d[2 + j] = t.psi;
         ns1[j] += t.psi;
         ns2[j] += t.dpsi;
