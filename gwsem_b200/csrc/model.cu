@@ -338,8 +338,7 @@ void gwsem_model::prepare(const int32_t* row_filter, int src_rows) {
   if (fit_kind == 2) prepare_ml();
 }
 
-// ML: covariate bookkeeping for the kernel, and the per-model warm start (see prepare_marginals:
-// the estimates for a reference genotype column, fitted once from the model's own start values).
+// ML: covariate bookkeeping for the kernel, then the per-model warm start.
 void gwsem_model::prepare_ml() {
   cudaStream_t st = engine->stream;
   std::vector<int32_t> man_static(p);
@@ -349,6 +348,14 @@ void gwsem_model::prepare_ml() {
   fp.man_static = upload_vec(pool, man_static, st);
   fp.snp_exo = snp_exo >= 0;
   fp.snp_exo_index = std::max(snp_exo, 0);
+  prepare_warm();
+}
+
+// Per-model warm start (see prepare_marginals): the estimates for a reference genotype column
+// (codes 0,1,2,0,1,2,... down the file), fitted once from the model's own start values.  Every SNP
+// starts its iteration there, so a row still does not depend on its neighbours (R/model.R:188).
+void gwsem_model::prepare_warm() {
+  cudaStream_t st = engine->stream;
   fp.par_warm = nullptr;
   const int64_t rb = (n_pad / 4 + 15) / 16 * 16;
   std::vector<uint8_t> ref(rb, 0);

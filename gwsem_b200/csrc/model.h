@@ -46,6 +46,7 @@ struct gwsem_model {
   // WLS marginals (fit == 1), ML (fit == 2)
   int fit_kind = 0;
   void prepare_ml();
+  void prepare_warm();
   int marg_mode = 0;   // 0: snp is a manifest variable; 1: snp is an exogenous predictor of one ordinal item
   int snp_exo = -1;    // which exogenous covariate is the genotype column (mode 1)
   gwsem::ProbitProgram pp;
