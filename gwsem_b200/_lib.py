@@ -22,7 +22,7 @@ class ModelSpec(C.Structure):
                 ("n_categories", C.POINTER(C.c_int32)), ("n_exo", C.c_int32),
                 ("exo_data", C.POINTER(C.POINTER(C.c_double))), ("exo_latent", C.POINTER(C.c_int32)),
                 ("exo_free", C.POINTER(C.c_uint8)), ("n_thresholds", C.c_int32),
-                ("thresholds", C.POINTER(C.c_double))]
+                ("thresholds", C.POINTER(C.c_double)), ("exo_kind", C.POINTER(C.c_int32))]
 
 
 class Result(C.Structure):

@@ -67,20 +67,23 @@ gwsem_model::gwsem_model(gwsem_engine* e, const gwsem_model_spec* s) : engine(e)
     exo_latent.assign(s->exo_latent, s->exo_latent + s->n_exo);
     for (int k = 0; k < s->n_exo; ++k) {
       const double* col = s->exo_data[k];
-      if (!col) {
+      const int ek = s->exo_kind ? s->exo_kind[k] : (col ? 0 : 1);
+      if (ek == 1) {
         if (snp_exo >= 0) fail("ML: more than one exogenous covariate without data");
         snp_exo = k;
         kind.push_back(1);
         var_base.push_back(-1);
       } else {
+        if (!col) fail("ML: exogenous covariate %d has no data column", k);
         auto it = base_of.find(col);
         if (it == base_of.end()) {
           it = base_of.emplace(col, (int)base.size()).first;
           base.emplace_back(col, col + n_rows);
           used_as_moderator.push_back(false);
         }
-        kind.push_back(0);
+        kind.push_back(ek == 2 ? 2 : 0);   // 2: genotype x this column (gxe product as definition variable)
         var_base.push_back(it->second);
+        if (ek == 2) used_as_moderator[it->second] = true;
       }
     }
     pm = p + s->n_exo;
@@ -100,24 +103,35 @@ gwsem_model::gwsem_model(gwsem_engine* e, const gwsem_model_spec* s) : engine(e)
     n_categories.assign(s->n_categories, s->n_categories + p);
     exo_latent.assign(s->exo_latent, s->exo_latent + s->n_exo);
     exo_free.assign(s->exo_free, s->exo_free + (size_t)p * s->n_exo);
+    exo_kind.assign(s->n_exo, 0);
     for (int k = 0; k < s->n_exo; ++k) {
-      if (!s->exo_data[k]) {  // the genotype column as an exogenous predictor (buildItem, ordinal phenotype)
+      const int ek = s->exo_kind ? s->exo_kind[k] : (s->exo_data[k] ? 0 : 1);
+      exo_kind[k] = ek;
+      if (ek == 1) {  // the genotype column as an exogenous predictor (buildItem with exogenous = TRUE)
         if (marg_mode != 1 || snp_exo >= 0) fail("marginals: unexpected exogenous covariate without data");
         snp_exo = k;
         exo_cols.emplace_back();
         continue;
       }
+      if (!s->exo_data[k]) fail("marginals: exogenous covariate %d has no data column", k);
+      if (ek == 2 && marg_mode != 1) fail("marginals: a gxe product can only be a definition variable next to an exogenous snp");
       exo_cols.emplace_back(s->exo_data[k], s->exo_data[k] + n_rows);
       for (int r = 0; r < n_rows; ++r)
         if (!std::isfinite(exo_cols[k][r])) row_ok[r] = 0;
     }
     if (marg_mode == 1) {
-      if (kind[0] != 0 || p != 1 || snp_exo < 0 || n_categories[0] < 2)
-        fail("marginals with an exogenous snp is implemented for a single ordinal item (buildItem with an ordered factor)");
+      if (kind[0] != 0 || p != 1 || snp_exo < 0)
+        fail("marginals with an exogenous snp is implemented for a single item (buildItem with exogenous = TRUE)");
+      if (n_categories[0] == 1) fail("marginals: the item has a single category");
+      if (n_categories[0] == 0) marg_mode = 2;   // continuous item: per-SNP linear regression (linreg.cu)
+      else
+        for (int k = 0; k < s->n_exo; ++k)
+          if (exo_kind[k] == 2) fail("marginals: gxe products with an ordinal item are not implemented");
+      if (s->n_exo > gwsem::kLinregMaxX) fail("marginals: at most %d definition variables", gwsem::kLinregMaxX);
     }
     for (int v = 0; v < p; ++v)
       for (int k = 0; k < s->n_exo; ++k)
-        if (exo_free[(size_t)v * s->n_exo + k] != (marg_mode == 1 || v > 0))
+        if (exo_free[(size_t)v * s->n_exo + k] != (marg_mode >= 1 || v > 0))
           fail("marginals: every item must be regressed on every exogenous covariate and snp on none");
     thresholds.assign(s->thresholds, s->thresholds + 4 * (size_t)s->n_thresholds);
     q = p * (p + 1) / 2;

@@ -7,6 +7,7 @@
 #include "kernels.h"
 #include "marginals.h"
 #include "probit.h"
+#include "linreg.h"
 
 struct gwsem_model {
   gwsem_engine* engine;
@@ -50,6 +51,8 @@ struct gwsem_model {
   int marg_mode = 0;   // 0: snp is a manifest variable; 1: snp is an exogenous predictor of one ordinal item
   int snp_exo = -1;    // which exogenous covariate is the genotype column (mode 1)
   gwsem::ProbitProgram pp;
+  gwsem::LinregProgram lp;   // marg_mode 2: one continuous item on definition variables that include the snp
+  std::vector<int32_t> exo_kind;
   std::vector<int32_t> n_categories, exo_latent;
   std::vector<std::vector<double>> exo_cols;
   std::vector<uint8_t> exo_free;

@@ -26,6 +26,65 @@ const T* up(std::vector<DeviceBuffer<uint8_t>>& pool, const std::vector<T>& v, c
 
 void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
   cudaStream_t st = engine->stream;
+  if (marg_mode == 2) {
+    // one continuous item regressed on definition variables that include the snp (and gxe products)
+    const int K = (int)exo_cols.size();
+    lp = LinregProgram();
+    lp.K = K; lp.P = P; lp.min_variance = min_variance;
+    std::vector<int> col_of_exo(K, -1);
+    int ks = 0;
+    for (int k = 0; k < K; ++k) {
+      lp.kind[k] = exo_kind[k];
+      if (exo_kind[k] != 1) { col_of_exo[k] = ks; lp.col[k] = ks++; }
+    }
+    lp.Ks = ks; lp.Ksp = std::max(ks, 1);
+    std::vector<double> y(n_pad, 0.0), Xs((size_t)n_pad * lp.Ksp, 0.0);
+    const double* yv = base[var_base[0]].data();
+    for (int s = 0; s < n_src; ++s) {
+      const int r = dest_of[s];
+      if (r < 0 || !row_ok[r]) continue;
+      y[s] = yv[r];
+      for (int k = 0; k < K; ++k)
+        if (exo_kind[k] != 1) Xs[(size_t)s * lp.Ksp + col_of_exo[k]] = exo_cols[k][r];
+    }
+    // model parameter -> position in (intercept, slopes in exo order, residual variance)
+    std::vector<int32_t> par_map(P, -1);
+    const int n_cells = (int)cells.size() / 5;
+    for (int c = 0; c < n_cells; ++c) {
+      const double* x = &cells[5 * (size_t)c];
+      const int mat = (int)x[0], rr = (int)x[1], cc = (int)x[2], par = (int)x[3];
+      if (par < 0) {
+        if (mat == 1 && rr == 0 && cc == 0) fail("marginals: the continuous item's residual variance must be free");
+        continue;
+      }
+      if (mat == 0) {
+        int which = -1;
+        for (int k = 0; k < K; ++k)
+          if (exo_latent[k] == cc) which = k;
+        if (rr != 0 || which < 0) fail("marginals: free path that is not a slope of the item on a definition variable");
+        par_map[par] = 1 + which;
+      } else if (mat == 1) {
+        if (rr != 0 || cc != 0) fail("marginals: unexpected free covariance in a single-item model");
+        par_map[par] = 1 + K;
+      } else {
+        if (cc != 0) fail("marginals: unexpected free mean in a single-item model");
+        par_map[par] = 0;
+      }
+    }
+    for (int k = 0; k < P; ++k)
+      if (par_map[k] < 0) fail("marginals: parameter %d is not the mean, a slope or the variance of the item", k);
+    {
+      std::vector<char> seen(K + 2, 0);
+      for (int k = 0; k < P; ++k) seen[par_map[k]] = 1;
+      for (int k = 0; k < K + 2; ++k)
+        if (!seen[k]) fail("marginals: the single-item regression must be saturated (mean, every slope and the variance free)");
+    }
+    lp.y = up(pool, y, st);
+    lp.Xs = up(pool, Xs, st);
+    lp.par_map = up(pool, par_map, st);
+    lp.par_start = fp.par_start;
+    return;
+  }
   if (marg_mode == 1) {
     // one ordinal item regressed on snp + covariates: no-SNP probit fit as the Newton start
     std::vector<int> rows;
@@ -47,7 +106,7 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
     it.fit(rows, X);
     const int K = (int)X.size();
     pp = ProbitProgram();
-    pp.n_cat = C; pp.K = K; pp.Kp = std::max(K, 1); pp.P = P;
+    pp.n_cat = C; pp.K = K; pp.Kp = std::max(K, 1); pp.P = P; pp.min_variance = min_variance;
     std::vector<uint8_t> cat(n_pad, 0);
     std::vector<double> Xd((size_t)n_pad * pp.Kp, 0.0), theta0;
     for (int s = 0; s < n_src; ++s) {
@@ -311,6 +370,19 @@ void gwsem_model::run_marginals(const uint8_t* d_packed, int64_t pitch, const do
       maf1 = d_mafs.p;
     }
     launch_probit_snp(engine, pp, d_packed, pitch, n, n_src, layout.d_inc8, plink1, d_geno, n_pad, maf1, r);
+    return;
+  }
+  if (marg_mode == 2) {
+    const double* maf1 = d_maf_in;
+    if (!d_geno) {
+      d_counts.ensure(8 * (size_t)n);
+      d_miss.ensure(16);
+      d_mafs.ensure(n);
+      launch_count_missing(engine, d_packed, pitch, n, plink1, layout, d_featT, 0, 1, d_counts.p, d_miss.p);
+      launch_maf_from_counts(engine, d_counts.p, layout.n_kept, n, d_mafs.p);
+      maf1 = d_mafs.p;
+    }
+    launch_linreg_snp(engine, lp, d_packed, pitch, n, n_src, layout.d_inc8, plink1, d_geno, n_pad, maf1, r);
     return;
   }
   d_summary.ensure((size_t)n * mp.sum_stride);

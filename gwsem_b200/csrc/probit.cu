@@ -72,6 +72,41 @@ __global__ void __launch_bounds__(kT)
   }
   int status = GWSEM_STATUS_ITERATION_LIMIT, iters = 0;
   bool failed = false;
+  // observed variance of the genotype among the people used (mxData minVariance)
+  {
+    double c0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int i = tid; i < n_src; i += kT) {
+      double g;
+      if (genotype(i, &g)) { c0 += 1.0; s1 += g; s2 = fma(g, g, s2); }
+    }
+    __shared__ double mv[3][kT / 32];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if ((tid & 31) == 0) { mv[0][tid >> 5] = c0; mv[1][tid >> 5] = s1; mv[2][tid >> 5] = s2; }
+    __syncthreads();
+    c0 = s1 = s2 = 0.0;
+    for (int w = 0; w < kT / 32; ++w) { c0 += mv[0][w]; s1 += mv[1][w]; s2 += mv[2][w]; }
+    if (c0 < 2.0 || !((s2 - s1 * s1 / c0) / (c0 - 1.0) >= pp.min_variance)) {
+      const int P0 = pp.P;
+      const double na0 = __longlong_as_double((long long)GWSEM_NA_BITS);
+      for (int k = tid; k < P0 * P0; k += kT) res.vcov[(int64_t)snp * P0 * P0 + k] = na0;
+      for (int k = tid; k < P0; k += kT) res.est[(int64_t)snp * P0 + k] = pp.par_start[k];
+      if (tid == 0) {
+        res.maf[snp] = maf_in[snp];
+        res.n_used[snp] = (int)c0;
+        res.iterations[snp] = 0;
+        res.catch_var[snp] = -2;
+        res.catch_code[snp] = GWSEM_CATCH_MIN_VARIANCE;
+        res.status[snp] = GWSEM_STATUS_NA;
+        res.fit[snp] = na0;
+      }
+      return;
+    }
+  }
   for (int iter = 0; iter < 40; ++iter) {
     double accH = 0.0, accG = 0.0;
     int cnt = 0;

@@ -15,6 +15,7 @@ struct ProbitProgram {
   const double* theta0 = nullptr;  // no-SNP fit: C-1 thresholds, K slopes
   const int32_t* par_map = nullptr;  // model parameter -> index in (thresholds, snp slope, covariate slopes)
   const double* par_start = nullptr;
+  double min_variance = 0.0;
 };
 
 void launch_probit_snp(gwsem_engine* e, const ProbitProgram& pp, const uint8_t* d_rows, int64_t pitch, int n_snps,

@@ -126,9 +126,14 @@ class Model:
             ncat[j] = int((n_categories or {}).get(name, 0))
         exo = list(flat["exo_pred"])
         exo_ptrs = (C.POINTER(C.c_double) * max(len(exo), 1))()
+        exo_kind = np.zeros(max(len(exo), 1), np.int32)
         for k, name in enumerate(exo):
             if name == "snp" and "snp" not in data:
-                continue  # NULL: the genotype column itself (buildItem with an ordered phenotype)
+                exo_kind[k] = 1
+                continue  # NULL: the genotype column itself (buildItem with exogenous = TRUE)
+            if name.startswith("snp_") and name[4:] in flat["gxe"] and name not in data:
+                exo_kind[k] = 2   # genotype x moderator as a definition variable
+                name = name[4:]
             arr = np.ascontiguousarray(np.asarray(data[name], dtype=np.float64))
             self._keep.append(arr)
             exo_ptrs[k] = arr.ctypes.data_as(C.POINTER(C.c_double))
@@ -136,7 +141,7 @@ class Model:
         exo_free = np.ascontiguousarray(flat["exo_free"].astype(np.uint8) if flat["exo_free"] is not None
                                         else np.zeros((nm, 0), np.uint8))
         thr = np.ascontiguousarray(flat["thresholds"], np.float64)
-        self._keep += [ncat, exo_ptrs, exo_latent, exo_free, thr]
+        self._keep += [ncat, exo_ptrs, exo_latent, exo_free, thr, exo_kind]
         cells = np.ascontiguousarray(flat["cells"], np.float64)
         start = np.ascontiguousarray(flat["par_start"], np.float64)
         lb = np.ascontiguousarray(flat["par_lbound"], np.float64)
@@ -149,7 +154,8 @@ class Model:
                               ncat.ctypes.data_as(C.POINTER(C.c_int32)), len(exo), exo_ptrs,
                               exo_latent.ctypes.data_as(C.POINTER(C.c_int32)),
                               exo_free.ctypes.data_as(C.POINTER(C.c_uint8)), len(thr),
-                              thr.ctypes.data_as(C.POINTER(C.c_double)))
+                              thr.ctypes.data_as(C.POINTER(C.c_double)),
+                              exo_kind.ctypes.data_as(C.POINTER(C.c_int32)))
         self.n_rows = n_rows
         self.h = C.c_void_p()
         check(lib().gwsem_model_create(engine.h, C.byref(spec), C.byref(self.h)))

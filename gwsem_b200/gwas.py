@@ -145,10 +145,11 @@ def GWAS(model, snpData, out="out.log", *dots, SNP=None, startFrom=1, rowFilter=
             raise NotImplementedError("fitfun='ML' with ordinal items is not implemented (continuous items only)")
     elif flat["continuous_type"] == "marginals":
         snp_exo_item = "snp" in flat["exo_pred"] and len(flat["manifest"]) == 1
-        if model.gxe or not (flat["manifest"][0] == "snp" or snp_exo_item):
+        item_ordinal = snp_exo_item and n_categories.get(flat["manifest"][0], 0) > 0
+        if not (flat["manifest"][0] == "snp" or snp_exo_item) or (model.gxe and (not snp_exo_item or item_ordinal)):
             raise NotImplementedError("WLS marginals is implemented for models whose first manifest variable is snp "
-                                      "(buildOneFac / buildOneFacRes / buildTwoFac) and for buildItem with one "
-                                      "ordered phenotype; gxe terms under marginals are not implemented")
+                                      "(buildOneFac / buildOneFacRes / buildTwoFac, no gxe) and for buildItem with one "
+                                      "depVar and exogenous = TRUE (ordered: no gxe; continuous: gxe allowed)")
     eng = _engine(device)
     with Source(snpData, method, src_rows) as src:
         gm = Model(eng, flat, data, n_categories)

@@ -114,6 +114,8 @@ typedef struct {
   const uint8_t* exo_free;            /* n_manifest x n_exo, row major: slope is a statistic */
   int32_t n_thresholds;
   const double* thresholds;           /* n_thresholds x 4: manifest, k, param (-1 = fixed), value */
+  const int32_t* exo_kind;            /* n_exo or NULL: 0 data column, 1 the genotype (exo_data NULL), 2 genotype x exo_data column
+                                         (a gxe product `snp_<moderator>` as definition variable, R/model.R:427-434) */
 } gwsem_model_spec;
 
 int gwsem_model_create(gwsem_engine* e, const gwsem_model_spec* spec, gwsem_model** out);

@@ -392,13 +392,23 @@ def fit_snp_marginals(flat, pheno_cols, snp, n_cats):
     names = flat["manifest"]
     cols = [snp if m == "snp" else pheno_cols[m] for m in names]
     # buildItem with an ordered phenotype: `snp` itself is an exogenous predictor (R/model.R:560-576)
-    X = (np.column_stack([snp if c == "snp" else pheno_cols[c] for c in flat["exo_pred"]])
+    def exo_column(c):   # `snp_<moderator>`: the gxe product as a definition variable (R/model.R:427-434)
+        if c == "snp":
+            return snp
+        if c.startswith("snp_") and c[4:] in flat["gxe"] and c not in pheno_cols:
+            with np.errstate(invalid="ignore"):
+                return snp * pheno_cols[c[4:]]
+        return pheno_cols[c]
+    X = (np.column_stack([exo_column(c) for c in flat["exo_pred"]])
          if flat["exo_pred"] else np.zeros((len(snp), 0)))
     keep = np.isfinite(np.column_stack(cols + [X])).all(1)
     cols = [c[keep] for c in cols]
     X = X[keep]
     out["n"] = int(keep.sum())
     kinds = ["ord" if n_cats.get(m, 0) > 1 else "cont" for m in names]
+    if "snp" in flat["exo_pred"] and not (np.var(snp[keep], ddof=1) >= flat["min_variance"]):
+        out["catch1"] = f"{flat['name']}.data: 'snp' has observed variance less than {flat['min_variance']:g}"
+        return out
     for j, m in enumerate(names):
         if kinds[j] == "cont" and not (np.var(cols[j], ddof=1) >= flat["min_variance"]):
             out["catch1"] = f"{flat['name']}.data: '{m}' has observed variance less than {flat['min_variance']:g}"

@@ -233,3 +233,84 @@ def test_build_item_ordinal_gwas_on_fixtures(engine, tmp_path):
                 assert row[f"V{nme}:{nme}"] == pytest.approx(w["vcov"][k, k], rel=2 * SE_RTOL), (fname, snp, nme)
         lr = signif(loadResults(out, "snp_to_anxiety"), "snp_to_anxiety")
         assert np.isfinite(lr["P"]).sum() >= len(pick) - 1
+
+
+@pytest.mark.parametrize("gxe,n_cov", [("mod", 2), (None, 1), ("mod", 0)])
+def test_build_item_continuous_exogenous_matches_oracle(engine, gxe, n_cov):
+    """buildItem(..., fitfun='WLS', exogenous=TRUE) with a continuous depVar: the gene-environment
+    vignette's model (tools/vignettes/GeneEnvironmentInteraction.Rmd:47-49).  snp and snp_<moderator>
+    are definition variables; per SNP this is the regression of the item on them and the covariates."""
+    import marginals_oracle as mo
+    from gwsem_b200.engine import Model
+    from gwsem_b200.model import buildItem
+    n = 1500
+    rng = np.random.default_rng(8)
+    codes = synth.simulate_hardcalls(n, 6, seed=12, maf_range=(0.15, 0.5))
+    codes[1, :70] = 3
+    codes[2] = 0                                   # monomorphic
+    codes[5, ::11] = 3
+    geno = np.array([0.0, 1.0, 2.0, np.nan])[codes]
+    ph = pd.DataFrame({"mod": rng.normal(size=n)})
+    for k in range(n_cov):
+        ph[f"pc{k + 1}"] = rng.normal(size=n)
+    ph["phe"] = (0.2 * np.nan_to_num(geno[0]) + 0.3 * ph["mod"] + 0.15 * np.nan_to_num(geno[0]) * ph["mod"]
+                 + sum(0.1 * ph[f"pc{k + 1}"] for k in range(n_cov)) + rng.normal(size=n) + 2.0)
+    covs = (["mod"] if gxe else []) + [f"pc{k + 1}" for k in range(n_cov)]
+    model = buildItem(ph, "phe", covariates=covs or None, fitfun="WLS", exogenous=True, gxe=gxe)
+    flat = flatten(model)
+    assert flat["manifest"] == ["phe"] and flat["exo_pred"][0] == "snp" and flat["continuous_type"] == "marginals"
+    data, ncat = model_columns(model)
+    want = [mo.fit_snp_marginals(flat, data, g, ncat) for g in geno]
+    assert [bool(w["catch1"]) for w in want] == [False, False, True, False, False, False]
+    gm = Model(engine, flat, data, ncat)
+    res = gm.fit_2bit(synth.pack_2bit(codes))
+    compare(res, want, flat["par_names"])
+    assert res.catch_code[2] == 1                  # observed variance of snp below minVariance
+    # closed form: OLS coefficients
+    names = flat["par_names"]
+    ok = np.isfinite(geno[0])
+    cols = [np.ones(ok.sum()), geno[0][ok]] + ([geno[0][ok] * ph["mod"][ok]] if gxe else []) + [ph[c][ok] for c in covs]
+    beta = np.linalg.lstsq(np.column_stack(cols), ph["phe"][ok], rcond=None)[0]
+    assert res.est[0][names.index("snp_to_phe")] == pytest.approx(beta[1], rel=1e-9)
+    if gxe:
+        assert res.est[0][names.index("snp_mod_to_phe")] == pytest.approx(beta[2], rel=1e-9)
+    bed = np.array([3, 2, 0, 1], np.uint8)[codes]
+    res2 = gm.fit_2bit(synth.pack_2bit(bed), plink1=True)
+    good = res.catch_code == 0
+    assert np.array_equal(res2.est[good].view(np.uint64), res.est[good].view(np.uint64))
+    gm.close()
+
+
+def test_gxe_vignette_model_through_gwas(engine, tmp_path):
+    """The vignette's GxE call through GWAS() on the bundled files (hardcalls and dosages), with the
+    follow-up the vignette does: loadResults + signifGxE on the interaction term."""
+    import os
+    import marginals_oracle as mo
+    from conftest import EXTDATA, GOLDEN
+    from gwsem_b200 import GWAS, loadResults, signifGxE
+    from gwsem_b200.model import buildItem
+    ps = pd.read_csv(os.path.join(EXTDATA, "example.psam"), sep="\t")
+    rng = np.random.default_rng(6)
+    ph = pd.DataFrame({"mod": rng.normal(size=500), "pc1": rng.normal(size=500)})
+    ph["phe"] = ps["phenotype"] + 0.3 * ph["mod"] + rng.normal(size=500)
+    model = buildItem(ph, "phe", covariates=["mod", "pc1"], fitfun="WLS", exogenous=True, gxe="mod")
+    flat = flatten(model)
+    data, ncat = model_columns(model)
+    pick = [1, 2, 90, 199]
+    for fname, gold_name in (("example.bed", "example_bed.npz"), ("example.pgen", "example_pgen.npz")):
+        out = str(tmp_path / "out.log")
+        GWAS(model, os.path.join(EXTDATA, fname), out, SNP=pick)
+        log = pd.read_csv(out, sep="\t", quoting=3, dtype={"catch1": str, "statusCode": str})
+        gold = np.load(os.path.join(GOLDEN, gold_name))
+        for row, snp in zip(log.to_dict("records"), [s - 1 for s in pick]):
+            w = mo.fit_snp_marginals(flat, data, gold["geno"][snp], ncat)
+            if w["catch1"]:
+                assert isinstance(row["catch1"], str) and row["catch1"]
+                continue
+            assert row["statusCode"] == "OK"
+            se = np.sqrt(np.diag(w["vcov"]))
+            for k, nme in enumerate(flat["par_names"]):
+                assert abs(row[nme] - w["est"][k]) <= EST_RTOL * max(abs(w["est"][k]), se[k]), (fname, snp, nme)
+                assert row[f"V{nme}:{nme}"] == pytest.approx(w["vcov"][k, k], rel=2 * SE_RTOL), (fname, snp, nme)
+        lr = signifGxE(loadResults(out, "snp_mod_to_phe"), "snp_mod_to_phe", level=0.5)
+        assert np.isfinite(lr["P"]).sum() >= len(pick) - 1
