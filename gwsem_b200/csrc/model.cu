@@ -124,9 +124,6 @@ gwsem_model::gwsem_model(gwsem_engine* e, const gwsem_model_spec* s) : engine(e)
         fail("marginals with an exogenous snp is implemented for a single item (buildItem with exogenous = TRUE)");
       if (n_categories[0] == 1) fail("marginals: the item has a single category");
       if (n_categories[0] == 0) marg_mode = 2;   // continuous item: per-SNP linear regression (linreg.cu)
-      else
-        for (int k = 0; k < s->n_exo; ++k)
-          if (exo_kind[k] == 2) fail("marginals: gxe products with an ordinal item are not implemented");
       if (s->n_exo > gwsem::kLinregMaxX) fail("marginals: at most %d definition variables", gwsem::kLinregMaxX);
     }
     for (int v = 0; v < p; ++v)

@@ -99,25 +99,31 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
       const double c = it.values[r];
       if (c < 0 || c >= C || c != std::floor(c)) fail("marginals: the item holds a code outside 0..%d", C - 1);
     }
+    // start values: the ordered probit of the item on the plain covariates (no snp terms)
     std::vector<const double*> X;
-    std::vector<int> other;  // exogenous covariates besides the snp
-    for (int k = 0; k < (int)exo_cols.size(); ++k)
-      if (k != snp_exo) { X.push_back(exo_cols[k].data()); other.push_back(k); }
-    it.fit(rows, X);
-    const int K = (int)X.size();
+    const int K = (int)exo_cols.size();
+    std::vector<int> col_of_exo(K, -1);
     pp = ProbitProgram();
-    pp.n_cat = C; pp.K = K; pp.Kp = std::max(K, 1); pp.P = P; pp.min_variance = min_variance;
+    int ks = 0;
+    for (int k = 0; k < K; ++k) {
+      pp.kind[k] = exo_kind[k];
+      if (exo_kind[k] != 1) { col_of_exo[k] = ks; pp.col[k] = ks++; }
+      if (exo_kind[k] == 0) X.push_back(exo_cols[k].data());
+    }
+    it.fit(rows, X);
+    pp.n_cat = C; pp.K = K; pp.Kp = std::max(ks, 1); pp.P = P; pp.min_variance = min_variance;
     std::vector<uint8_t> cat(n_pad, 0);
     std::vector<double> Xd((size_t)n_pad * pp.Kp, 0.0), theta0;
     for (int s = 0; s < n_src; ++s) {
       const int r = dest_of[s];
       if (r < 0 || !row_ok[r]) continue;
       cat[s] = (uint8_t)it.values[r];
-      for (int k = 0; k < K; ++k) Xd[(size_t)s * pp.Kp + k] = X[k][r];
+      for (int k = 0; k < K; ++k)
+        if (exo_kind[k] != 1) Xd[(size_t)s * pp.Kp + col_of_exo[k]] = exo_cols[k][r];
     }
     theta0.insert(theta0.end(), it.th.begin(), it.th.end());
-    theta0.insert(theta0.end(), it.beta.begin(), it.beta.end());
-    // model parameter -> position in (thresholds, snp slope, covariate slopes); the item's variance must be 1
+    for (int k = 0, plain = 0; k < K; ++k) theta0.push_back(exo_kind[k] == 0 ? it.beta[plain++] : 0.0);
+    // model parameter -> position in (thresholds, slopes in the model's order); the item's variance must be 1
     std::vector<int32_t> par_map(P, -1);
     const int n_cells = (int)cells.size() / 5;
     for (int c = 0; c < n_cells; ++c) {
@@ -127,11 +133,10 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
       if (mat == 0 && par >= 0) {
         if (rr != 0) fail("marginals: unexpected free path in a single-item model");
         int which = -1;
-        for (int k = 0; k < (int)exo_latent.size(); ++k)
+        for (int k = 0; k < K; ++k)
           if (exo_latent[k] == cc) which = k;
         if (which < 0) fail("marginals: free path from a variable that is not an exogenous covariate");
-        if (which == snp_exo) par_map[par] = C - 1;
-        else par_map[par] = C + (int)(std::find(other.begin(), other.end(), which) - other.begin());
+        par_map[par] = C - 1 + which;
       }
       if (mat == 2 && par >= 0) fail("marginals: free means are not part of a single ordinal item model");
     }

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(kT)
                       const double* __restrict__ maf_in, gwsem_result res) {
   extern __shared__ double dyn[];
   const int snp = blockIdx.x, tid = threadIdx.x;
-  const int C = pp.n_cat, K = pp.K, d = C + K;     // thresholds C-1, snp slope, K covariate slopes
+  const int C = pp.n_cat, K = pp.K, d = C - 1 + K;  // thresholds C-1, then a slope per definition variable
   const int n_ent = d * (d + 1) / 2 + d;           // lower triangle of H / OPG, then the score
   const int slices = max(1, kT / n_ent);
   double* theta = dyn;                 // d
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kT)
     return code != 3u;
   };
   // start from the fit without the SNP (slope 0)
-  for (int k = tid; k < d; k += kT) theta[k] = k < C - 1 ? pp.theta0[k] : (k == C - 1 ? 0.0 : pp.theta0[k - 1]);
+  for (int k = tid; k < d; k += kT) theta[k] = pp.theta0[k];
   if (tid == 0) { n_sh = 0; flag_sh = 0; }
   __syncthreads();
   const int my_ent = tid % n_ent, my_slice = tid / n_ent;
@@ -116,11 +116,12 @@ __global__ void __launch_bounds__(kT)
       int cat = 0;
       if (i < n_src && genotype(i, &g)) {
         cat = pp.cat[i];
-        double eta = theta[C - 1] * g;
+        double eta = 0.0;
+        const double* xs = pp.X + (int64_t)i * pp.Kp;
         for (int k = 0; k < K; ++k) {
-          const double x = pp.X[(int64_t)i * pp.Kp + k];
+          const double x = pp.kind[k] == 0 ? xs[pp.col[k]] : (pp.kind[k] == 1 ? g : g * xs[pp.col[k]]);
           tX[tid * K + k] = x;
-          eta = fma(theta[C + k], x, eta);
+          eta = fma(theta[C - 1 + k], x, eta);
         }
         const double z1 = (cat < C - 1 ? theta[cat] : 12.0) - eta, z0 = (cat > 0 ? theta[cat - 1] : -12.0) - eta;
         const double p1 = cat < C - 1 ? dphi(z1) : 0.0, p0 = cat > 0 ? dphi(z0) : 0.0;
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(kT)
           // derivatives of z1, z0 with respect to parameter a (threshold / slope)
           auto jz = [&](int a, double* j1, double* j0) {
             if (a < C - 1) { *j1 = (c == a) ? 1.0 : 0.0; *j0 = (c == a + 1) ? 1.0 : 0.0; }
-            else { const double x = a == C - 1 ? tg[p] : tX[p * K + (a - C)]; *j1 = -x; *j0 = -x; }
+            else { const double x = tX[p * K + (a - (C - 1))]; *j1 = -x; *j0 = -x; }
           };
           double a1, a0;
           jz(ea, &a1, &a0);
@@ -257,7 +258,7 @@ void launch_probit_snp(gwsem_engine* e, const ProbitProgram& pp, const uint8_t* 
                        int n_src, const uint8_t* d_inc8, int plink1, const double* d_geno, int n_pad, const double* d_maf,
                        const gwsem_result& d_res) {
   if (n_snps <= 0) return;
-  const int d = pp.n_cat + pp.K, n_ent = d * (d + 1) / 2 + d;
+  const int d = pp.n_cat - 1 + pp.K, n_ent = d * (d + 1) / 2 + d;
   if (n_ent > kT) fail("probit: %d parameters per SNP is more than this kernel handles", d);
   const int slices = std::max(1, kT / n_ent);
   const size_t doubles = (size_t)2 * d + 2 * d * d + 5 * kT + (size_t)kT * std::max(pp.K, 1) +

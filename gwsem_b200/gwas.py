@@ -145,11 +145,10 @@ def GWAS(model, snpData, out="out.log", *dots, SNP=None, startFrom=1, rowFilter=
             raise NotImplementedError("fitfun='ML' with ordinal items is not implemented (continuous items only)")
     elif flat["continuous_type"] == "marginals":
         snp_exo_item = "snp" in flat["exo_pred"] and len(flat["manifest"]) == 1
-        item_ordinal = snp_exo_item and n_categories.get(flat["manifest"][0], 0) > 0
-        if not (flat["manifest"][0] == "snp" or snp_exo_item) or (model.gxe and (not snp_exo_item or item_ordinal)):
+        if not (flat["manifest"][0] == "snp" or snp_exo_item) or (model.gxe and not snp_exo_item):
             raise NotImplementedError("WLS marginals is implemented for models whose first manifest variable is snp "
                                       "(buildOneFac / buildOneFacRes / buildTwoFac, no gxe) and for buildItem with one "
-                                      "depVar and exogenous = TRUE (ordered: no gxe; continuous: gxe allowed)")
+                                      "depVar and exogenous = TRUE (gxe allowed)")
     eng = _engine(device)
     with Source(snpData, method, src_rows) as src:
         gm = Model(eng, flat, data, n_categories)

@@ -314,3 +314,29 @@ def test_gxe_vignette_model_through_gwas(engine, tmp_path):
                 assert row[f"V{nme}:{nme}"] == pytest.approx(w["vcov"][k, k], rel=2 * SE_RTOL), (fname, snp, nme)
         lr = signifGxE(loadResults(out, "snp_mod_to_phe"), "snp_mod_to_phe", level=0.5)
         assert np.isfinite(lr["P"]).sum() >= len(pick) - 1
+
+
+def test_build_item_ordinal_with_gxe_matches_oracle(engine):
+    """An ordered depVar with a gxe term (the vignette: "It is possible to conduct GxE analyses on binary or
+    ordinal variables"): snp and snp_<moderator> are definition variables of the ordered probit."""
+    import marginals_oracle as mo
+    from gwsem_b200.engine import Model
+    from gwsem_b200.model import buildItem
+    n = 2000
+    rng = np.random.default_rng(9)
+    codes = synth.simulate_hardcalls(n, 4, seed=14, maf_range=(0.2, 0.5))
+    codes[1, :50] = 3
+    geno = np.array([0.0, 1.0, 2.0, np.nan])[codes]
+    ph = pd.DataFrame({"mod": rng.integers(0, 2, n).astype(float), "pc1": rng.normal(size=n)})
+    ystar = 0.2 * np.nan_to_num(geno[0]) + 0.3 * ph["mod"] + 0.2 * np.nan_to_num(geno[0]) * ph["mod"] + 0.1 * ph["pc1"] + rng.normal(size=n)
+    ph["phe"] = pd.Categorical(np.searchsorted([0.2, 1.1], ystar), ordered=True)
+    model = buildItem(ph, "phe", covariates=["mod", "pc1"], gxe="mod")
+    flat = flatten(model)
+    assert flat["exo_pred"][:2] == ["snp", "snp_mod"] and flat["continuous_type"] == "marginals"
+    data, ncat = model_columns(model)
+    want = [mo.fit_snp_marginals(flat, data, g, ncat) for g in geno]
+    assert all(w["status"] == "OK" for w in want)
+    gm = Model(engine, flat, data, ncat)
+    res = gm.fit_2bit(synth.pack_2bit(codes))
+    compare(res, want, flat["par_names"])
+    gm.close()
