@@ -107,6 +107,76 @@ def _offdiag(model, names):
     return [n for n in want if n in names]
 
 
+def _gwas_multigroup(model, snpData, out, SNP, startFrom, rowFilter, device, batch_snps):
+    """GWAS(mg, c(sample1=file1, sample2=file2)) (R/model.R:132-163, tests/testthat/test-multigroup.R).
+    With no parameter label shared between the groups the multigroup fit (a sum of the groups' fit
+    functions) separates: every group is fitted on its own file and the rows are joined by SNP index.
+    Shared labels would couple the groups' iterations and are not implemented."""
+    import tempfile
+    import pandas as pd
+    from .model import MultigroupModel
+    if not isinstance(snpData, dict) or not snpData:
+        raise ValueError("Must provide model names for snpData. For example,\n {'" + str(getattr(model, "name", "model")) + "': path}")
+    if not isinstance(model, MultigroupModel):
+        raise ValueError("several snpData files need a multigroup model (MultigroupModel(name, g1, g2, ...))")
+    by_name = {m.name: m for m in model.submodels}
+    for k in snpData:
+        if k not in by_name:
+            raise ValueError(f"Cannot find model associated with snpData: '{k}'")
+    if isinstance(rowFilter, dict):
+        unknown = [k for k in rowFilter if k not in by_name]
+        if unknown:
+            raise ValueError("Cannot find model associated with rowFilter: " + ", ".join(f"'{k}'" for k in unknown))
+    elif rowFilter is not None:
+        raise ValueError("rowFilter must be a dict keyed by sub-model name for a multigroup model")
+    seen = {}
+    for m in model.submodels:
+        for lab in flatten(m)["par_names"]:
+            if lab in seen:
+                raise NotImplementedError(f"parameter '{lab}' is shared by sub-models '{seen[lab]}' and '{m.name}': "
+                                          "groups coupled by shared parameters are not implemented")
+            seen[lab] = m.name
+    parts, results = [], []
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, path in snpData.items():
+            sub_out = os.path.join(tmp, name + ".log")
+            results.append(GWAS(by_name[name], path, sub_out, SNP=SNP, startFrom=startFrom,
+                                rowFilter=(rowFilter or {}).get(name), device=device, batch_snps=batch_snps))
+            parts.append(pd.read_csv(sub_out, sep="\t", quoting=3, keep_default_na=False,
+                                     dtype=str))
+    n = min(len(p_) for p_ in parts)
+    first = parts[0].iloc[:n].copy()
+    shared = ["OpenMxEvals", "iterations", "timestamp", "MxComputeLoop1", "fit", "fitUnits", "sampleSize", "statusCode",
+              "CHR", "BP", "SNP", "A1", "A2", "RSID", "MAF", "catch1"]
+    merged = first[[c for c in ["OpenMxEvals", "iterations", "timestamp", "MxComputeLoop1"] if c in first]].copy()
+    for p_ in parts:
+        for c in p_.columns:
+            if c not in shared and not c.startswith("V"):
+                merged[c] = p_[c].iloc[:n].to_numpy()
+    num = lambda col: pd.to_numeric(pd.Series(col).replace("NA", np.nan), errors="coerce")
+    merged["fit"] = sum(num(p_["fit"].iloc[:n].to_numpy()) for p_ in parts).map(lambda v: "NA" if pd.isna(v) else repr(float(v)))
+    merged["fitUnits"] = first["fitUnits"].to_numpy()
+    merged["sampleSize"] = sum(pd.to_numeric(p_["sampleSize"].iloc[:n]) for p_ in parts).astype(int).astype(str)
+    status = first["statusCode"].to_numpy().copy()
+    catch1 = first["catch1"].to_numpy().copy()
+    for p_ in parts[1:]:
+        st, ca = p_["statusCode"].iloc[:n].to_numpy(), p_["catch1"].iloc[:n].to_numpy()
+        status = np.where(status == "OK", st, status)
+        catch1 = np.where(catch1 == "", ca, catch1)
+    merged["statusCode"] = status
+    for p_ in parts:
+        for c in p_.columns:
+            if c.startswith("V") and ":" in c:
+                merged[c] = p_[c].iloc[:n].to_numpy()
+    for c in ["CHR", "BP", "SNP", "A1", "A2", "RSID", "MAF"]:   # variant context and MAF of the first group's file
+        if c in first:
+            merged[c] = first[c].to_numpy()
+    merged["catch1"] = catch1
+    merged.to_csv(out, sep="\t", index=False, quoting=3)
+    print(f"Done. See '{out}' for results")
+    return GWASResult(model, out, n, None, sum(r.loadCounter for r in results))
+
+
 class GWASResult:
     """What the reference's GWAS() returns invisibly: the model with the last SNP loaded."""
 
@@ -121,7 +191,8 @@ def GWAS(model, snpData, out="out.log", *dots, SNP=None, startFrom=1, rowFilter=
     if dots:
         raise ValueError("Rejected are any values passed in the '...' argument")
     if not isinstance(snpData, str):
-        raise NotImplementedError("multi-group snpData (one file per sub-model) is not implemented")
+        return _gwas_multigroup(model, snpData, out, SNP=SNP, startFrom=startFrom, rowFilter=rowFilter, device=device,
+                                batch_snps=batch_snps)
     psd = processSnpData(snpData)
     method, ext, stem = psd["method"][0], psd["snpFileExt"][0], psd["stem"][0]
     if isinstance(rowFilter, dict):

@@ -437,3 +437,50 @@ def flatten(model):
                 min_variance=float(model.minVariance), gxe=list(model.gxe),
                 exo_pred=list(model.exoPred),
                 exo_free=None if model.exoFree is None else model.exoFree.to_numpy(bool))
+
+
+# ---------------------------------------------------------------------------- multigroup helpers
+# tests/testthat/test-multigroup.R:15-36 assembles a multigroup model from OpenMx pieces; these are
+# the minimal counterparts: mxRename, omxSetParameters (relabelling only), mxModel(name, g1, g2,
+# mxFitFunctionMultigroup(...)).
+
+def mxRename(model, newname):
+    """A copy of `model` under another name."""
+    import copy
+    m = copy.deepcopy(model)
+    m.name = newname
+    return m
+
+
+def coefNames(model):
+    """names(coef(model)): the free-parameter labels in the order the log uses."""
+    return list(flatten(model)["par_names"])
+
+
+def omxSetParameters(model, labels, newlabels):
+    """Relabel free parameters (the only use the reference's tests make of omxSetParameters)."""
+    import copy
+    labels, newlabels = list(labels), list(newlabels)
+    if len(labels) != len(newlabels):
+        raise ValueError("labels and newlabels differ in length")
+    ren = dict(zip(labels, newlabels))
+    m = copy.deepcopy(model)
+    for mat in (m.A, m.S, m.M):
+        lab = mat["labels"]
+        for idx in np.ndindex(lab.shape):
+            if lab[idx] in ren:
+                lab[idx] = ren[lab[idx]]
+    for thr in m.thresholds.values():
+        thr["labels"] = [ren.get(l, l) for l in thr["labels"]]
+    return m
+
+
+class MultigroupModel:
+    """mxModel(name, submodels..., mxFitFunctionMultigroup(names)): the fit is the sum of the groups' fits."""
+
+    def __init__(self, name, *submodels):
+        self.name = name
+        self.submodels = list(submodels)
+        names = [m.name for m in self.submodels]
+        if len(set(names)) != len(names):
+            raise ValueError("sub-models must have distinct names")

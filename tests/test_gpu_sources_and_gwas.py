@@ -255,3 +255,37 @@ def test_gwas_row_filter_and_gxe(engine, tmp_path):
     lr = loadResults(out, "snp_mod_to_i3")
     g = signifGxE(lr, "snp_mod_to_i3", level=.5)
     assert np.isfinite(g["ME.SE"][~isSuspicious(g)]).all() and (~isSuspicious(g)).sum() > 30
+
+
+def test_multigroup_independent_groups(engine, tmp_path):
+    """tests/testthat/test-multigroup.R: two buildItem models with their own parameter labels and
+    their own .bed file, fitted jointly as a multigroup model, reproduce the two separate fits."""
+    import os
+    import pandas as pd
+    from conftest import EXTDATA
+    from gwsem_b200 import GWAS, MultigroupModel, buildItem, coefNames, mxRename, omxSetParameters
+    logs = {}
+    groups = []
+    for k in (1, 2):
+        fam = pd.read_csv(os.path.join(EXTDATA, f"group{k}.fam"), sep=r"\s+", header=None,
+                          names=["V1", "V2", "V3", "V4", "V5", "V6"])
+        g = mxRename(buildItem(fam, depVar="V6"), f"sample{k}")
+        g = omxSetParameters(g, labels=coefNames(g), newlabels=[f"S{k}{n}" for n in coefNames(g)])
+        groups.append(g)
+        out = str(tmp_path / f"g{k}.log")
+        GWAS(g, os.path.join(EXTDATA, f"group{k}.bed"), out, SNP=[1, 2, 3])
+        logs[k] = pd.read_csv(out, sep="\t", quoting=3)
+    mg = MultigroupModel("mg", *groups)
+    out = str(tmp_path / "mg.log")
+    GWAS(mg, {"sample1": os.path.join(EXTDATA, "group1.bed"), "sample2": os.path.join(EXTDATA, "group2.bed")}, out,
+         SNP=[1, 2, 3])
+    both = pd.read_csv(out, sep="\t", quoting=3)
+    assert len(both) == 3 and list(both["MxComputeLoop1"]) == [1, 2, 3]
+    for k in (1, 2):
+        for name in coefNames(groups[k - 1]):
+            assert np.allclose(both[name], logs[k][name], rtol=1e-12, equal_nan=True)
+            assert np.allclose(both[f"V{name}:{name}"], logs[k][f"V{name}:{name}"], rtol=1e-12, equal_nan=True)
+    assert np.allclose(both["fit"], logs[1]["fit"] + logs[2]["fit"])
+    shared = MultigroupModel("mg2", groups[0], mxRename(groups[0], "again"))
+    with pytest.raises(NotImplementedError, match="shared"):
+        GWAS(shared, {"sample1": os.path.join(EXTDATA, "group1.bed"), "again": os.path.join(EXTDATA, "group1.bed")}, out, SNP=[1])
