@@ -12,6 +12,7 @@
 #include <map>
 #include <sstream>
 #include <charconv>
+#include <chrono>
 #include <future>
 #include <thread>
 
@@ -44,6 +45,8 @@ struct Stager {
   int n_pad;
   int64_t pitch;  // canonical row pitch (bytes, multiple of 16, >= n_pad / 4)
   PinnedBuffer<uint8_t> h_bytes;
+  PinnedBuffer<uint8_t> h_bgen[2];   // inflated bgen blocks, read ahead like h_fixed
+  std::vector<uint64_t> bgen_off[2];
   PinnedBuffer<uint8_t> h_fixed[2];  // fixed-width records: read ahead by a host thread (see read_fixed)
   DeviceBuffer<uint8_t> d_bytes, d_vt, d_rows;
   DeviceBuffer<uint64_t> d_off;
@@ -215,8 +218,8 @@ struct Stager {
   }
 
   // BGEN: inflates the probability blocks of variants[] (index order) and uploads them
-  void stage_bgen(const uint32_t* variants, int n) {
-    cudaStream_t st = e->stream;
+  // host half: inflated probability blocks of variants[] (index order) into pinned slot `slot`
+  void read_bgen(const uint32_t* variants, int n, int slot) {
     std::vector<std::pair<uint64_t, uint32_t>> payload(n);
     std::vector<uint64_t> starts(n + 1), lens(n);
     uint64_t cur = 0;
@@ -249,20 +252,55 @@ struct Stager {
       cur += ulen;
     }
     starts[n] = cur;
-    h_bytes.ensure(cur + 16);
-    for (int k = 0; k < n; ++k) {
-      scratch.resize(payload[k].second + 8);
-      s->read_at(payload[k].first, scratch.data(), payload[k].second);
-      inflated.resize(lens[k]);
-      bgen_inflate(*s, scratch.data(), payload[k].second, inflated);
-      memcpy(h_bytes.p + starts[k], inflated.data(), lens[k]);
+    if (cur + 16 > h_bgen[slot].n) fail("bgen: a batch of %d variants needs %llu bytes of staging, more than reserved", n, (unsigned long long)cur);
+    uint8_t* dst = h_bgen[slot].p;
+    {
+      // blocks are independent: read + inflate them on a few host threads (zlib / zstd are the cost)
+      if (s->bgen_compression == 2) {  // resolve the zstd entry point before the threads start
+        std::vector<uint8_t> none;
+        try { bgen_inflate(*s, nullptr, 0, none); } catch (const std::exception&) {}
+      }
+      const int threads = (int)std::min<unsigned>(std::min(16u, std::max(1u, std::thread::hardware_concurrency())), (unsigned)n);
+      std::vector<std::exception_ptr> err(std::max(threads, 1));
+      auto work = [&](int t) {
+        try {
+          std::vector<uint8_t> in, outv;
+          for (int k = t; k < n; k += threads) {
+            in.resize(payload[k].second + 8);
+            s->read_at(payload[k].first, in.data(), payload[k].second);
+            outv.resize(lens[k]);
+            bgen_inflate(*s, in.data(), payload[k].second, outv);
+            memcpy(dst + starts[k], outv.data(), lens[k]);
+          }
+        } catch (...) { err[t] = std::current_exception(); }
+      };
+      std::vector<std::thread> pool;
+      for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
+      if (threads > 0) work(0);
+      for (auto& th : pool) th.join();
+      for (auto& e2 : err) if (e2) std::rethrow_exception(e2);
     }
-    off = starts;
-    d_bytes.upload(h_bytes.p, cur + 16, st);
-    d_off.upload(off.data(), off.size(), st);
+    bgen_off[slot] = starts;
+  }
+  // device half
+  void upload_bgen(int n, int slot) {
+    cudaStream_t st = e->stream;
+    d_bytes.upload(h_bgen[slot].p, bgen_off[slot][n] + 16, st);
+    d_off.upload(bgen_off[slot].data(), bgen_off[slot].size(), st);
     d_err.ensure(n);
     n_rows_staged = n;
   }
+  // staging memory for batches of up to max_n variants: the uncompressed size of a block is bounded by its layout
+  void ensure_bgen(int max_n) {
+    const uint64_t per = s->bgen_layout == 1 ? 6ull * s->n_samples : 16ull + 9ull * s->n_samples;  // ploidy bytes + two probabilities of <= 32 bits
+    for (auto& b2 : h_bgen) b2.ensure((size_t)max_n * per + 16);
+  }
+  void stage_bgen(const uint32_t* variants, int n) {
+    ensure_bgen(n);
+    read_bgen(variants, n, 0);
+    upload_bgen(n, 0);
+  }
+
 
   void check_bgen_errors(int n) {
     h_err.resize(n);
@@ -574,13 +612,28 @@ int gwsem_gwas_run(gwsem_model* m, gwsem_source* s, const gwsem_job* job, int64_
       const int slot = (int)((at / batch) & 1);
       reading = std::async(std::launch::async, [&sg, &todo, at, cnt, slot] { sg.read_fixed(&todo[at], cnt, slot); });
     };
+    const bool ahead_bgen = s->kind == gwsem_source::kBgen;
+    auto start_read_bgen = [&](size_t at) {
+      if (at >= todo.size()) return;
+      const int cnt = (int)std::min<size_t>(batch, todo.size() - at);
+      const int slot = (int)((at / batch) & 1);
+      reading = std::async(std::launch::async, [&sg, &todo, at, cnt, slot] { sg.read_bgen(&todo[at], cnt, slot); });
+    };
     if (ahead) {
       sg.ensure_fixed((int)std::min<size_t>(batch, todo.size()));
       start_read(0);
     }
+    if (ahead_bgen) {
+      sg.ensure_bgen((int)std::min<size_t>(batch, todo.size()));
+      start_read_bgen(0);
+    }
+    static const bool timing = getenv("GWSEM_TIMING") != nullptr;   // development aid: phase times on stderr
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_stage = 0, t_fit = 0, t_wait = 0, t_dl = 0;
     for (size_t t0 = 0; t0 < todo.size(); t0 += batch) {
       const int n = (int)std::min<size_t>(batch, todo.size() - t0);
       const uint32_t* v = &todo[t0];
+      const double c0 = now();
       m->ensure_result_buffers(n);
       gwsem_result dres = m->device_result();
       if (ahead) {
@@ -600,7 +653,10 @@ int gwsem_gwas_run(gwsem_model* m, gwsem_source* s, const gwsem_job* job, int64_
           m->fit_rows_device(d_geno.p, d_maf.p, n, dres);
         }
       } else {
-        sg.stage_bgen(v, n);
+        reading.get();
+        sg.upload_bgen(n, (int)((t0 / batch) & 1));
+        start_read_bgen(t0 + batch);
+        if (timing) { GW_CUDA(cudaStreamSynchronize(st)); t_stage += now() - c0; }
         d_geno.ensure((size_t)n * sg.n_pad);
         d_maf.ensure(n);
         BgenBatch bb;
@@ -611,16 +667,23 @@ int gwsem_gwas_run(gwsem_model* m, gwsem_source* s, const gwsem_job* job, int64_
         sg.check_bgen_errors(n);
         m->fit_rows_device(d_geno.p, d_maf.p, n, dres);
       }
+      double c1 = 0;
+      if (timing) { GW_CUDA(cudaStreamSynchronize(st)); c1 = now(); t_fit += c1 - c0; }
       if (pending.valid()) pending.get();  // at most one batch in flight behind the device
+      if (timing) { t_wait += now() - c1; c1 = now(); }
       RowBatch& cur = rb[(t0 / batch) & 1];
       cur.resize(n, P);
       std::copy(v, v + n, cur.variant.begin());
       m->download_result(cur.view(), dres, n, 0);
       GW_CUDA(cudaStreamSynchronize(st));
+      if (timing) t_dl += now() - c1;
       pending = std::async(std::launch::async, [&write_batch, &cur] { write_batch(cur); });
       written += n;
     }
     if (pending.valid()) pending.get();
+    if (timing)
+      fprintf(stderr, "gwsem timing: batch %d, stage(bgen only) %.3f s, stage+fit %.3f s, wait-for-writer %.3f s, download %.3f s\n",
+              batch, t_stage, t_fit, t_wait, t_dl);
     fclose(fo);
     if (rows_written) *rows_written = written;
   });

@@ -462,13 +462,125 @@ __global__ void __launch_bounds__(128)
   if (t == 0) n_out[snp] = cnt;
 }
 
+// The same table with the people axis split over the eight warps of the CTA and S SNPs per CTA
+// sharing every feature load: lane = feature (NFG groups of 32), four people in flight per step.
+// Each warp owns a contiguous slice of people and sums it in order; the eight partial sums are then
+// added in warp order: deterministic.
+template <int S, int NFG>
+__global__ void __launch_bounds__(256)
+    power_sums_split_kernel(FitProgram fp, int n_snps, int n_src, int n_pad, const uint8_t* __restrict__ inc8,
+                            const double* __restrict__ geno, const double* __restrict__ featT, int n_featm_pad,
+                            double* __restrict__ R, int32_t* __restrict__ n_out) {
+  extern __shared__ double red[];   // [8][NFG * 32][5]
+  __shared__ int cnt_sh[8][S];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int snp0 = blockIdx.x * S, nf = fp.nf;
+  const double nan = __longlong_as_double(0x7FF8000000000000ll);
+  double acc[S][NFG][5];
+#pragma unroll
+  for (int s = 0; s < S; ++s)
+#pragma unroll
+    for (int q = 0; q < NFG; ++q)
+#pragma unroll
+      for (int a = 0; a < 5; ++a) acc[s][q][a] = 0.0;
+  int cnt[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) cnt[s] = 0;
+  const int chunk = ((n_src + 7) / 8 + 31) / 32 * 32;
+  const int lo = warp * chunk, hi = min(n_src, lo + chunk);
+  for (int i0 = lo; i0 < hi; i0 += 32) {
+    const int i = i0 + lane;
+    double g[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      g[s] = nan;
+      if (i < hi && inc8[i] && snp0 + s < n_snps) {
+        const double v = geno[(int64_t)(snp0 + s) * n_pad + i];
+        if (!isinf(v)) g[s] = v;
+      }
+    }
+    const int lim = min(32, hi - i0);
+    for (int j0 = 0; j0 < lim; j0 += 4) {
+      double h[4][NFG];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double* frow = featT + (int64_t)(i0 + j0 + u) * n_featm_pad;
+#pragma unroll
+        for (int q = 0; q < NFG; ++q) {
+          const int f = q * 32 + lane;
+          h[u][q] = (j0 + u < lim && f < nf) ? (f == 0 ? 1.0 : frow[f - 1]) : 0.0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const double gj = __shfl_sync(0xffffffffu, g[s], (j0 + u) & 31);
+          const bool ok = gj == gj && j0 + u < lim;
+          if (ok) ++cnt[s];
+          const double g1 = ok ? gj : 0.0, g2 = g1 * g1, g3 = g2 * g1, g4 = g2 * g2;
+#pragma unroll
+          for (int q = 0; q < NFG; ++q) {
+            const double hv = ok ? h[u][q] : 0.0;
+            acc[s][q][0] += hv;
+            acc[s][q][1] = fma(g1, hv, acc[s][q][1]);
+            acc[s][q][2] = fma(g2, hv, acc[s][q][2]);
+            acc[s][q][3] = fma(g3, hv, acc[s][q][3]);
+            acc[s][q][4] = fma(g4, hv, acc[s][q][4]);
+          }
+        }
+      }
+    }
+  }
+  if (lane == 0)
+#pragma unroll
+    for (int s = 0; s < S; ++s) cnt_sh[warp][s] = cnt[s];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NFG; ++q)
+#pragma unroll
+      for (int a = 0; a < 5; ++a) red[((warp * NFG + q) * 32 + lane) * 5 + a] = acc[s][q][a];
+    __syncthreads();
+    if (snp0 + s < n_snps) {
+      for (int e = tid; e < NFG * 32 * 5; e += 256) {
+        const int f = e / 5, a = e % 5;
+        if (f >= nf) continue;
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[(w * NFG * 32 + f) * 5 + a];
+        R[(int64_t)(snp0 + s) * 5 * nf + a * nf + f] = v;
+      }
+      if (tid == 0) {
+        int c = 0;
+        for (int w = 0; w < 8; ++w) c += cnt_sh[w][s];
+        n_out[snp0 + s] = c;
+      }
+    }
+  }
+}
+
 void launch_power_sums(gwsem_engine* e, const FitProgram& fp, const PeopleLayout& pl, int n_snps,
                        const double* d_geno, const double* d_featT, int n_featm_pad, double* d_R, int32_t* d_n) {
   if (n_snps <= 0) return;
   if (fp.nf > 256) fail("too many features for the generic statistics kernel (%d > 256)", fp.nf);
-  power_sums_kernel<<<n_snps, 128, 0, e->stream>>>(fp, pl.n_src, pl.n_pad, pl.d_inc8, d_geno, d_featT, n_featm_pad,
-                                                   d_R, d_n);
+  e->prof_begin(kFamClassSums);
+  const int nfg = (fp.nf + 31) / 32;
+#define GW_PS(SS, NFG)                                                                                               \
+  {                                                                                                                  \
+    const size_t smem = (size_t)8 * NFG * 32 * 5 * sizeof(double);                                                   \
+    GW_CUDA(cudaFuncSetAttribute(power_sums_split_kernel<SS, NFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    power_sums_split_kernel<SS, NFG><<<(n_snps + SS - 1) / SS, 256, smem, e->stream>>>(                              \
+        fp, n_snps, pl.n_src, pl.n_pad, pl.d_inc8, d_geno, d_featT, n_featm_pad, d_R, d_n);                          \
+  }
+  if (nfg == 1) GW_PS(4, 1)
+  else if (nfg == 2) GW_PS(4, 2)
+  else if (nfg <= 4) GW_PS(2, 4)
+  else GW_PS(1, 8)
+#undef GW_PS
   GW_CUDA(cudaGetLastError());
+  e->prof_end(kFamClassSums);
   e->launches++;
 }
 
