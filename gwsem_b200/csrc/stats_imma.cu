@@ -71,22 +71,41 @@ __global__ void __launch_bounds__(WARPS * 32)
   const int snp0 = blockIdx.x * kSnps;
   const int n_tiles = (n_blocks + kBlocks - 1) / kBlocks;
 
+  // Staging with cp.async: a thread copies the same 16-byte column of kPasses rows of every tile and the
+  // same pieces of the (tile-padded, contiguous) feature block, so the addresses are one pointer bump
+  // per copy -- the generic index arithmetic cost a third of the kernel's instructions.
+  constexpr int kThreads = WARPS * 32;
+  constexpr int kPieces = TILE / 64;                  // 16-byte pieces per staged row
+  constexpr int kRowsPerPass = kThreads / kPieces;
+  constexpr int kPasses = kSnps / kRowsPerPass;
+  constexpr int kBCopies = kBStage / 16 / kThreads;
+  static_assert(kThreads % kPieces == 0 && kSnps % kRowsPerPass == 0 && kBStage % (16 * kThreads) == 0, "staging layout");
+  const int gc = tid % kPieces, gr = tid / kPieces;
+  const int64_t pass_stride = (int64_t)kRowsPerPass * pitch;
+  const uint8_t* gsrc = rows + (int64_t)(snp0 + gr) * pitch + gc * 16;
+  const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem);
+  const unsigned gdst = smem0 + gr * kGRow + gc * 16;
+  const unsigned bdst = smem0 + kGStage + tid * 16;
+  const int8_t* bsrc = Bq + tid * 16;
+  unsigned row_ok = 0;
+#pragma unroll
+  for (int k = 0; k < kPasses; ++k) row_ok |= (snp0 + gr + k * kRowsPerPass < n_snps ? 1u : 0u) << k;
   auto load_stage = [&](int tile, int s) {
-    // genotype rows: kSnps x (TILE / 4) bytes in 16-byte pieces
-    constexpr int kPieces = TILE / 64;
-    for (int idx = tid; idx < kSnps * kPieces; idx += WARPS * 32) {
-      const int r = idx / kPieces, c = idx % kPieces;
-      const int64_t off = (int64_t)tile * (TILE / 4) + c * 16;
-      const bool ok = snp0 + r < n_snps && off + 16 <= pitch;
-      cp_async16(smem + s * kStage + r * kGRow + c * 16, rows + (ok ? (int64_t)(snp0 + r) * pitch + off : 0), ok);
+    const bool col_ok = (int64_t)tile * (TILE / 4) + gc * 16 + 16 <= pitch;
+    const uint8_t* p = gsrc + (int64_t)tile * (TILE / 4);
+    const unsigned d = gdst + s * kStage;
+#pragma unroll
+    for (int k = 0; k < kPasses; ++k) {
+      const bool ok = col_ok && ((row_ok >> k) & 1u);
+      const int bytes = ok ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d + k * kRowsPerPass * kGRow), "l"(ok ? p : rows), "r"(bytes) : "memory");
+      p += pass_stride;
     }
-    // feature block: contiguous kBStage bytes
-    const int64_t base = (int64_t)tile * kBStage, limit = (int64_t)n_blocks * NT * 8 * 32;
-    for (int idx = tid; idx < kBStage / 16; idx += WARPS * 32) {
-      const int64_t off = base + (int64_t)idx * 16;
-      const bool ok = off + 16 <= limit;
-      cp_async16(smem + s * kStage + kGStage + idx * 16, Bq + (ok ? off : 0), ok);
-    }
+    const int8_t* q = bsrc + (int64_t)tile * kBStage;
+    const unsigned db = bdst + s * kStage;
+#pragma unroll
+    for (int k = 0; k < kBCopies; ++k)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(db + k * kThreads * 16), "l"(q + k * kThreads * 16) : "memory");
     cp_async_commit();
   };
 
@@ -97,9 +116,11 @@ __global__ void __launch_bounds__(WARPS * 32)
     for (int j = 0; j < NT; ++j)
 #pragma unroll
       for (int k = 0; k < 4; ++k) acc[m][j][k] = 0;
-  // PRMT tables (kernel arguments tab1 / tab2): byte index = 2-bit code, 1 where the code is the class.
-  // het: PLINK 2 code 1, PLINK 1 code 2; hom ALT: PLINK 2 code 2, PLINK 1 code 0.
-  const unsigned pick = (unsigned)t | ((unsigned)(4 + t) << 4);  // bytes t of both words of the 64-bit block
+  // PRMT tables (kernel arguments tab1 / tab2): byte index = 2-bit code, 0xFF (-1 as s8) where the code is
+  // the class.  het: PLINK 2 code 1, PLINK 1 code 2; hom ALT: PLINK 2 code 2, PLINK 1 code 0.
+  // A selector nibble is four raw bits [c' c' c c]: bits 0-1 are the person's code, bit 2 picks the same
+  // table again (both PRMT operands hold it) and bit 3 asks for sign replication, which maps 0x00 / 0xFF
+  // to themselves -- so the packed word is the selector as it is, without masking or nibble spreading.
 
   load_stage(0, 0);
   for (int tile = 0; tile < n_tiles; ++tile) {
@@ -111,31 +132,44 @@ __global__ void __launch_bounds__(WARPS * 32)
       cp_async_wait<0>();
     }
     __syncthreads();
-    const uint8_t* Gw = smem + s * kStage + (warp * MT * 8 + g) * kGRow;
+    const uint8_t* Gw = smem + s * kStage + (warp * MT * 8 + g) * kGRow + t * 4;
     const uint8_t* Bw = smem + s * kStage + kGStage + g * 32 + t * 8;
 #pragma unroll 2
-    for (int kb = 0; kb < kBlocks; ++kb) {
-      uint2 bf[NT];
+    for (int kp = 0; kp < kBlocks / 2; ++kp) {   // a pair of 32-person blocks = one 16-byte piece of a packed row
+      uint2 bf[2][NT];
 #pragma unroll
-      for (int j = 0; j < NT; ++j) bf[j] = *reinterpret_cast<const uint2*>(Bw + (kb * NT * 8 + j * 8) * 32);
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) bf[h][j] = *reinterpret_cast<const uint2*>(Bw + ((2 * kp + h) * NT * 8 + j * 8) * 32);
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
-        const uint2 w = *reinterpret_cast<const uint2*>(Gw + m * 8 * kGRow + kb * 8);
-        unsigned x = __byte_perm(w.x, w.y, pick);    // byte 0: people 4t..4t+3, byte 1: people 16+4t..
-        x = __byte_perm(x, 0u, 0x4140);              // 0x00HH00LL
-        // spread with multiply-adds (FMA pipe) instead of shift-or-mask (ALU pipe, the busy one):
-        // a byte 16 h + l becomes 256 h + l, then a nibble 4 c1 + c0 becomes 16 c1 + c0
-        x = (x & 0x00F000F0u) * 15u + x;             // 0x0H0H0L0L
-        x = (x & 0x0C0C0C0Cu) * 3u + x;              // eight nibbles = eight 2-bit codes
-        const unsigned xh = x >> 16;
-        const unsigned a0 = prmt(tab1, 0u, x), a1 = prmt(tab2, 0u, x);
-        const unsigned a2 = prmt(tab1, 0u, xh), a3 = prmt(tab2, 0u, xh);
+        // 16 people of this lane's SNP: codes 0-7 feed the first block of the pair, 8-15 the second;
+        // within a block the even codes are k = 4t.., the odd ones k = 16 + 4t..
+        const unsigned w = *reinterpret_cast<const unsigned*>(Gw + m * 8 * kGRow + kp * 16);
+        const unsigned w2 = w >> 2, wh = w >> 16, wh2 = w >> 18;
+        {
+          const unsigned a0 = prmt(tab1, tab1, w), a1 = prmt(tab2, tab2, w);
+          const unsigned a2 = prmt(tab1, tab1, w2), a3 = prmt(tab2, tab2, w2);
 #pragma unroll
-        for (int j = 0; j < NT; ++j) mma_s8(acc[m][j], a0, a1, a2, a3, bf[j].x, bf[j].y);
+          for (int j = 0; j < NT; ++j) mma_s8(acc[m][j], a0, a1, a2, a3, bf[0][j].x, bf[0][j].y);
+        }
+        {
+          const unsigned a0 = prmt(tab1, tab1, wh), a1 = prmt(tab2, tab2, wh);
+          const unsigned a2 = prmt(tab1, tab1, wh2), a3 = prmt(tab2, tab2, wh2);
+#pragma unroll
+          for (int j = 0; j < NT; ++j) mma_s8(acc[m][j], a0, a1, a2, a3, bf[1][j].x, bf[1][j].y);
+        }
       }
     }
     __syncthreads();
   }
+  // the one-hot entries are -1: the accumulators hold the negated sums
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[m][j][k] = -acc[m][j][k];
   // ---- recombine the digits: a thread holds digits (0,1) or (2,3) of one feature per n-tile
 #pragma unroll
   for (int m = 0; m < MT; ++m) {
@@ -173,11 +207,11 @@ void launch_imma(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_
   if (plink1) {
     auto k = class_sums_imma_kernel<NT, MT, WARPS, TILE, true>;
     GW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, WARPS * 32, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums, 0x00010000u, 0x00000001u, d_counts, count_slot);
+    k<<<grid, WARPS * 32, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums, 0x00FF0000u, 0x000000FFu, d_counts, count_slot);
   } else {
     auto k = class_sums_imma_kernel<NT, MT, WARPS, TILE, false>;
     GW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, WARPS * 32, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums, 0x00000100u, 0x00010000u, d_counts, count_slot);
+    k<<<grid, WARPS * 32, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums, 0x0000FF00u, 0x00FF0000u, d_counts, count_slot);
   }
   GW_CUDA(cudaGetLastError());
   e->launches++;
@@ -186,13 +220,25 @@ void launch_imma(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_
 }  // namespace
 
 int imma_chunk_features(int n_feat) { return n_feat <= 4 ? 4 : 16; }
+// 32-person blocks of the digit layout, padded with zero blocks to whole staging tiles of any kernel
+// variant (TILE <= 1024 people): the feature copies need no bounds check
+static inline int imma_blocks(int n_pad) { return (n_pad / 32 + 31) / 32 * 32; }
 
 // Host side of the digit layout: chunk c covers features [c * cf, (c + 1) * cf), cf = imma_chunk_features;
-// within a chunk: [block of 32 people][column = feature_in_chunk * 4 + digit][position], position of
-// person k in the block = 8 * ((k % 16) / 4) + 4 * (k / 16) + k % 4 (the two halves a thread needs are adjacent).
+// within a chunk: [block of 32 people][column = feature_in_chunk * 4 + digit][position].  Person p of a pair of
+// blocks (64 people = 16 packed bytes) sits in 32-bit word t = p / 16 of the piece, which lane t expands: codes
+// 0-7 of the word go to the first block, 8-15 to the second, even codes to MMA k = 4t + j, odd ones to
+// k = 16 + 4t + j (j = code index / 2); position of k in the block = 8 * ((k % 16) / 4) + 4 * (k / 16) + k % 4
+// (the two halves of a thread's B fragment are adjacent).
+static inline void imma_position(int i, int& blk, int& pos) {
+  const int p = i % 64, t = p / 16, r = p % 16, r8 = r % 8;
+  const int k = 16 * (r8 & 1) + 4 * t + r8 / 2;
+  blk = (i / 64) * 2 + r / 8;
+  pos = 8 * ((k % 16) / 4) + 4 * (k / 16) + k % 4;
+}
 size_t imma_feature_bytes(int n_feat, int n_pad) {
   const int cf = imma_chunk_features(n_feat), chunks = (n_feat + cf - 1) / cf;
-  return (size_t)chunks * (n_pad / 32) * (cf * 4) * 32;
+  return (size_t)chunks * imma_blocks(n_pad) * (cf * 4) * 32;
 }
 
 bool imma_has_counts(int n_feat) { return n_feat > 0 && n_feat % imma_chunk_features(n_feat) != 0; }
@@ -200,14 +246,15 @@ bool imma_has_counts(int n_feat) { return n_feat > 0 && n_feat % imma_chunk_feat
 void imma_pack_features(const std::vector<std::vector<int64_t>>& q, int n_pad, const std::vector<uint8_t>& inc8,
                         const std::vector<uint8_t>& kept, std::vector<int8_t>& out) {
   const int n_feat = (int)q.size(), cf = imma_chunk_features(n_feat), chunks = (n_feat + cf - 1) / cf;
-  const int n_blocks = n_pad / 32, ncol = cf * 4;
+  const int n_blocks = imma_blocks(n_pad), ncol = cf * 4;
   out.assign(imma_feature_bytes(n_feat, n_pad), 0);
   for (int f = 0; f < n_feat; ++f) {
     const int c = f / cf, fi = f % cf;
     int8_t* base = out.data() + (size_t)c * n_blocks * ncol * 32;
     for (int i = 0; i < n_pad; ++i) {
       int64_t v = q[f][i];
-      const int blk = i / 32, k = i % 32, pos = 8 * ((k % 16) / 4) + 4 * (k / 16) + k % 4;
+      int blk, pos;
+      imma_position(i, blk, pos);
       for (int d = 0; d < 4; ++d) {
         const int64_t digit = ((v + 128) & 255) - 128;  // balanced digit in [-128, 127]
         base[((size_t)blk * ncol + fi * 4 + d) * 32 + pos] = (int8_t)digit;
@@ -220,7 +267,8 @@ void imma_pack_features(const std::vector<std::vector<int64_t>>& q, int n_pad, c
     const int c = n_feat / cf, fi = n_feat % cf;
     int8_t* base = out.data() + (size_t)c * n_blocks * ncol * 32;
     for (int i = 0; i < n_pad; ++i) {
-      const int blk = i / 32, k = i % 32, pos = 8 * ((k % 16) / 4) + 4 * (k / 16) + k % 4;
+      int blk, pos;
+      imma_position(i, blk, pos);
       base[((size_t)blk * ncol + fi * 4 + 0) * 32 + pos] = inc8[i] ? 1 : 0;
       base[((size_t)blk * ncol + fi * 4 + 1) * 32 + pos] = kept[i] ? 1 : 0;
     }
@@ -234,7 +282,8 @@ void launch_class_sums_imma(gwsem_engine* e, const uint8_t* d_packed, int64_t pi
   if (pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(d_packed) & 15))
     fail("packed genotype rows must be 16-byte aligned with a pitch that is a multiple of 16 (pitch=%lld)",
          (long long)pitch);
-  const int n_blocks = pl.n_pad / 32, cf = imma_chunk_features(n_feat);
+  const int n_blocks = imma_blocks(pl.n_pad), cf = imma_chunk_features(n_feat);
+  const int n_live = (pl.n_pad / 32 + 1) / 2 * 2;   // blocks that hold people (whole pairs); the rest is padding
   e->prof_begin(kFamClassSums);
   for (int f0 = 0, c = 0; f0 < n_feat; f0 += cf, ++c) {
     const int8_t* Bq = d_featq + (size_t)c * n_blocks * (cf * 4) * 32;
@@ -245,18 +294,23 @@ void launch_class_sums_imma(gwsem_engine* e, const uint8_t* d_packed, int64_t pi
     if (cf == 4) {
       static const int variant = getenv("GWSEM_IMMA_VARIANT") ? atoi(getenv("GWSEM_IMMA_VARIANT")) : 0;  // tuning aid
       switch (variant) {  //          NT MT WARPS TILE
-        case 1: launch_imma<2, 2, 8, 1024>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        case 2: launch_imma<2, 4, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        case 3: launch_imma<2, 2, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        case 4: launch_imma<2, 2, 4, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        case 5: launch_imma<2, 4, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        case 6: launch_imma<2, 2, 8, 256>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        case 7: launch_imma<2, 1, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        case 8: launch_imma<2, 4, 4, 1024>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        default: launch_imma<2, 4, 4, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        case 9: launch_imma<2, 4, 4, 256>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        case 10: launch_imma<2, 2, 4, 256>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        case 11: launch_imma<2, 4, 8, 256>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        case 12: launch_imma<2, 2, 2, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        case 13: launch_imma<2, 4, 2, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        case 1: launch_imma<2, 2, 8, 1024>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        case 2: launch_imma<2, 4, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        case 3: launch_imma<2, 2, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        case 4: launch_imma<2, 4, 4, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        case 5: launch_imma<2, 4, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        case 6: launch_imma<2, 2, 8, 256>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        case 7: launch_imma<2, 1, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        case 8: launch_imma<2, 4, 4, 1024>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        default: launch_imma<2, 2, 4, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
       }
     }
-    else launch_imma<8, 2, 4, 512>(e, d_packed, pitch, n_snps, plink1, n_blocks, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot);
+    else launch_imma<8, 2, 4, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot);
   }
   e->prof_end(kFamClassSums);
 }
