@@ -33,20 +33,24 @@ int imma_chunk_features(int n_feat);
 size_t imma_feature_bytes(int n_feat, int n_pad);
 // inc8 / kept (n_pad each, non-zero = member): when the last chunk has a free feature slot its first two
 // columns hold these indicators and the kernel also writes the het / hom-ALT counts of both sets into
-// d_counts[snp][0,1,3,4] (imma_has_counts)
+// d_counts[snp][0,1,3,4] (imma_has_counts) and, when d_miss_list is given, appends the SNPs that have a code-3
+// (PLINK 1: code-1) call anywhere in their row to d_miss_list (count in *d_miss_n, zeroed by the caller);
+// launch_count_missing(light, d_list, d_list_n) then visits only those rows
 bool imma_has_counts(int n_feat);
 void imma_pack_features(const std::vector<std::vector<int64_t>>& q, int n_pad, const std::vector<uint8_t>& inc8,
                         const std::vector<uint8_t>& kept, std::vector<int8_t>& out);
 void launch_class_sums_imma(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
                             const PeopleLayout& pl, const int8_t* d_featq, const double* d_inv_scale, int n_feat,
-                            double* d_sums, int32_t* d_counts);
+                            double* d_sums, int32_t* d_counts, int32_t* d_miss_list = nullptr,
+                            int32_t* d_miss_n = nullptr);
 
 // counts[snp][8] = {n_class1, n_class2, n_missing over included people; the same three over the
 // people kept by rowFilter (for MAF); 0; 0} and, for the missing class, sums of `n_featm`
 // person-major features (d_featT[person][n_featm_pad]): d_miss[snp][n_featm].
 void launch_count_missing(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
                           const PeopleLayout& pl, const double* d_featT, int n_featm, int n_featm_pad,
-                          int32_t* d_counts, double* d_miss, bool light = false);
+                          int32_t* d_counts, double* d_miss, bool light = false, const int32_t* d_list = nullptr,
+                          const int32_t* d_list_n = nullptr);
 
 // ---- fit.cu
 struct FitProgram;  // device-resident model description, built in model.cu

@@ -412,10 +412,24 @@ void gwsem_model::fit_2bit_device(const uint8_t* d_packed, int64_t pitch, int n_
     }
     static const bool dfma_first = getenv("GWSEM_CS_DFMA") != nullptr;
     const bool light = !dfma_first && imma_has_counts(nfd);
-    launch_count_missing(engine, rows, pitch, n, plink1, layout, d_featT, nfm, nfm_pad, d_counts.p, d_miss.p, light);
     static const bool dfma = getenv("GWSEM_CS_DFMA") != nullptr;  // A/B aid: the FP64 class-sum kernel
-    if (dfma) launch_class_sums(engine, rows, pitch, n, plink1, layout, d_feat, nfd, d_sums.p);
-    else launch_class_sums_imma(engine, rows, pitch, n, plink1, layout, d_featq, d_inv_scale, nfd, d_sums.p, d_counts.p);
+    if (light) {
+      // the class-sum kernel lists the SNPs that have a missing call; count_missing then reads only those rows
+      // (none in imputed data) instead of streaming the whole batch a second time
+      d_miss_list.ensure((size_t)n + 1);
+      cudaStream_t st = engine->stream;
+      GW_CUDA(cudaMemsetAsync(d_miss_list.p + n, 0, sizeof(int32_t), st));
+      GW_CUDA(cudaMemsetAsync(d_counts.p, 0, 8 * (size_t)n * sizeof(int32_t), st));
+      GW_CUDA(cudaMemsetAsync(d_miss.p, 0, (size_t)std::max(nfm, 1) * n * sizeof(double), st));
+      launch_class_sums_imma(engine, rows, pitch, n, plink1, layout, d_featq, d_inv_scale, nfd, d_sums.p, d_counts.p,
+                             d_miss_list.p, d_miss_list.p + n);
+      launch_count_missing(engine, rows, pitch, n, plink1, layout, d_featT, nfm, nfm_pad, d_counts.p, d_miss.p, true,
+                           d_miss_list.p, d_miss_list.p + n);
+    } else {
+      launch_count_missing(engine, rows, pitch, n, plink1, layout, d_featT, nfm, nfm_pad, d_counts.p, d_miss.p, false);
+      if (dfma) launch_class_sums(engine, rows, pitch, n, plink1, layout, d_feat, nfd, d_sums.p);
+      else launch_class_sums_imma(engine, rows, pitch, n, plink1, layout, d_featq, d_inv_scale, nfd, d_sums.p, d_counts.p);
+    }
     gwsem_result r = d_res;
     r.est += (size_t)s0 * P; r.vcov += (size_t)s0 * P * P; r.fit += s0; r.maf += s0; r.n_used += s0;
     r.status += s0; r.catch_code += s0; r.catch_var += s0; r.iterations += s0;

@@ -35,7 +35,7 @@ struct gwsem_model {
   const double* d_inv_scale = nullptr;    // 2^-s_f per dense feature
   const int32_t* d_dest_of = nullptr;
   std::vector<gwsem::DeviceBuffer<uint8_t>> pool;
-  gwsem::DeviceBuffer<int32_t> d_counts;
+  gwsem::DeviceBuffer<int32_t> d_counts, d_miss_list;
   gwsem::DeviceBuffer<double> d_sums, d_miss, d_R, d_mafs;
   gwsem::DeviceBuffer<int32_t> d_nrows;
   gwsem::DeviceBuffer<uint8_t> d_stage2[2];

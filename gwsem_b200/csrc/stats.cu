@@ -259,10 +259,15 @@ __global__ void __launch_bounds__(128)
     count_missing_kernel(const uint8_t* __restrict__ packed, int64_t pitch, int n_snps, int n_pad,
                          const unsigned long long* __restrict__ incmask,
                          const unsigned long long* __restrict__ rowmask, const double* __restrict__ featT,
-                         int n_featm, int n_featm_pad, int32_t* __restrict__ counts, double* __restrict__ miss) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+                         int n_featm, int n_featm_pad, int32_t* __restrict__ counts, double* __restrict__ miss,
+                         const int32_t* __restrict__ list, const int32_t* __restrict__ list_n) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n_snps) return;
+  if (list) {   // only the rows the class-sum kernel found a missing call in (any order: rows are independent)
+    if (row >= *list_n) return;
+    row = list[row];
+  }
   const unsigned long long* words = reinterpret_cast<const unsigned long long*>(packed + (int64_t)row * pitch);
   const int n_words = n_pad >> 5;
   int c1 = 0, c2 = 0, c3 = 0, r1 = 0, r2 = 0, r3 = 0;
@@ -343,7 +348,8 @@ __global__ void __launch_bounds__(128)
 
 void launch_count_missing(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
                           const PeopleLayout& pl, const double* d_featT, int n_featm, int n_featm_pad,
-                          int32_t* d_counts, double* d_miss, bool light) {
+                          int32_t* d_counts, double* d_miss, bool light, const int32_t* d_list,
+                          const int32_t* d_list_n) {
   if (n_snps <= 0) return;
   if (n_featm > 256) fail("too many missing-class features (%d > 256)", n_featm);
   if (pitch % 8 != 0 || pitch * 4 < pl.n_pad) fail("pitch %lld too small for %d padded people", (long long)pitch, pl.n_pad);
@@ -352,7 +358,7 @@ void launch_count_missing(gwsem_engine* e, const uint8_t* d_packed, int64_t pitc
   e->prof_begin(kFamCountMissing);
 #define GW_CM(P1, LT)                                                                                              \
   count_missing_kernel<P1, LT><<<grid, warps * 32, 0, e->stream>>>(d_packed, pitch, n_snps, pl.n_pad, pl.d_incmask, \
-                                                                   pl.d_rowmask, d_featT, n_featm, n_featm_pad, d_counts, d_miss)
+                                                                   pl.d_rowmask, d_featT, n_featm, n_featm_pad, d_counts, d_miss, d_list, d_list_n)
   if (plink1) { if (light) GW_CM(true, true); else GW_CM(true, false); }
   else { if (light) GW_CM(false, true); else GW_CM(false, false); }
 #undef GW_CM

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(WARPS * 32)
     class_sums_imma_kernel(const uint8_t* __restrict__ rows, int64_t pitch, int n_snps, int n_blocks,
                            const int8_t* __restrict__ Bq, const double* __restrict__ inv_scale, int f0, int n_feat,
                            double* __restrict__ sums, unsigned tab1, unsigned tab2, int32_t* __restrict__ counts,
-                           int count_slot) {
+                           int count_slot, int32_t* __restrict__ miss_list, int32_t* __restrict__ miss_n) {
   constexpr int kSnps = WARPS * MT * 8;
   constexpr int kGRow = TILE / 4 + kGPad;            // staged genotype row, bytes
   constexpr int kBlocks = TILE / 32;                 // 32-person blocks per stage
@@ -116,6 +116,12 @@ __global__ void __launch_bounds__(WARPS * 32)
     for (int j = 0; j < NT; ++j)
 #pragma unroll
       for (int k = 0; k < 4; ++k) acc[m][j][k] = 0;
+  // Missing calls (code 3; PLINK 1: code 1) are rare or absent in imputed data: every packed word is OR-ed
+  // into a per-SNP detector (one multiply-by-two and one LOP3), and only the SNPs that trip it are listed
+  // for count_missing_kernel.  People masks are not applied here: a false positive only costs time.
+  unsigned mdet[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) mdet[m] = 0u;
   // PRMT tables (kernel arguments tab1 / tab2): byte index = 2-bit code, 0xFF (-1 as s8) where the code is
   // the class.  het: PLINK 2 code 1, PLINK 1 code 2; hom ALT: PLINK 2 code 2, PLINK 1 code 0.
   // A selector nibble is four raw bits [c' c' c c]: bits 0-1 are the person's code, bit 2 picks the same
@@ -146,7 +152,8 @@ __global__ void __launch_bounds__(WARPS * 32)
         // 16 people of this lane's SNP: codes 0-7 feed the first block of the pair, 8-15 the second;
         // within a block the even codes are k = 4t.., the odd ones k = 16 + 4t..
         const unsigned w = *reinterpret_cast<const unsigned*>(Gw + m * 8 * kGRow + kp * 16);
-        const unsigned w2 = w >> 2, wh = w >> 16, wh2 = w >> 18;
+        const unsigned w2 = w >> 2, wh = w >> 16, wh2 = w >> 18, ws = w * 2u;
+        mdet[m] |= PLINK1 ? (~w & ws) : (w & ws);   // odd bits: low and high bit of a code both set (PLINK 1: low only)
         {
           const unsigned a0 = prmt(tab1, tab1, w), a1 = prmt(tab2, tab2, w);
           const unsigned a2 = prmt(tab1, tab1, w2), a3 = prmt(tab2, tab2, w2);
@@ -162,6 +169,16 @@ __global__ void __launch_bounds__(WARPS * 32)
       }
     }
     __syncthreads();
+  }
+  if (miss_list) {
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      unsigned f = mdet[m] & 0xAAAAAAAAu;
+      f |= __shfl_xor_sync(0xffffffffu, f, 1);
+      f |= __shfl_xor_sync(0xffffffffu, f, 2);
+      const int snp = snp0 + (warp * MT + m) * 8 + g;
+      if (t == 0 && f != 0u && snp < n_snps) miss_list[atomicAdd(miss_n, 1)] = snp;
+    }
   }
   // the one-hot entries are -1: the accumulators hold the negated sums
 #pragma unroll
@@ -200,18 +217,18 @@ __global__ void __launch_bounds__(WARPS * 32)
 template <int NT, int MT, int WARPS, int TILE>
 void launch_imma(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1, int n_blocks,
                  const int8_t* Bq, const double* inv_scale, int f0, int n_feat, double* d_sums, int32_t* d_counts,
-                 int count_slot) {
+                 int count_slot, int32_t* d_miss_list, int32_t* d_miss_n) {
   constexpr int kSnps = WARPS * MT * 8;
   const size_t smem = 2 * ((size_t)kSnps * (TILE / 4 + kGPad) + (size_t)(TILE / 32) * NT * 8 * 32);
   const int grid = (n_snps + kSnps - 1) / kSnps;
   if (plink1) {
     auto k = class_sums_imma_kernel<NT, MT, WARPS, TILE, true>;
     GW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, WARPS * 32, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums, 0x00FF0000u, 0x000000FFu, d_counts, count_slot);
+    k<<<grid, WARPS * 32, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums, 0x00FF0000u, 0x000000FFu, d_counts, count_slot, d_miss_list, d_miss_n);
   } else {
     auto k = class_sums_imma_kernel<NT, MT, WARPS, TILE, false>;
     GW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, WARPS * 32, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums, 0x0000FF00u, 0x00FF0000u, d_counts, count_slot);
+    k<<<grid, WARPS * 32, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums, 0x0000FF00u, 0x00FF0000u, d_counts, count_slot, d_miss_list, d_miss_n);
   }
   GW_CUDA(cudaGetLastError());
   e->launches++;
@@ -277,7 +294,7 @@ void imma_pack_features(const std::vector<std::vector<int64_t>>& q, int n_pad, c
 
 void launch_class_sums_imma(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
                             const PeopleLayout& pl, const int8_t* d_featq, const double* d_inv_scale, int n_feat,
-                            double* d_sums, int32_t* d_counts) {
+                            double* d_sums, int32_t* d_counts, int32_t* d_miss_list, int32_t* d_miss_n) {
   if (n_snps <= 0 || n_feat <= 0) return;
   if (pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(d_packed) & 15))
     fail("packed genotype rows must be 16-byte aligned with a pitch that is a multiple of 16 (pitch=%lld)",
@@ -291,26 +308,28 @@ void launch_class_sums_imma(gwsem_engine* e, const uint8_t* d_packed, int64_t pi
     const bool last = f0 + cf >= n_feat;
     int32_t* d_cnt = (last && d_counts && imma_has_counts(n_feat)) ? d_counts : nullptr;
     const int count_slot = n_feat % cf;
+    int32_t* d_ml = d_cnt ? d_miss_list : nullptr;   // the chunk that writes the counts also lists the SNPs with missing calls
+    int32_t* d_mn = d_cnt ? d_miss_n : nullptr;
     if (cf == 4) {
       static const int variant = getenv("GWSEM_IMMA_VARIANT") ? atoi(getenv("GWSEM_IMMA_VARIANT")) : 0;  // tuning aid
       switch (variant) {  //          NT MT WARPS TILE
-        case 9: launch_imma<2, 4, 4, 256>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        case 10: launch_imma<2, 2, 4, 256>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        case 11: launch_imma<2, 4, 8, 256>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        case 12: launch_imma<2, 2, 2, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        case 13: launch_imma<2, 4, 2, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        case 1: launch_imma<2, 2, 8, 1024>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        case 2: launch_imma<2, 4, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        case 3: launch_imma<2, 2, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        case 4: launch_imma<2, 4, 4, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        case 5: launch_imma<2, 4, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        case 6: launch_imma<2, 2, 8, 256>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        case 7: launch_imma<2, 1, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        case 8: launch_imma<2, 4, 4, 1024>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
-        default: launch_imma<2, 2, 4, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot); break;
+        case 9: launch_imma<2, 4, 4, 256>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn); break;
+        case 10: launch_imma<2, 2, 4, 256>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn); break;
+        case 11: launch_imma<2, 4, 8, 256>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn); break;
+        case 12: launch_imma<2, 2, 2, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn); break;
+        case 13: launch_imma<2, 4, 2, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn); break;
+        case 1: launch_imma<2, 2, 8, 1024>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn); break;
+        case 2: launch_imma<2, 4, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn); break;
+        case 3: launch_imma<2, 2, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn); break;
+        case 4: launch_imma<2, 4, 4, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn); break;
+        case 5: launch_imma<2, 4, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn); break;
+        case 6: launch_imma<2, 2, 8, 256>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn); break;
+        case 7: launch_imma<2, 1, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn); break;
+        case 8: launch_imma<2, 4, 4, 1024>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn); break;
+        default: launch_imma<2, 2, 4, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn); break;
       }
     }
-    else launch_imma<8, 2, 4, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot);
+    else launch_imma<8, 2, 4, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn);
   }
   e->prof_end(kFamClassSums);
 }

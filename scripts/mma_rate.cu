@@ -35,7 +35,7 @@ __global__ void mma_kernel(int* out, int iters, unsigned seed) {
 // IMMA mixed with independent integer ALU work (PRMT / SHF as in the one-hot expansion): do the pipes overlap?
 template <int NACC, int ALU>
 __global__ void mix_kernel(int* out, int iters, unsigned seed) {
-  int acc[NACC][4];
+  int acc[NACC + 1][4];
   for (int k = 0; k < NACC; ++k)
     for (int j = 0; j < 4; ++j) acc[k][j] = 0;
   unsigned a0 = seed + threadIdx.x, a1 = a0 * 3u, a2 = a0 * 5u, a3 = a0 * 7u, b0 = a0 ^ 0x1234u, b1 = a0 ^ 0x4321u;
@@ -93,6 +93,6 @@ int main() {
   for (int w : {4, 8, 16}) run<0, 8>(w, "imma s8");
   for (int w : {4, 8, 16}) run<2, 8>(w, "imma k16");
   for (int w : {4, 16}) run<1, 8>(w, "bmma b1");
-  for (int w : {8, 16}) { run_mix<8, 0>(w); run_mix<0, 24>(w); run_mix<8, 24>(w); run_mix<8, 48>(w); }
+  for (int w : {8, 16}) { run_mix<8, 0>(w); run_mix<1, 24>(w); run_mix<8, 24>(w); run_mix<8, 48>(w); }
   return 0;
 }
