@@ -44,6 +44,17 @@ void launch_class_sums_imma(gwsem_engine* e, const uint8_t* d_packed, int64_t pi
                             double* d_sums, int32_t* d_counts, int32_t* d_miss_list = nullptr,
                             int32_t* d_miss_n = nullptr);
 
+// The same contraction on the 5th-generation tensor cores (stats_tc5.cu: tcgen05.mma kind::i8, one-hot A operand
+// written to tensor memory); its own digit layout, same buffer size.  cs_use_tc5(): which of the two the engine uses
+// (GWSEM_CS_KERNEL=imma|tc5, development aid).
+bool cs_use_tc5();
+void tc5_pack_features(const std::vector<std::vector<int64_t>>& q, int n_pad, const std::vector<uint8_t>& inc8,
+                       const std::vector<uint8_t>& kept, std::vector<int8_t>& out);
+void launch_class_sums_tc5(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
+                           const PeopleLayout& pl, const int8_t* d_featq, const double* d_inv_scale, int n_feat,
+                           double* d_sums, int32_t* d_counts, int32_t* d_miss_list = nullptr,
+                           int32_t* d_miss_n = nullptr);
+
 // counts[snp][8] = {n_class1, n_class2, n_missing over included people; the same three over the
 // people kept by rowFilter (for MAF); 0; 0} and, for the missing class, sums of `n_featm`
 // person-major features (d_featT[person][n_featm_pad]): d_miss[snp][n_featm].

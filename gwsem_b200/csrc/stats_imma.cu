@@ -81,26 +81,22 @@ __global__ void __launch_bounds__(WARPS * 32)
   constexpr int kBCopies = kBStage / 16 / kThreads;
   static_assert(kThreads % kPieces == 0 && kSnps % kRowsPerPass == 0 && kBStage % (16 * kThreads) == 0, "staging layout");
   const int gc = tid % kPieces, gr = tid / kPieces;
-  const int64_t pass_stride = (int64_t)kRowsPerPass * pitch;
-  const uint8_t* gsrc = rows + (int64_t)(snp0 + gr) * pitch + gc * 16;
   const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem);
   const unsigned gdst = smem0 + gr * kGRow + gc * 16;
   const unsigned bdst = smem0 + kGStage + tid * 16;
   const int8_t* bsrc = Bq + tid * 16;
-  unsigned row_ok = 0;
+  // No predicates: rows past the batch are clamped to its last row (their results are not stored) and pieces
+  // past the pitch to the last piece of the row (the feature digits of those people are zero padding).
+  const uint8_t* gp[kPasses];
 #pragma unroll
-  for (int k = 0; k < kPasses; ++k) row_ok |= (snp0 + gr + k * kRowsPerPass < n_snps ? 1u : 0u) << k;
+  for (int k = 0; k < kPasses; ++k) gp[k] = rows + (int64_t)min(snp0 + gr + k * kRowsPerPass, n_snps - 1) * pitch;
+  const int last_piece = (int)pitch - 16;
   auto load_stage = [&](int tile, int s) {
-    const bool col_ok = (int64_t)tile * (TILE / 4) + gc * 16 + 16 <= pitch;
-    const uint8_t* p = gsrc + (int64_t)tile * (TILE / 4);
+    const int off = min(tile * (TILE / 4) + gc * 16, last_piece);
     const unsigned d = gdst + s * kStage;
 #pragma unroll
-    for (int k = 0; k < kPasses; ++k) {
-      const bool ok = col_ok && ((row_ok >> k) & 1u);
-      const int bytes = ok ? 16 : 0;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d + k * kRowsPerPass * kGRow), "l"(ok ? p : rows), "r"(bytes) : "memory");
-      p += pass_stride;
-    }
+    for (int k = 0; k < kPasses; ++k)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + k * kRowsPerPass * kGRow), "l"(gp[k] + off) : "memory");
     const int8_t* q = bsrc + (int64_t)tile * kBStage;
     const unsigned db = bdst + s * kStage;
 #pragma unroll
@@ -318,6 +314,7 @@ void launch_class_sums_imma(gwsem_engine* e, const uint8_t* d_packed, int64_t pi
         case 11: launch_imma<2, 4, 8, 256>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn); break;
         case 12: launch_imma<2, 2, 2, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn); break;
         case 13: launch_imma<2, 4, 2, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn); break;
+        case 14: launch_imma<2, 2, 4, 1024>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn); break;
         case 1: launch_imma<2, 2, 8, 1024>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn); break;
         case 2: launch_imma<2, 4, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn); break;
         case 3: launch_imma<2, 2, 8, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn); break;
