@@ -45,9 +45,9 @@ void launch_class_sums_imma(gwsem_engine* e, const uint8_t* d_packed, int64_t pi
                             int32_t* d_miss_n = nullptr);
 
 // The same contraction on the 5th-generation tensor cores (stats_tc5.cu: tcgen05.mma kind::i8, one-hot A operand
-// written to tensor memory); its own digit layout, same buffer size.  cs_use_tc5(): which of the two the engine uses
-// (GWSEM_CS_KERNEL=imma|tc5, development aid).
-bool cs_use_tc5();
+// written to tensor memory); its own digit layout, same buffer size.  cs_use_tc5(n_feat): which of the two the engine
+// uses for a model (tcgen05 for chunks of 64 digit columns, mma.sync for 16; GWSEM_CS_KERNEL=imma|tc5 forces one).
+bool cs_use_tc5(int n_feat);
 void tc5_pack_features(const std::vector<std::vector<int64_t>>& q, int n_pad, const std::vector<uint8_t>& inc8,
                        const std::vector<uint8_t>& kept, std::vector<int8_t>& out);
 void launch_class_sums_tc5(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,

@@ -15,18 +15,20 @@
 //   with the integer ALU work of the expansion (scripts/mma_rate.cu); here the tensor work is asynchronous
 //   and the expansion is the only thing the warps issue.
 //
-// TMEM columns (32-bit): [0, N) D_het, [N, 2N) D_hom, then A[buffer][class] of 16 columns each (2 blocks x 8).
+// TMEM columns (32-bit): [0, N) D_het, [N, 2N) D_hom, then A[buffer][class] of 16 columns each (2 blocks x 8),
+// three buffers.
 #include "common.h"
 #include "kernels.h"
 
 #include <cstdlib>
 #include <string>
+#include <type_traits>
 
 namespace gwsem {
 
 namespace {
 
-constexpr int kTcThreads = 128;   // = SNPs per CTA = TMEM lanes
+constexpr int kTcThreads = 128;   // expanding threads = SNPs per CTA = TMEM lanes; a fifth warp issues the MMAs
 constexpr int kTcGPad = 16;
 
 __device__ __forceinline__ unsigned prmt_raw(unsigned a, unsigned b, unsigned sel) {
@@ -44,11 +46,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
-      "}\n" ::"r"(addr), "r"(parity)
+      "}\n" ::"r"(addr), "r"(parity), "r"(20000u)   // suspend-time hint (ns): fewer polls while the phase is pending
       : "memory");
 }
 
@@ -88,11 +90,12 @@ __device__ __forceinline__ void mma_i8_ts(unsigned d_tmem, unsigned a_tmem, uint
 
 // N = digit columns of the chunk (16 or 64), TILE = people per cp.async stage
 template <int N, int TILE, bool PLINK1>
-__global__ void __launch_bounds__(kTcThreads)
+__global__ void __launch_bounds__(kTcThreads + 32)
     class_sums_tc5_kernel(const uint8_t* __restrict__ rows, int64_t pitch, int n_snps, int n_blocks,
                           const int8_t* __restrict__ Bq, const double* __restrict__ inv_scale, int f0, int n_feat,
                           double* __restrict__ sums, unsigned tab1, unsigned tab2, int32_t* __restrict__ counts,
-                          int count_slot, int32_t* __restrict__ miss_list, int32_t* __restrict__ miss_n) {
+                          int count_slot, int32_t* __restrict__ miss_list, int32_t* __restrict__ miss_n,
+                          unsigned m30, unsigned m16, unsigned m14) {
   constexpr int kSnps = kTcThreads;
   constexpr int kGRow = TILE / 4 + kTcGPad;
   constexpr int kBlocks = TILE / 32;
@@ -100,14 +103,17 @@ __global__ void __launch_bounds__(kTcThreads)
   constexpr int kBStage = kBlocks * kBBlock;
   constexpr int kGStage = kSnps * kGRow;
   constexpr int kStage = kGStage + kBStage;
-  constexpr int kCols = 2 * N + 64 <= 128 ? 128 : 256;   // TMEM allocation (power of two)
+  constexpr int kCols = 2 * N + 3 * 32 <= 128 ? 128 : 256;   // TMEM allocation (power of two)
+  constexpr int kBufs = (kCols - 2 * N) / 32;                // A buffers in tensor memory: 3 (N = 16) or 4 (N = 64)
+  static_assert(kBufs == 3 || kBufs == 4, "A ring");
   constexpr unsigned kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((128u >> 4) << 24);
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ __align__(8) uint64_t full_bar[kBufs], empty_bar[kBufs];
   __shared__ unsigned tmem_base_sh;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int snp0 = blockIdx.x * kSnps;
   const int n_tiles = (n_blocks + kBlocks - 1) / kBlocks;
+  constexpr int kPairs = kBlocks / 2;                    // A stages (pairs of blocks) per tile
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -117,138 +123,167 @@ __global__ void __launch_bounds__(kTcThreads)
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
+    for (int b = 0; b < kBufs; ++b) {
+      mbar_init(&full_bar[b], kTcThreads);   // every expanding thread arrives once its lane of the A buffer is stored
+      mbar_init(&empty_bar[b], 1);           // tcgen05.commit: the MMAs that read the buffer are done
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const unsigned tmem_base = tmem_base_sh;
-  const unsigned lane_base = tmem_base + ((unsigned)(warp * 32) << 16);   // this warp's 32 lanes
-  const unsigned d_col[2] = {0u, (unsigned)N};
-  auto a_col = [&](int buf, int cls) { return (unsigned)(2 * N + (buf * 2 + cls) * 16); };
-
-  // ---- staging (cp.async, one pointer bump per copy; see stats_imma.cu)
-  constexpr int kPieces = TILE / 64;
-  constexpr int kRowsPerPass = kTcThreads / kPieces;
-  constexpr int kPasses = kSnps / kRowsPerPass;
-  constexpr int kBCopies = kBStage / 16 / kTcThreads;
-  static_assert(kBStage % (16 * kTcThreads) == 0, "staging layout");
-  const int gc = tid % kPieces, gr = tid / kPieces;
   const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem);
-  const unsigned gdst = smem0 + gr * kGRow + gc * 16;
-  const unsigned bdst = smem0 + kGStage + tid * 16;
-  const int8_t* bsrc = Bq + tid * 16;
-  const int last_piece = (int)pitch - 16;
-  auto load_stage = [&](int tile, int s) {
-    const int off = min(tile * (TILE / 4) + gc * 16, last_piece);
-    const unsigned d = gdst + s * kStage;
-#pragma unroll
-    for (int k = 0; k < kPasses; ++k) {
-      const uint8_t* p = rows + (int64_t)min(snp0 + gr + k * kRowsPerPass, n_snps - 1) * pitch + off;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + k * kRowsPerPass * kGRow), "l"(p) : "memory");
-    }
-    const int8_t* q = bsrc + (int64_t)tile * kBStage;
-    const unsigned db = bdst + s * kStage;
-#pragma unroll
-    for (int k = 0; k < kBCopies; ++k)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(db + k * kTcThreads * 16), "l"(q + k * kTcThreads * 16) : "memory");
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
+  constexpr unsigned kDHet = 0u, kDHom = (unsigned)N, kA0 = 2u * N;   // A[buf][cls] at kA0 + (2 buf + cls) * 16
 
-  unsigned mdet = 0u;      // missing-call detector (see stats_imma.cu)
-  int a_stage = 0;         // pairs of blocks expanded so far; buffer = a_stage & 1
-  load_stage(0, 0);
-  for (int tile = 0; tile < n_tiles; ++tile) {
-    const int s = tile & 1;
-    if (tile + 1 < n_tiles) {
-      load_stage(tile + 1, s ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    // the MMAs read the feature digits through the async proxy
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    const uint8_t* Gt = smem + s * kStage + tid * kGRow;
-    const unsigned b_tile = smem0 + s * kStage + kGStage;
-#pragma unroll 1
-    for (int kp = 0; kp < kBlocks / 2; ++kp, ++a_stage) {
-      const int buf = a_stage & 1;
-      const uint4 w4 = *reinterpret_cast<const uint4*>(Gt + kp * 16);
-      const unsigned w[4] = {w4.x, w4.y, w4.z, w4.w};
-      unsigned ah[16], ao[16];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const unsigned x = w[q], x2 = x >> 2, xh = x >> 16, xh2 = x >> 18;
-        mdet |= PLINK1 ? (~x & (x * 2u)) : (x & (x * 2u));
-        ah[4 * q + 0] = prmt_raw(tab1, tab1, x);
-        ah[4 * q + 1] = prmt_raw(tab1, tab1, x2);
-        ah[4 * q + 2] = prmt_raw(tab1, tab1, xh);
-        ah[4 * q + 3] = prmt_raw(tab1, tab1, xh2);
-        ao[4 * q + 0] = prmt_raw(tab2, tab2, x);
-        ao[4 * q + 1] = prmt_raw(tab2, tab2, x2);
-        ao[4 * q + 2] = prmt_raw(tab2, tab2, xh);
-        ao[4 * q + 3] = prmt_raw(tab2, tab2, xh2);
-      }
-      if (a_stage >= 2) {   // the MMAs that read this buffer two pairs ago must be done
-        mbar_wait(&mbar[buf], (unsigned)(((a_stage >> 1) - 1) & 1));
+  if (warp == 4) {
+    // ---- MMA warp (one lane): per A stage two blocks x two classes, then a commit that frees the buffer
+    if (lane == 0) {
+      const int total = n_tiles * kPairs;
+      int buf = 0;
+      unsigned phase = 0;
+      for (int a = 0, tile = 0, kp = 0; a < total; ++a) {
+        mbar_wait(&full_bar[buf], phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      }
-      tmem_st16(lane_base + a_col(buf, 0), ah);
-      tmem_st16(lane_base + a_col(buf, 1), ao);
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const unsigned b_tile = smem0 + (tile & 1) * kStage + kGStage;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const uint64_t bd = smem_desc(b_tile + (2 * kp + h) * kBBlock, N * 16, 128);
-          const unsigned acc = (a_stage > 0 || h > 0) ? 1u : 0u;
-          mma_i8_ts(tmem_base + d_col[0], tmem_base + a_col(buf, 0) + h * 8, bd, kIdesc, acc);
-          mma_i8_ts(tmem_base + d_col[1], tmem_base + a_col(buf, 1) + h * 8, bd, kIdesc, acc);
+          const unsigned acc = (a > 0 || h > 0) ? 1u : 0u;
+          mma_i8_ts(tmem_base + kDHet, tmem_base + kA0 + (2 * buf + 0) * 16 + h * 8, bd, kIdesc, acc);
+          mma_i8_ts(tmem_base + kDHom, tmem_base + kA0 + (2 * buf + 1) * 16 + h * 8, bd, kIdesc, acc);
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                         (unsigned)__cvta_generic_to_shared(&mbar[buf]))
+                         (unsigned)__cvta_generic_to_shared(&empty_bar[buf]))
                      : "memory");
+        if (++buf == kBufs) { buf = 0; phase ^= 1u; }
+        if (++kp == kPairs) { kp = 0; ++tile; }
       }
     }
-    // the next iteration's cp.async overwrites the other stage: its MMAs (previous tile) are older than the
-    // two pairs waited for below, so draining the last two commits covers them
-    {
-      const int last = a_stage - 1;
-      mbar_wait(&mbar[last & 1], (unsigned)((last >> 1) & 1));
-      if (last >= 1) mbar_wait(&mbar[(last - 1) & 1], (unsigned)(((last - 1) >> 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
-    __syncthreads();
-  }
+    __syncwarp();
+  } else {
+    // ---- expanding warps: thread = SNP = TMEM lane
+    const unsigned lane_base = tmem_base + ((unsigned)(warp * 32) << 16);
+    // staging (cp.async, one pointer bump per copy; see stats_imma.cu)
+    constexpr int kPieces = TILE / 64;
+    constexpr int kRowsPerPass = kTcThreads / kPieces;
+    constexpr int kPasses = kSnps / kRowsPerPass;
+    constexpr int kBCopies = kBStage / 16 / kTcThreads;
+    static_assert(kBStage % (16 * kTcThreads) == 0, "staging layout");
+    const int gc = tid % kPieces, gr = tid / kPieces;
+    const unsigned gdst = smem0 + gr * kGRow + gc * 16;
+    const unsigned bdst = smem0 + kGStage + tid * 16;
+    const int8_t* bsrc = Bq + tid * 16;
+    const int last_piece = (int)pitch - 16;
+    const uint8_t* gp[kPasses];   // rows past the batch are clamped to its last row (not stored), pieces past the pitch to the last piece
+#pragma unroll
+    for (int k = 0; k < kPasses; ++k) gp[k] = rows + (int64_t)min(snp0 + gr + k * kRowsPerPass, n_snps - 1) * pitch;
+    auto load_stage = [&](int tile, int s) {
+      const int off = min(tile * (TILE / 4) + gc * 16, last_piece);
+      const unsigned d = gdst + s * kStage;
+#pragma unroll
+      for (int k = 0; k < kPasses; ++k)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + k * kRowsPerPass * kGRow), "l"(gp[k] + off) : "memory");
+      const int8_t* q = bsrc + (int64_t)tile * kBStage;
+      const unsigned db = bdst + s * kStage;
+#pragma unroll
+      for (int k = 0; k < kBCopies; ++k)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(db + k * kTcThreads * 16), "l"(q + k * kTcThreads * 16) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto expanders_sync = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
 
-  // ---- epilogue: this thread's SNP, both classes, N digit columns each (the one-hot entries are -1)
-  const int snp = snp0 + tid;
-  if (miss_list && (mdet & 0xAAAAAAAAu) != 0u && snp < n_snps) miss_list[atomicAdd(miss_n, 1)] = snp;
+    unsigned mdet = 0u;      // missing-call detector (see stats_imma.cu)
+    constexpr int kIssue = kBufs < kPairs ? kBufs : kPairs - 1;   // stage of a tile at which the next tile's copies start
+    static_assert(kIssue >= kBufs, "tiles shorter than the A ring are not handled");
+    const int total = n_tiles * kPairs;   // A stages; stage a uses buffer a % kBufs, phase = parity of a / kBufs
+    int a = 0, kp = 0, tile = 0;
+    unsigned phase = 0;
+    const uint8_t* Gt = nullptr;
+    load_stage(0, 0);
+    // One A stage with a compile-time buffer: the TMEM addresses and barrier addresses are constants of the unrolled body.
+    auto do_stage = [&](auto bufc) {
+      constexpr int BUF = decltype(bufc)::value;
+      if (kp == 0) {   // tile start
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the MMAs read the feature digits through the async proxy
+        expanders_sync();   // tile landed for everyone; everyone is done with the previous tile's packed rows
+        Gt = smem + (tile & 1) * kStage + tid * kGRow;
+      }
+      const uint4 w4 = *reinterpret_cast<const uint4*>(Gt + kp * 16);
+      unsigned ah[16], ao[16];
+      // right shifts as multiply-high by a power of two the compiler cannot see (kernel arguments): they go to the
+      // FMA pipe, the PRMTs keep the ALU pipe to themselves
+#define GW_EXPAND(Q, X)                                                                       \
+  {                                                                                           \
+    const unsigned x = (X), x2 = __umulhi(x, m30), xh = __umulhi(x, m16), xh2 = __umulhi(x, m14); \
+    mdet |= PLINK1 ? (~x & (x * 2u)) : (x & (x * 2u));                                        \
+    ah[4 * Q + 0] = prmt_raw(tab1, tab1, x);                                                  \
+    ah[4 * Q + 1] = prmt_raw(tab1, tab1, x2);                                                 \
+    ah[4 * Q + 2] = prmt_raw(tab1, tab1, xh);                                                 \
+    ah[4 * Q + 3] = prmt_raw(tab1, tab1, xh2);                                                \
+    ao[4 * Q + 0] = prmt_raw(tab2, tab2, x);                                                  \
+    ao[4 * Q + 1] = prmt_raw(tab2, tab2, x2);                                                 \
+    ao[4 * Q + 2] = prmt_raw(tab2, tab2, xh);                                                 \
+    ao[4 * Q + 3] = prmt_raw(tab2, tab2, xh2);                                                \
+  }
+      GW_EXPAND(0, w4.x) GW_EXPAND(1, w4.y) GW_EXPAND(2, w4.z) GW_EXPAND(3, w4.w)
+#undef GW_EXPAND
+      if (a >= kBufs) {   // the MMAs that read this buffer kBufs stages ago must be done
+        mbar_wait(&empty_bar[BUF], phase ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      // That commit also covers every MMA of the previous tile once kp >= kBufs, and all expanding threads left
+      // that tile's packed rows at the barrier above: the other shared-memory stage is free.
+      if (kp == kIssue && tile + 1 < n_tiles) load_stage(tile + 1, (tile + 1) & 1);
+      tmem_st16(lane_base + kA0 + (2 * BUF + 0) * 16, ah);
+      tmem_st16(lane_base + kA0 + (2 * BUF + 1) * 16, ao);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&full_bar[BUF])) : "memory");
+      ++a;
+      if (++kp == kPairs) { kp = 0; ++tile; }
+    };
+#pragma unroll 1
+    while (a < total) {
+      do_stage(std::integral_constant<int, 0>{});
+      if (a < total) do_stage(std::integral_constant<int, 1>{});
+      if (a < total) do_stage(std::integral_constant<int, 2>{});
+      if constexpr (kBufs > 3) {
+        if (a < total) do_stage(std::integral_constant<int, 3>{});
+      }
+      phase ^= 1u;
+    }
+    // all MMAs done: the last kBufs commits
 #pragma unroll
-  for (int cls = 0; cls < 2; ++cls) {
+    for (int d = 1; d <= kBufs; ++d)
+      if (a >= d) mbar_wait(&empty_bar[(a - d) % kBufs], (unsigned)(((a - d) / kBufs) & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- epilogue: this thread's SNP, both classes, N digit columns each (the one-hot entries are -1)
+    const int snp = snp0 + tid;
+    if (miss_list && (mdet & 0xAAAAAAAAu) != 0u && snp < n_snps) miss_list[atomicAdd(miss_n, 1)] = snp;
 #pragma unroll
-    for (int c0 = 0; c0 < N; c0 += 16) {
-      int v[16];
-      tmem_ld16(lane_base + d_col[cls] + c0, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (snp < n_snps) {
+    for (int cls = 0; cls < 2; ++cls) {
 #pragma unroll
-        for (int fi = 0; fi < 4; ++fi) {
-          const int slot = c0 / 4 + fi, f = f0 + slot;
-          if (counts && slot == count_slot) {
-            int32_t* c = counts + 8 * (int64_t)snp;
-            c[0 + cls] = -v[4 * fi + 0];   // included people
-            c[3 + cls] = -v[4 * fi + 1];   // people kept by rowFilter
-          }
-          if (f < n_feat) {
-            const double lo = (double)(-v[4 * fi + 0]) + 256.0 * (double)(-v[4 * fi + 1]);
-            const double hi = (double)(-v[4 * fi + 2]) + 256.0 * (double)(-v[4 * fi + 3]);
-            sums[((int64_t)snp * 2 + cls) * n_feat + f] = (lo + 65536.0 * hi) * inv_scale[f];
+      for (int c0 = 0; c0 < N; c0 += 16) {
+        int v[16];
+        tmem_ld16(lane_base + (cls ? kDHom : kDHet) + c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (snp < n_snps) {
+#pragma unroll
+          for (int fi = 0; fi < 4; ++fi) {
+            const int slot = c0 / 4 + fi, f = f0 + slot;
+            if (counts && slot == count_slot) {
+              int32_t* c = counts + 8 * (int64_t)snp;
+              c[0 + cls] = -v[4 * fi + 0];   // included people
+              c[3 + cls] = -v[4 * fi + 1];   // people kept by rowFilter
+            }
+            if (f < n_feat) {
+              const double lo = (double)(-v[4 * fi + 0]) + 256.0 * (double)(-v[4 * fi + 1]);
+              const double hi = (double)(-v[4 * fi + 2]) + 256.0 * (double)(-v[4 * fi + 3]);
+              sums[((int64_t)snp * 2 + cls) * n_feat + f] = (lo + 65536.0 * hi) * inv_scale[f];
+            }
           }
         }
       }
@@ -270,13 +305,13 @@ void launch_tc5(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_s
   if (plink1) {
     auto k = class_sums_tc5_kernel<N, TILE, true>;
     GW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, kTcThreads, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums,
-                                             0x00FF0000u, 0x000000FFu, d_counts, count_slot, d_miss_list, d_miss_n);
+    k<<<grid, kTcThreads + 32, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums,
+                                             0x00FF0000u, 0x000000FFu, d_counts, count_slot, d_miss_list, d_miss_n, 1u << 30, 1u << 16, 1u << 14);
   } else {
     auto k = class_sums_tc5_kernel<N, TILE, false>;
     GW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, kTcThreads, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums,
-                                             0x0000FF00u, 0x00FF0000u, d_counts, count_slot, d_miss_list, d_miss_n);
+    k<<<grid, kTcThreads + 32, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums,
+                                             0x0000FF00u, 0x00FF0000u, d_counts, count_slot, d_miss_list, d_miss_n, 1u << 30, 1u << 16, 1u << 14);
   }
   GW_CUDA(cudaGetLastError());
   e->launches++;
@@ -284,12 +319,18 @@ void launch_tc5(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_s
 
 }  // namespace
 
-bool cs_use_tc5() {
-  static const bool on = [] {
+// Which contraction kernel serves a model with n_feat class-summed features.  The tcgen05 kernel is bound by the
+// tensor-memory store port (the one-hot A operand is 16x the packed bytes; measured 128 B/clk/SM), the mma.sync
+// kernel by IMMA issue + ALU: equal at 16 digit columns (0.70 ms per 65,536 SNPs x 100k people), and the tcgen05
+// kernel wins 1.6x at 64 columns, where mma.sync needs four times the IMMAs for the same expansion.
+// GWSEM_CS_KERNEL=imma|tc5 forces one of them (development aid).
+bool cs_use_tc5(int n_feat) {
+  static const int forced = [] {
     const char* v = getenv("GWSEM_CS_KERNEL");
-    return !(v && std::string(v) == "imma");
+    return !v ? 0 : std::string(v) == "imma" ? 1 : std::string(v) == "tc5" ? 2 : 0;
   }();
-  return on;
+  if (forced) return forced == 2;
+  return imma_chunk_features(n_feat) > 4;
 }
 
 // Host side of the tcgen05 digit layout.  Chunks as in imma_pack_features (the buffer has the same size).  Within a
@@ -350,7 +391,7 @@ void launch_class_sums_tc5(gwsem_engine* e, const uint8_t* d_packed, int64_t pit
     int32_t* d_mn = d_cnt ? d_miss_n : nullptr;
     const int count_slot = n_feat % cf;
     if (cf == 4) launch_tc5<16, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn);
-    else launch_tc5<64, 256>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn);
+    else launch_tc5<64, 512>(e, d_packed, pitch, n_snps, plink1, n_live, Bq, d_inv_scale, f0, n_feat, d_sums, d_cnt, count_slot, d_ml, d_mn);
   }
   e->prof_end(kFamClassSums);
 }
