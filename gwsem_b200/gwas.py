@@ -186,6 +186,45 @@ class GWASResult:
         self.loadCounter = load_counter   # m$compute$steps[[2]]$debug$loadCounter
 
 
+class ComputePlan:
+    """The per-SNP loop prepareComputePlan attaches to a model (R/model.R:122-195), as data: the engine runs
+    exactly these steps for every SNP -- reset starts, load the SNP column, load its context, fit, standard
+    errors, one checkpoint row -- in batches on the device (gwsem_gwas_run)."""
+
+    def __init__(self, model, snpData, out, SNP, startFrom, rowFilter):
+        self.snpData, self.out, self.SNP, self.startFrom, self.rowFilter = snpData, out, SNP, startFrom, rowFilter
+        ml = flatten(model)["fitfun"] != "WLS" if isinstance(snpData, str) else None
+        self.steps = ["ST: mxComputeSetOriginalStarts", f"LD: mxComputeLoadData({snpData!r}, column='snp')",
+                      "LC: mxComputeLoadContext(CHR, BP, SNP, A1, A2)",
+                      "TC: mxComputeTryCatch(GD: mxComputeGradientDescent" +
+                      (", ND: mxComputeNumericDeriv, SE: mxComputeStandardError, HQ: mxComputeHessianQuality)" if ml
+                       else ", SE: mxComputeStandardError)"),
+                      f"CK: mxComputeCheckpoint({out!r}, standardErrors=FALSE, vcov=TRUE)"]
+
+    def __repr__(self):
+        return "mxComputeLoop[\n  " + "\n  ".join(self.steps) + "\n]"
+
+
+def prepareComputePlan(model, snpData, out="out.log", *dots, SNP=None, startFrom=1, rowFilter=None):
+    """R/model.R:122-195: returns the model with its compute plan (model.compute); GWAS() builds the same plan
+    and runs it.  mxRun(model) of the reference = run_plan(model) here."""
+    if dots:
+        raise ValueError("Rejected are any values passed in the '...' argument")
+    if isinstance(snpData, str):
+        processSnpData(snpData)   # rejects unknown formats as the reference does
+    model.compute = ComputePlan(model, snpData, out, SNP, startFrom, rowFilter)
+    return model
+
+
+def run_plan(model, device=0, batch_snps=0):
+    """mxRun() of a model prepared by prepareComputePlan."""
+    plan = getattr(model, "compute", None)
+    if plan is None:
+        raise ValueError("model has no compute plan: call prepareComputePlan first")
+    return GWAS(model, plan.snpData, plan.out, SNP=plan.SNP, startFrom=plan.startFrom, rowFilter=plan.rowFilter,
+                device=device, batch_snps=batch_snps)
+
+
 def GWAS(model, snpData, out="out.log", *dots, SNP=None, startFrom=1, rowFilter=None, device=0, batch_snps=0):
     """R/model.R:305-315."""
     if dots:

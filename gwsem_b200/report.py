@@ -55,6 +55,12 @@ def loadResults(path, focus, *dots, extraColumns=()):
     return pd.concat(got, ignore_index=True)
 
 
+def loadSuspicious(path, focus, *dots, extraColumns=(), signAdj=None, moderatorLevel=None):
+    """R/report.R:139-143: removed in the reference since 2.0.6 (deprecate_stop); same behaviour here."""
+    raise RuntimeError("`loadSuspicious()` was deprecated in gwsem 2.0.6 and is now defunct. "
+                       "Use r1 = loadResults(path, focus); r1[isSuspicious(r1, focus)] instead.")
+
+
 def signif(result, focus, signAdj=None):
     """R/report.R:174-190: Z = est / sqrt(V), two-sided normal P."""
     if not isinstance(focus, str):

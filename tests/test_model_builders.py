@@ -83,3 +83,23 @@ def test_flatten_roundtrip(pheno):
     assert len(f["par_names"]) == 16 and f["cells"].shape[1] == 5
     free = f["cells"][f["cells"][:, 3] >= 0]
     assert set(free[:, 3].astype(int)) == set(range(16))
+
+
+def test_prepare_compute_plan_and_namespace(pheno):
+    """Every export of the reference NAMESPACE exists; prepareComputePlan attaches the per-SNP loop (R/model.R:122-195)."""
+    import gwsem_b200 as g
+    for name in ["GWAS", "buildAnalysesPlan", "buildItem", "buildOneFac", "buildOneFacRes", "buildOneItem", "buildTwoFac",
+                 "isSuspicious", "loadResults", "loadSuspicious", "numAvailableRecords", "prepareComputePlan",
+                 "setupExogenousCovariates", "setupThresholds", "signif", "signifGxE"]:
+        assert callable(getattr(g, name)), name
+    m = g.buildItem(pheno, "i1")
+    with pytest.raises(ValueError, match="Rejected"):
+        g.prepareComputePlan(m, "x.pgen", "out.log", "stray")
+    m = g.prepareComputePlan(m, "x.pgen", "o.log", SNP=[1, 2], startFrom=1)
+    text = repr(m.compute)
+    assert "mxComputeLoadData('x.pgen'" in text and "mxComputeCheckpoint('o.log'" in text and "StandardError" in text
+    assert "NumericDeriv" not in text
+    ml = g.prepareComputePlan(g.buildItem(pheno, "i1", fitfun="ML"), "x.bgen")
+    assert "NumericDeriv" in repr(ml.compute) and "HessianQuality" in repr(ml.compute)
+    with pytest.raises(RuntimeError, match="defunct"):
+        g.loadSuspicious("o.log", "snp_to_i1")
