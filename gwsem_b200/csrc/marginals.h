@@ -43,6 +43,7 @@ struct MargProgram {
   int n_cat[kMargMaxItems] = {0};
   int col_of[kMargMaxItems + 1] = {0};
   double item_sd[kMargMaxItems] = {0};       // continuous items: residual sd
+  double zmax[kMargMaxItems] = {0};          // ordinal items: largest |standardised threshold| any person carries (sentinels excluded)
   const double* sc0 = nullptr;               // [n_pad][q0p] file order, zero rows for excluded people
   const double* zz = nullptr;                // [n_pad][J][5]: z1, z0, phi(z1), phi(z0), Phi(z1)-Phi(z0) (continuous: v)
   const double* cc = nullptr;                // [n_pad][J][3]: tetrachoric-series coefficients c1..c3 (continuous: v)

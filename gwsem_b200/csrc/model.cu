@@ -337,7 +337,8 @@ void gwsem_model::prepare(const int32_t* row_filter, int src_rows) {
     std::vector<int8_t> packed_q;
     std::vector<uint8_t> kept8(n_pad, 0);
     for (int s2 = 0; s2 < src_rows; ++s2) kept8[s2] = dest_of[s2] >= 0;
-    if (cs_use_tc5(nfd)) tc5_pack_features(fq, n_pad, inc8, kept8, packed_q);
+    use_tc5 = cs_use_tc5(nfd);
+    if (use_tc5) tc5_pack_features(fq, n_pad, inc8, kept8, packed_q);
     else imma_pack_features(fq, n_pad, inc8, kept8, packed_q);
     d_featq = upload_vec(pool, packed_q, st);
     d_inv_scale = upload_vec(pool, inv_scale, st);
@@ -422,7 +423,7 @@ void gwsem_model::fit_2bit_device(const uint8_t* d_packed, int64_t pitch, int n_
       GW_CUDA(cudaMemsetAsync(d_miss_list.p + n, 0, sizeof(int32_t), st));
       GW_CUDA(cudaMemsetAsync(d_counts.p, 0, 8 * (size_t)n * sizeof(int32_t), st));
       GW_CUDA(cudaMemsetAsync(d_miss.p, 0, (size_t)std::max(nfm, 1) * n * sizeof(double), st));
-      if (cs_use_tc5(nfd))
+      if (use_tc5)
         launch_class_sums_tc5(engine, rows, pitch, n, plink1, layout, d_featq, d_inv_scale, nfd, d_sums.p, d_counts.p,
                               d_miss_list.p, d_miss_list.p + n);
       else
@@ -433,7 +434,7 @@ void gwsem_model::fit_2bit_device(const uint8_t* d_packed, int64_t pitch, int n_
     } else {
       launch_count_missing(engine, rows, pitch, n, plink1, layout, d_featT, nfm, nfm_pad, d_counts.p, d_miss.p, false);
       if (dfma) launch_class_sums(engine, rows, pitch, n, plink1, layout, d_feat, nfd, d_sums.p);
-      else if (cs_use_tc5(nfd)) launch_class_sums_tc5(engine, rows, pitch, n, plink1, layout, d_featq, d_inv_scale, nfd, d_sums.p, d_counts.p);
+      else if (use_tc5) launch_class_sums_tc5(engine, rows, pitch, n, plink1, layout, d_featq, d_inv_scale, nfd, d_sums.p, d_counts.p);
       else launch_class_sums_imma(engine, rows, pitch, n, plink1, layout, d_featq, d_inv_scale, nfd, d_sums.p, d_counts.p);
     }
     gwsem_result r = d_res;

@@ -36,6 +36,7 @@ struct gwsem_model {
   const int32_t* d_dest_of = nullptr;
   std::vector<gwsem::DeviceBuffer<uint8_t>> pool;
   gwsem::DeviceBuffer<int32_t> d_counts, d_miss_list;
+  bool use_tc5 = false;   // which class-sum kernel the packed digits were laid out for (cs_use_tc5 at prepare time)
   gwsem::DeviceBuffer<double> d_sums, d_miss, d_R, d_mafs;
   gwsem::DeviceBuffer<int32_t> d_nrows;
   gwsem::DeviceBuffer<uint8_t> d_stage2[2];

@@ -202,7 +202,9 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
         e[4] = 0.5 * (std::erfc(-e[0] * 0.7071067811865476) - std::erfc(-e[1] * 0.7071067811865476));
         if (e[1] > 0) e[4] = 0.5 * (std::erfc(e[1] * 0.7071067811865476) - std::erfc(e[0] * 0.7071067811865476));
         if (e[0] >= 12.0) e[2] = 0.0;   // open categories: the sentinel bound carries no density
+        else mp.zmax[j] = std::max(mp.zmax[j], std::fabs(e[0]));
         if (e[1] <= -12.0) e[3] = 0.0;
+        else mp.zmax[j] = std::max(mp.zmax[j], std::fabs(e[1]));
         double* c = &cc[((size_t)s * J + j) * 3];
         c[0] = (e[3] - e[2]) / e[4];
         c[1] = (e[1] * e[3] - e[0] * e[2]) / e[4];

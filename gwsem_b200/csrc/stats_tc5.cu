@@ -325,11 +325,9 @@ void launch_tc5(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_s
 // kernel wins 1.6x at 64 columns, where mma.sync needs four times the IMMAs for the same expansion.
 // GWSEM_CS_KERNEL=imma|tc5 forces one of them (development aid).
 bool cs_use_tc5(int n_feat) {
-  static const int forced = [] {
-    const char* v = getenv("GWSEM_CS_KERNEL");
-    return !v ? 0 : std::string(v) == "imma" ? 1 : std::string(v) == "tc5" ? 2 : 0;
-  }();
-  if (forced) return forced == 2;
+  const char* v = getenv("GWSEM_CS_KERNEL");   // read when a model is prepared (the digit layout follows the kernel)
+  if (v && std::string(v) == "imma") return false;
+  if (v && std::string(v) == "tc5") return true;
   return imma_chunk_features(n_feat) > 4;
 }
 

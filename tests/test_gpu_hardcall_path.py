@@ -156,3 +156,32 @@ def test_fit_with_row_filter_and_missing_phenotypes(engine):
     want = oracle_rows(flat, model.data, codes[:, ~rf])
     compare(res, want, flat["par_names"])
     gm.close()
+
+
+@pytest.mark.parametrize("builder,n", [("item", 4097), ("onefacres", 3001), ("item", 100_000)])
+def test_tcgen05_and_mma_sync_class_sums_are_bit_identical(engine, builder, n, monkeypatch):
+    """The class sums are an exact integer contraction: the tcgen05 kernel (stats_tc5.cu) and the mma.sync kernel
+    (stats_imma.cu) must give the same bits whatever the tile shape or summation order, at the bench's cohort size
+    too, with missing calls and in PLINK 1 coding."""
+    from gwsem_b200.engine import Model
+    ph = make_pheno(n, seed=n, n_items=5)
+    items = [f"i{k}" for k in range(1, 6)]
+    model = buildItem(ph, "i1") if builder == "item" else buildOneFacRes(ph[items], items)
+    flat = flatten(model)
+    codes = synth.simulate_hardcalls(n, 40, seed=n + 1, missing_rate=0.01)
+    codes[5, :] = np.where(codes[5, :] == 3, 0, codes[5, :])   # one SNP without a missing call
+    data = {c: model.data[c].to_numpy(float) for c in model.data.columns if c != "snp"}
+    packed = synth.pack_2bit(codes)
+    bed = synth.pack_2bit(np.array([3, 2, 0, 1], np.uint8)[codes])
+    out = {}
+    for kernel in ("imma", "tc5"):
+        monkeypatch.setenv("GWSEM_CS_KERNEL", kernel)
+        gm = Model(engine, flat, data)
+        out[kernel] = (gm.fit_2bit(packed), gm.fit_2bit(bed, plink1=True))
+        gm.close()
+    for a, b in zip(out["imma"], out["tc5"]):
+        for f in ("est", "vcov", "fit", "maf"):
+            assert np.array_equal(getattr(a, f).view(np.uint64), getattr(b, f).view(np.uint64)), f
+        for f in ("n_used", "status", "catch_code"):
+            assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    assert np.array_equal(out["imma"][0].est.view(np.uint64), out["imma"][1].est.view(np.uint64))
