@@ -54,7 +54,8 @@ def use_workload(name):
                     "x 32,768 SNPs of packed hardcalls per step per GPU (the 1M-SNP file streams through in such batches)")
         KERNEL = "marg_stats_kernel<3,false,1>"
         NOTE = ("achieved = 12,500 B/SNP of packed genotypes x SNPs per launch / CUDA-event launch time; the kernel is "
-                "FP64-issue bound (polyserial scores per person), so the HBM fraction is low by construction")
+                "bound by the latency of dependent FP64 chains (polyserial scores per person; ncu: FP64 pipe 32 %, "
+                "0.34 issue/cycle/SMSP at 16 warps/SM), so the HBM fraction is low by construction")
 
 
 def build_model(ph):
