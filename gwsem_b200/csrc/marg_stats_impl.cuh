@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(kT, 2)
   __shared__ double rho_sh[J];
   __shared__ double pc_sh[J][4];
   __shared__ int low_sh[J];
+  __shared__ double sums_sh[J][3];
   __shared__ int done_sh;
   const int snp = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* out = summary + (int64_t)snp * mp.sum_stride;
@@ -311,7 +312,29 @@ __global__ void __launch_bounds__(kT, 2)
       low_sh[tid] = mp.n_cat[tid] > 0 && dmax <= kLowD && mp.zmax[tid] * dmax + 0.5 * dmax * dmax <= kLowX;
     }
     __syncthreads();
-    if (iter == 0) {
+    // Iteration 0 without a pass over people: for hardcalls u takes three values, so the three sums are combinations
+    // of genotype-class sums of six per-person products (mp.cs_sums, exact fixed point; class 0 = totals - het - hom).
+    const bool from_sums = iter == 0 && !DOSAGE && mp.cs_sums != nullptr && n == mp.n_incl;
+    if (from_sums) {
+      if (tid < J) {
+        const double* S1 = mp.cs_sums + ((int64_t)snp * 2 + 0) * mp.cs_nf + 6 * tid;
+        const double* S2 = mp.cs_sums + ((int64_t)snp * 2 + 1) * mp.cs_nf + 6 * tid;
+        const double* T = mp.cs_tot + 6 * tid;
+        double a = 0.0, b = 0.0, c = 0.0;
+#pragma unroll
+        for (int cls = 0; cls < 3; ++cls) {
+          double S[6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) S[k] = cls == 0 ? T[k] - S1[k] - S2[k] : (cls == 1 ? S1[k] : S2[k]);
+          const double uu = uc[cls], he2 = uu * uu - 1.0, he3 = uu * (uu * uu - 3.0);
+          a += uu * S[0];
+          b += he2 * S[1] - uu * uu * S[2];
+          c += he3 * S[3] + 2.0 * uu * uu * uu * S[4] - 3.0 * uu * he2 * S[5];
+        }
+        sums_sh[tid][0] = a; sums_sh[tid][1] = b; sums_sh[tid][2] = c;
+      }
+      __syncthreads();
+    } else if (iter == 0) {
       for (int i = tid; i < n_src; i += kT) {
         double u;
         if (!std_geno(i, &u)) continue;
@@ -352,7 +375,9 @@ __global__ void __launch_bounds__(kT, 2)
     double worst = 0.0;
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-      const double a = block_sum(s1[j], red, tid), b = block_sum(s2[j], red, tid), c = block_sum(s3[j], red, tid);
+      double a, b, c;
+      if (from_sums) { a = sums_sh[j][0]; b = sums_sh[j][1]; c = sums_sh[j][2]; }
+      else { a = block_sum(s1[j], red, tid); b = block_sum(s2[j], red, tid); c = block_sum(s3[j], red, tid); }
       double step;
       if (iter == 0) {  // root of the quadratic model a + b rho + c rho^2 / 2 nearest to the Newton point
         step = b < 0.0 ? -a / b : 0.0;

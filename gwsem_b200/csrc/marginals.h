@@ -68,6 +68,12 @@ struct MargProgram {
   const int32_t* elim_a_row = nullptr;
   const int32_t* elim_b_par = nullptr;
   const int32_t* elim_b_row = nullptr;
+  // series pass at rho = 0 from genotype-class sums (hardcalls without missing calls, all items ordinal): per item the
+  // six products {c1, c2, c1^2, c3, c1^3, c1 c2} of the tetrachoric coefficients, class-summed exactly by the tcgen05
+  // kernel; cs_sums[snp][2][6 J] (het, hom ALT) is set per launch, cs_tot[6 J] are the sums over all included people
+  int cs_nf = 0;
+  const double* cs_sums = nullptr;
+  const double* cs_tot = nullptr;
   // summary record per SNP (doubles)
   int sum_stride = 0, o_rho = 0, o_a22 = 0, o_a21snp = 0, o_a21item = 0, o_bdd = 0, o_bd0 = 0;
   int o_msum = 0, o_mmat = 0;  // missing-call people: sum of their item-side score rows, and of the outer products

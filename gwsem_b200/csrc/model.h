@@ -60,7 +60,9 @@ struct gwsem_model {
   std::vector<double> thresholds;  // n x 4
   gwsem::MarginalsHost mh;
   gwsem::MargProgram mp;
-  gwsem::DeviceBuffer<double> d_summary;
+  gwsem::DeviceBuffer<double> d_summary, d_cs_sums;
+  const int8_t* d_csq = nullptr;          // marginals: digits of the series products (tcgen05 layout)
+  const double* d_cs_inv_scale = nullptr;
   void prepare_marginals(const std::vector<int>& dest_of);
   void run_marginals(const uint8_t* d_packed, int64_t pitch, const double* d_geno, const double* d_maf_in, int n,
                      int plink1, const gwsem_result& r);

@@ -284,6 +284,56 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
   mp.sc0 = up(pool, sc0, st);
   mp.zz = up(pool, zz, st);
   mp.cc = up(pool, cc, st);
+  // Series pass from class sums: six products of c1..c3 per ordinal item, rounded to a 2^-s grid (|h| 2^s <= 2^30) and
+  // packed as base-256 digits for the tcgen05 class-sum kernel.  Only when every item is ordinal.
+  mp.cs_nf = 0;
+  d_csq = nullptr;
+  {
+    bool all_ord = J > 0;
+    for (int j = 0; j < J; ++j) all_ord = all_ord && mh.items[j].n_cat > 0;
+    if (all_ord && 6 * J <= 64) {
+      const int nF = 6 * J;
+      std::vector<std::vector<double>> h(nF, std::vector<double>(n_pad, 0.0));
+      for (int s2 = 0; s2 < n_src; ++s2) {
+        const int r = dest_of[s2];
+        if (r < 0 || !row_ok[r]) continue;
+        for (int j = 0; j < J; ++j) {
+          const double* c = &cc[((size_t)s2 * J + j) * 3];
+          double* dst[6];
+          for (int k = 0; k < 6; ++k) dst[k] = &h[6 * j + k][s2];
+          *dst[0] = c[0]; *dst[1] = c[1]; *dst[2] = c[0] * c[0]; *dst[3] = c[2]; *dst[4] = c[0] * c[0] * c[0]; *dst[5] = c[0] * c[1];
+        }
+      }
+      std::vector<std::vector<int64_t>> q(nF, std::vector<int64_t>(n_pad, 0));
+      std::vector<double> inv(nF), tot(nF, 0.0);
+      for (int f = 0; f < nF; ++f) {
+        double mx = 0.0;
+        for (double v : h[f]) mx = std::max(mx, std::fabs(v));
+        int ex = 0;
+        if (mx > 0) std::frexp(mx, &ex);
+        const double sc = std::ldexp(1.0, 30 - ex);
+        inv[f] = std::ldexp(1.0, ex - 30);
+        long double acc = 0;
+        for (int s2 = 0; s2 < n_pad; ++s2) {
+          q[f][s2] = std::llrint(h[f][s2] * sc);
+          acc += (long double)q[f][s2];
+        }
+        tot[f] = (double)acc * inv[f];
+      }
+      std::vector<uint8_t> inc(n_pad, 0), kept(n_pad, 0);
+      for (int s2 = 0; s2 < n_src; ++s2) {
+        const int r = dest_of[s2];
+        inc[s2] = r >= 0 && row_ok[r];
+        kept[s2] = r >= 0;
+      }
+      std::vector<int8_t> packed;
+      tc5_pack_features(q, n_pad, inc, kept, packed);
+      d_csq = up(pool, packed, st);
+      d_cs_inv_scale = up(pool, inv, st);
+      mp.cs_tot = up(pool, tot, st);
+      mp.cs_nf = nF;
+    }
+  }
   mp.cat = up(pool, cat, st);
   mp.X = up(pool, X, st);
   mp.B00 = up(pool, mh.B00, st);
@@ -402,7 +452,14 @@ void gwsem_model::run_marginals(const uint8_t* d_packed, int64_t pitch, const do
     launch_maf_from_counts(engine, d_counts.p, layout.n_kept, n, d_mafs.p);
     maf = d_mafs.p;
   }
-  launch_marg_stats(engine, mp, d_packed, pitch, n, n_src, layout.d_inc8, d_geno ? nullptr : d_counts.p, plink1, d_geno,
+  MargProgram mpl = mp;
+  mpl.cs_sums = nullptr;
+  if (!d_geno && mp.cs_nf > 0) {
+    d_cs_sums.ensure((size_t)n * 2 * mp.cs_nf);
+    launch_class_sums_tc5(engine, d_packed, pitch, n, plink1, layout, d_csq, d_cs_inv_scale, mp.cs_nf, d_cs_sums.p, nullptr);
+    mpl.cs_sums = d_cs_sums.p;
+  }
+  launch_marg_stats(engine, mpl, d_packed, pitch, n, n_src, layout.d_inc8, d_geno ? nullptr : d_counts.p, plink1, d_geno,
                     n_pad, d_summary.p);
   launch_marg_fit(engine, fp, mp, n, d_summary.p, maf, r);
 }
