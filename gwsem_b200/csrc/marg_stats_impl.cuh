@@ -321,6 +321,9 @@ __global__ void __launch_bounds__(kT, 2)
         const double* S2 = mp.cs_sums + ((int64_t)snp * 2 + 1) * mp.cs_nf + 6 * tid;
         const double* T = mp.cs_tot + 6 * tid;
         double a = 0.0, b = 0.0, c = 0.0;
+        const int32_t* cn = counts + 8 * (int64_t)snp;
+        const double ncls[3] = {dn - (double)cn[0] - (double)cn[1], (double)cn[0], (double)cn[1]};
+        const bool ord = mp.n_cat[tid] > 0;
 #pragma unroll
         for (int cls = 0; cls < 3; ++cls) {
           double S[6];
@@ -328,9 +331,14 @@ __global__ void __launch_bounds__(kT, 2)
           for (int k = 0; k < 6; ++k) S[k] = cls == 0 ? T[k] - S1[k] - S2[k] : (cls == 1 ? S1[k] : S2[k]);
           const double uu = uc[cls], he2 = uu * uu - 1.0, he3 = uu * (uu * uu - 3.0);
           a += uu * S[0];
-          b += he2 * S[1] - uu * uu * S[2];
-          c += he3 * S[3] + 2.0 * uu * uu * uu * S[4] - 3.0 * uu * he2 * S[5];
+          if (ord) {
+            b += he2 * S[1] - uu * uu * S[2];
+            c += he3 * S[3] + 2.0 * uu * uu * uu * S[4] - 3.0 * uu * he2 * S[5];
+          } else {   // continuous item: S[0] = sum v, S[1] = sum v^2
+            b += -he2 * ncls[cls] - S[1];
+          }
         }
+        if (!ord) c = 6.0 * a;
         sums_sh[tid][0] = a; sums_sh[tid][1] = b; sums_sh[tid][2] = c;
       }
       __syncthreads();

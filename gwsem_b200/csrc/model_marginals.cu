@@ -285,13 +285,12 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
   mp.zz = up(pool, zz, st);
   mp.cc = up(pool, cc, st);
   // Series pass from class sums: six products of c1..c3 per ordinal item, rounded to a 2^-s grid (|h| 2^s <= 2^30) and
-  // packed as base-256 digits for the tcgen05 class-sum kernel.  Only when every item is ordinal.
+  // packed as base-256 digits for the tcgen05 class-sum kernel.
   mp.cs_nf = 0;
   d_csq = nullptr;
   {
-    bool all_ord = J > 0;
-    for (int j = 0; j < J; ++j) all_ord = all_ord && mh.items[j].n_cat > 0;
-    if (all_ord && 6 * J <= 64) {
+    // (a continuous item needs v and v^2 only: psi = u v, psi' = 1 - u^2 - v^2, psi'' = 6 u v; it keeps six slots)
+    if (J > 0 && 6 * J <= 64) {
       const int nF = 6 * J;
       std::vector<std::vector<double>> h(nF, std::vector<double>(n_pad, 0.0));
       for (int s2 = 0; s2 < n_src; ++s2) {
@@ -301,7 +300,11 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
           const double* c = &cc[((size_t)s2 * J + j) * 3];
           double* dst[6];
           for (int k = 0; k < 6; ++k) dst[k] = &h[6 * j + k][s2];
-          *dst[0] = c[0]; *dst[1] = c[1]; *dst[2] = c[0] * c[0]; *dst[3] = c[2]; *dst[4] = c[0] * c[0] * c[0]; *dst[5] = c[0] * c[1];
+          if (mh.items[j].n_cat > 0) {
+            *dst[0] = c[0]; *dst[1] = c[1]; *dst[2] = c[0] * c[0]; *dst[3] = c[2]; *dst[4] = c[0] * c[0] * c[0]; *dst[5] = c[0] * c[1];
+          } else {
+            *dst[0] = c[0]; *dst[1] = c[0] * c[0];   // v, v^2
+          }
         }
       }
       std::vector<std::vector<int64_t>> q(nF, std::vector<int64_t>(n_pad, 0));
