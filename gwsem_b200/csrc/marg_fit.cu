@@ -354,7 +354,13 @@ __global__ void __launch_bounds__(64)
   for (int e = lane; e < nt * nt; e += LANES) {
     const int x = e / nt, y = e % nt;
     double v = 0.0;
-    for (int k = 0; k < nt; ++k) v += T[x * nt + k] * Ai[y * nt + k];
+    // lanes hold different rows y of Ai (a stride of nt doubles: one bank when nt = 32): each lane starts its walk
+    // along k at its own y, so that a step touches nt different banks
+    for (int k = 0; k < nt; ++k) {
+      int kk = k + y;
+      if (kk >= nt) kk -= nt;
+      v += T[x * nt + kk] * Ai[y * nt + kk];
+    }
     acov[e] = v;
   }
   gsync<LANES>();
