@@ -496,7 +496,8 @@ int gwsem_gwas_run(gwsem_model* m, gwsem_source* s, const gwsem_job* job, int64_
     const int P = m->P;
     // SNP list (1-based in the API and in the log, R/model.R:59-64)
     std::vector<uint32_t> todo;
-    if (job->snp) {
+    if (job->n_snp >= 0) {   // an explicit list, possibly empty (a rank whose shard is empty writes the header only)
+      if (job->n_snp > 0 && !job->snp) fail("n_snp = %d but no SNP list", job->n_snp);
       for (int k = 0; k < job->n_snp; ++k) {
         if (job->snp[k] < 1) fail("SNP indices are 1-based");
         todo.push_back((uint32_t)job->snp[k] - 1);
@@ -508,7 +509,12 @@ int gwsem_gwas_run(gwsem_model* m, gwsem_source* s, const gwsem_job* job, int64_
     ContextFile ctx;
     if (job->context_path && job->context_path[0]) ctx.load(job->context_path);
 
-    FILE* fo = fopen(job->out_path, "w");
+    // the log is the checkpoint (R/model.R:191): whatever happens later, rows already formatted reach the disk
+    struct LogFile {
+      FILE* f = nullptr;
+      ~LogFile() { if (f) fclose(f); }
+    } log_guard;
+    FILE* fo = log_guard.f = fopen(job->out_path, "w");
     if (!fo) fail("cannot open %s for writing", job->out_path);
     std::string line;
     line.reserve(1 << 16);
@@ -594,10 +600,17 @@ int gwsem_gwas_run(gwsem_model* m, gwsem_source* s, const gwsem_job* job, int64_
       const int parts = (int)std::min<int64_t>(std::min(hw, 32u), std::max(1, b.n / 256));
       std::vector<std::string> text(parts);
       std::vector<std::thread> pool;
-      for (int t = 1; t < parts; ++t)
-        pool.emplace_back([&, t] { format_rows(b, (int)((int64_t)b.n * t / parts), (int)((int64_t)b.n * (t + 1) / parts), tbuf, text[t]); });
-      format_rows(b, 0, b.n / parts, tbuf, text[0]);
+      std::vector<std::exception_ptr> err(parts);   // format_rows can fail (a .pvar / .bim shorter than the file)
+      auto work = [&](int t) {
+        try {
+          format_rows(b, (int)((int64_t)b.n * t / parts), (int)((int64_t)b.n * (t + 1) / parts), tbuf, text[t]);
+        } catch (...) { err[t] = std::current_exception(); }
+      };
+      for (int t = 1; t < parts; ++t) pool.emplace_back(work, t);
+      work(0);
       for (auto& th : pool) th.join();
+      for (auto& e2 : err)
+        if (e2) std::rethrow_exception(e2);
       for (auto& part : text)
         if (fwrite(part.data(), 1, part.size(), fo) != part.size()) fail("write error on %s", job->out_path);
     };
@@ -630,6 +643,7 @@ int gwsem_gwas_run(gwsem_model* m, gwsem_source* s, const gwsem_job* job, int64_
     static const bool timing = getenv("GWSEM_TIMING") != nullptr;   // development aid: phase times on stderr
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_stage = 0, t_fit = 0, t_wait = 0, t_dl = 0;
+    try {
     for (size_t t0 = 0; t0 < todo.size(); t0 += batch) {
       const int n = (int)std::min<size_t>(batch, todo.size() - t0);
       const uint32_t* v = &todo[t0];
@@ -681,10 +695,18 @@ int gwsem_gwas_run(gwsem_model* m, gwsem_source* s, const gwsem_job* job, int64_
       written += n;
     }
     if (pending.valid()) pending.get();
+    } catch (...) {
+      // the helper threads use this frame's objects: let them finish before it unwinds
+      if (pending.valid()) pending.wait();
+      if (reading.valid()) reading.wait();
+      throw;
+    }
     if (timing)
       fprintf(stderr, "gwsem timing: batch %d, stage(bgen only) %.3f s, stage+fit %.3f s, wait-for-writer %.3f s, download %.3f s\n",
               batch, t_stage, t_fit, t_wait, t_dl);
-    fclose(fo);
+    log_guard.f = nullptr;
+    if (fflush(fo) != 0 || ferror(fo)) { fclose(fo); fail("write error on %s", job->out_path); }
+    if (fclose(fo) != 0) fail("write error on %s (close)", job->out_path);
     if (rows_written) *rows_written = written;
   });
 }

@@ -85,8 +85,7 @@ __device__ void implied_stats(const FitProgram& fp, const MargProgram& mp, Model
   gsync<LANES>();
   for (int e = lane; e < mp.n_stat; e += LANES) {
     const int kind = mp.stat_kind[e], a = mp.stat_a[e], b = mp.stat_b[e];
-    // manifest 0 is snp (continuous); item j is manifest j + 1
-    const bool ord_a = a > 0 && mp.n_cat[a - 1] > 0;
+    const bool ord_a = mp.vcat[a] > 0;
     const double sda = ord_a ? sqrt(C[a * nv + a]) : 1.0;
     double v;
     if (kind == 0) v = mu[a];
@@ -96,7 +95,7 @@ __device__ void implied_stats(const FitProgram& fp, const MargProgram& mp, Model
     } else if (kind == 2) v = Z[a * nv + fp.exo_latent[b]] / sda;
     else if (kind == 3) v = C[a * nv + a];
     else {
-      const bool ord_b = b > 0 && mp.n_cat[b - 1] > 0;
+      const bool ord_b = mp.vcat[b] > 0;
       const double sdb = ord_b ? sqrt(C[b * nv + b]) : 1.0;
       v = C[a * nv + b] / (sda * sdb);
     }
@@ -119,8 +118,8 @@ __device__ void marg_jacobian(const FitProgram& fp, const MargProgram& mp, Model
     const int ri = pairs ? idx : idx / n_c, ci = pairs ? idx : idx - ri * n_c;
     const int e = rows ? rows[ri] : ri, k = cols ? cols[ci] : ci;
     const int kind = mp.stat_kind[e], a = mp.stat_a[e], b = mp.stat_b[e];
-    const bool ord_a = a > 0 && mp.n_cat[a - 1] > 0;
-    const bool ord_b = kind == 4 && b > 0 && mp.n_cat[b - 1] > 0;
+    const bool ord_a = mp.vcat[a] > 0;
+    const bool ord_b = kind == 4 && mp.vcat[b] > 0;
     const int xa = kind == 2 ? fp.exo_latent[b] : 0;
     double dCaa = 0.0, dCbb = 0.0, dCab = 0.0, dmu = 0.0, dZ = 0.0;
     for (int ce = fp.par_cell_ptr[k]; ce < fp.par_cell_ptr[k + 1]; ++ce) {
@@ -190,15 +189,18 @@ __global__ void __launch_bounds__(64)
   const int group = threadIdx.x / LANES, lane = threadIdx.x % LANES;
   const int snp = blockIdx.x * (blockDim.x / LANES) + group;
   if (snp >= n_snps) return;
-  const int J = mp.J, n1 = mp.n1, npii = mp.npii, q0 = mp.q0, D = 2 + J;
-  const int nt = 2 + n1 + J + npii, ns = mp.n_stat, P = fp.P, nv = fp.nv;
+  const int J = mp.J, n1 = mp.n1, q0 = mp.q0, D = 2 + J;
+  const int nt = mp.nt, ns = mp.n_stat, P = fp.P, nv = fp.nv;
   const WarpScratch ws = marg_ws(fp.p, nv);
   const MargScratch ms = marg_layout(nt, ns, P, mp.n_a > 0 ? mp.n_b : 0);
   double* sm = smem_d + (size_t)group * (ws.total + ms.total);
   double* mx = sm + ws.total;
   const double* rec = summary + (int64_t)snp * mp.sum_stride;
-  const int n = (int)rec[0];
-  const double mu_g = rec[1], var_g = rec[2];
+  // full record (marg_exact.cu): every estimate and score product was taken over this SNP's retained people
+  const double* frec = mp.full ? mp.full + (int64_t)snp * mp.full_stride : nullptr;
+  const bool full = frec && (mp.full_all || frec[0] >= 0.0);
+  const int n = (int)(full ? frec[0] : rec[0]);
+  const double mu_g = full ? 0.0 : rec[1], var_g = full ? 0.0 : rec[2];
 
   double* est = res.est + (int64_t)snp * P;
   double* vcov = res.vcov + (int64_t)snp * P * P;
@@ -214,17 +216,41 @@ __global__ void __launch_bounds__(64)
     res.catch_var[snp] = -1;
     res.iterations[snp] = 0;
   }
-  if (n < 2 || !(var_g * (double)n / (double)(n - 1) >= fp.min_variance)) {
+  if (full) {
+    if (frec[1] != 0.0) {
+      if (lane == 0) { res.catch_code[snp] = (int)frec[1]; res.catch_var[snp] = (int)frec[2]; }
+      return;
+    }
+  } else if (n < 2 || !(var_g * (double)n / (double)(n - 1) >= fp.min_variance)) {
     if (lane == 0) { res.catch_code[snp] = GWSEM_CATCH_MIN_VARIANCE; res.catch_var[snp] = 0; }
     return;
   }
-  // item-only sums were taken over all included people: outer products are down-dated exactly with the
-  // missing-call people's rows; the item-pair A21 rows (not outer products) by the retained fraction
-  const double scale = (double)n / (double)mp.n_incl;
 
   // ---- theta, A, B.   index map: [0,1] snp | 2.. items | ir = 2+n1 .. rho(snp,item) | ii .. rho(item,item)
   const int ir = 2 + n1, ii = ir + J;
   double *th = mx + ms.th, *A = mx + ms.A, *B = mx + ms.B, *Ai = mx + ms.Ai, *T = mx + ms.T;
+  if (full) {
+    const int n1t = mp.n1t;
+    for (int e = lane; e < nt; e += LANES) th[e] = frec[mp.fo_theta + e];
+    for (int e = lane; e < nt * nt; e += LANES) {
+      const int x = e / nt, y = e % nt;
+      const double b = frec[mp.fo_B + e];
+      B[e] = b;
+      // A: block-diagonal stage-1 information (outer products), A21 rows, diagonal A22
+      double a = 0.0;
+      if (x < n1t && y < n1t) {
+        int vx = 0, vy = 0;
+        while (x >= mp.voff[vx + 1]) ++vx;
+        while (y >= mp.voff[vy + 1]) ++vy;
+        if (vx == vy) a = b;
+      } else if (x >= n1t) {
+        if (y < n1t) a = frec[mp.fo_a21 + (x - n1t) * n1t + y];
+        else if (y == x) a = b;
+      }
+      A[e] = a;
+      Ai[e] = x == y ? 1.0 : 0.0;
+    }
+  } else {
   for (int e = lane; e < nt; e += LANES) {
     double v;
     if (e == 0) v = mu_g;
@@ -244,7 +270,7 @@ __global__ void __launch_bounds__(64)
     if (dx >= 0 && dy >= 0) v = rec[mp.o_bdd + dx * D + dy];
     else if (dx >= 0) v = rec[mp.o_bd0 + dx * q0 + cy];
     else if (dy >= 0) v = rec[mp.o_bd0 + dy * q0 + cx];
-    else v = mp.B00[cx * q0 + cy] - rec[mp.o_mmat + cx * q0 + cy];
+    else v = mp.B00[cx * q0 + cy];
     B[e] = v;
     // A: block diagonal stage-1 information (outer products), A21 rows, diagonal A22
     double a = 0.0;
@@ -255,60 +281,21 @@ __global__ void __launch_bounds__(64)
         if (x - 2 >= mp.col_of[j] && x - 2 < mp.col_of[j + 1]) jx = j;
         if (y - 2 >= mp.col_of[j] && y - 2 < mp.col_of[j + 1]) jy = j;
       }
-      if (jx == jy) a = mp.B00[(x - 2) * q0 + (y - 2)] - rec[mp.o_mmat + (x - 2) * q0 + (y - 2)];
+      if (jx == jy) a = mp.B00[(x - 2) * q0 + (y - 2)];
     } else if (x >= ir && x < ii) {
       const int j = x - ir;
       if (y < 2) a = rec[mp.o_a21snp + 2 * j + y];
       else if (y < ir && y - 2 >= mp.col_of[j] && y - 2 < mp.col_of[j + 1]) a = rec[mp.o_a21item + (y - 2)];
       else if (y == x) a = rec[mp.o_a22 + j];
     } else if (x >= ii) {
-      if (y >= 2 && y < ir) a = mp.A21ii[(x - ii) * n1 + (y - 2)] * scale;
-      else if (y == x) a = mp.B00[(n1 + x - ii) * q0 + (n1 + x - ii)] - rec[mp.o_mmat + (n1 + x - ii) * q0 + (n1 + x - ii)];
+      if (y >= 2 && y < ir) a = mp.A21ii[(x - ii) * n1 + (y - 2)];
+      else if (y == x) a = mp.B00[(n1 + x - ii) * q0 + (n1 + x - ii)];
     }
     A[e] = a;
     Ai[e] = x == y ? 1.0 : 0.0;
   }
-  gsync<LANES>();
-  // ---- missing calls: one Newton step takes the item-side estimates from the full sample to the
-  // retained subset.  The full-sample score vanishes, so the subset score is minus the missing
-  // people's; information in outer-product form (already down-dated in A).
-  if (n < mp.n_incl) {
-    double* dth = T;            // nt: the step, indexed like theta
-    double* blk = T + nt;       // scratch for one stage-1 block
-    for (int e = lane; e < nt; e += LANES) dth[e] = 0.0;
-    gsync<LANES>();
-    for (int j = 0; j < J; ++j) {
-      const int c0 = mp.col_of[j], d = mp.col_of[j + 1] - c0;
-      // exact full-sample information minus the missing people's outer products
-      for (int e = lane; e < d * d; e += LANES)
-        blk[e] = mp.H11[mp.h11_of[j] + e] - rec[mp.o_mmat + (c0 + e / d) * q0 + (c0 + e % d)];
-      gsync<LANES>();
-      if (warp_cholesky<LANES>(blk, d, lane) && lane == 0) {
-        double* x = dth + 2 + c0;
-        for (int i = 0; i < d; ++i) {
-          double v = -rec[mp.o_msum + c0 + i];
-          for (int k = 0; k < i; ++k) v -= blk[i * d + k] * x[k];
-          x[i] = v / blk[i * d + i];
-        }
-        for (int i = d - 1; i >= 0; --i) {
-          double v = x[i];
-          for (int k = i + 1; k < d; ++k) v -= blk[k * d + i] * x[k];
-          x[i] = v / blk[i * d + i];
-        }
-      }
-      gsync<LANES>();
-    }
-    // correlations follow: 0 = score + d score/d rho * step_rho + d score/d theta1 * step_theta1
-    for (int e = lane; e < J + npii; e += LANES) {
-      const int x = ir + e;
-      double v = e < J ? 0.0 : -rec[mp.o_msum + n1 + (e - J)];
-      for (int y = 2; y < ir; ++y) v -= A[x * nt + y] * dth[y];
-      dth[x] = v / A[x * nt + x];
-    }
-    gsync<LANES>();
-    for (int e = lane; e < nt; e += LANES) th[e] += dth[e];
-    gsync<LANES>();
   }
+  gsync<LANES>();
 
   // ---- Ai = A^-1 by Gauss-Jordan with partial pivoting (A is block lower triangular, well conditioned)
   bool singular = false;
@@ -367,20 +354,21 @@ __global__ void __launch_bounds__(64)
 
   // ---- statistics and their delta-method rows (<= 3 non-zeros each)
   double *s = mx + ms.s, *hidx = mx + ms.hidx, *hcoef = mx + ms.hcoef, *L = mx + ms.L, *gscale = mx + ms.scale;
-  const double sd_g = sqrt(var_g);
+  // sd of a continuous manifest variable: its stage-1 variance is the last entry of its block of theta
+  auto sd_of = [&](int a) { return sqrt(th[mp.voff[a + 1] - 1]); };
   for (int e = lane; e < ns; e += LANES) {
     const int kind = mp.stat_kind[e], x = mp.stat_theta[e];
     double i0 = x, c0 = 1.0, i1 = 0, c1 = 0.0, i2 = 0, c2 = 0.0, v = th[x];
     if (kind == 4) {  // covariance of variables a > b: rho * sd_a * sd_b, sd = 1 for ordinal
       const int a = mp.stat_a[e], b = mp.stat_b[e];
-      const bool ca = a == 0 || mp.n_cat[a - 1] == 0, cb = b == 0 || mp.n_cat[b - 1] == 0;
-      const double sa = a == 0 ? sd_g : (ca ? mp.item_sd[a - 1] : 1.0), sb = b == 0 ? sd_g : (cb ? mp.item_sd[b - 1] : 1.0);
+      const bool ca = mp.vcat[a] == 0, cb = mp.vcat[b] == 0;
+      const double sa = ca ? sd_of(a) : 1.0, sb = cb ? sd_of(b) : 1.0;
       const double rho = th[x];
       v = rho * sa * sb;
       c0 = sa * sb;
       // variance parameter of a continuous variable: snp -> theta 1; item j -> last column of its block
-      if (ca) { i1 = a == 0 ? 1 : 2 + mp.col_of[a] - 1; c1 = rho * sb / (2.0 * sa); }
-      if (cb) { i2 = b == 0 ? 1 : 2 + mp.col_of[b] - 1; c2 = rho * sa / (2.0 * sb); }
+      if (ca) { i1 = mp.voff[a + 1] - 1; c1 = rho * sb / (2.0 * sa); }
+      if (cb) { i2 = mp.voff[b + 1] - 1; c2 = rho * sa / (2.0 * sb); }
     }
     s[e] = v;
     hidx[3 * e] = i0; hidx[3 * e + 1] = i1; hidx[3 * e + 2] = i2;
@@ -586,7 +574,7 @@ __global__ void __launch_bounds__(64)
 __global__ void __launch_bounds__(32) marg_pattern_kernel(FitProgram fp, MargProgram mp, double* __restrict__ out) {
   extern __shared__ double smem_d[];
   const int lane = threadIdx.x;
-  const int nt = 2 + mp.n1 + mp.J + mp.npii, ns = mp.n_stat, P = fp.P;
+  const int nt = mp.nt, ns = mp.n_stat, P = fp.P;
   const WarpScratch ws = marg_ws(fp.p, fp.nv);
   const MargScratch ms = marg_layout(nt, ns, P, 0);
   double *sm = smem_d, *mx = sm + ws.total;
@@ -605,7 +593,7 @@ __global__ void __launch_bounds__(32) marg_pattern_kernel(FitProgram fp, MargPro
 }  // namespace
 
 void launch_marg_pattern(gwsem_engine* e, const FitProgram& fp, const MargProgram& mp, double* d_out) {
-  const int nt = 2 + mp.n1 + mp.J + mp.npii;
+  const int nt = mp.nt;
   const size_t smem = ((size_t)marg_ws(fp.p, fp.nv).total + marg_layout(nt, mp.n_stat, fp.P, 0).total) * sizeof(double);
   if (smem > 227 * 1024) fail("marginals model too large for the per-SNP fit kernel (%zu bytes of scratch)", smem);
   GW_CUDA(cudaFuncSetAttribute(marg_pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -615,7 +603,7 @@ void launch_marg_pattern(gwsem_engine* e, const FitProgram& fp, const MargProgra
 }
 
 size_t marg_fit_scratch_doubles(const FitProgram& fp, const MargProgram& mp) {
-  const int nt = 2 + mp.n1 + mp.J + mp.npii;
+  const int nt = mp.nt;
   return (size_t)marg_ws(fp.p, fp.nv).total + marg_layout(nt, mp.n_stat, fp.P, mp.n_a > 0 ? mp.n_b : 0).total;
 }
 

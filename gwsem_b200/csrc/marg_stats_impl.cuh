@@ -221,72 +221,9 @@ __global__ void __launch_bounds__(kT, 2)
 #pragma unroll
   for (int j = 0; j < J; ++j) ordinal[j] = mp.n_cat[j] > 0;
 
-  // ---- people of the model whose call is missing for this SNP (naAction='omit' drops them from
-  // every statistic): their item-side score rows, summed and as outer products, let marg_fit.cu
-  // down-date the SNP-independent estimates and information to the retained subset.
-  if (n < mp.n_incl) {
-    // All warps scan for missing calls (ascending order: deterministic sums); the score rows of the
-    // people found are staged eight at a time and every thread owns a few entries of the sums.
-    constexpr int kCap = 4096;                        // people scanned per round
-    constexpr int kMaxOwn = (64 * 64 + 64 + kT - 1) / kT;
-    double* rowbuf = dyn;                             // [8][q0p]
-    int* list = reinterpret_cast<int*>(dyn + 8 * 64); // kCap entries
-    __shared__ int warp_cnt[kT / 32];
-    const int q0 = mp.q0, q0p = mp.q0p, n_el = q0 * q0 + q0;
-    double macc[kMaxOwn];
-#pragma unroll
-    for (int k = 0; k < kMaxOwn; ++k) macc[k] = 0.0;
-    for (int base = 0; base < n_src; base += kCap) {
-      int cnt = 0;
-      for (int s0 = base; s0 < min(n_src, base + kCap); s0 += kT) {
-        const int i = s0 + tid;
-        bool miss = false;
-        if (i < n_src && inc8[i]) {
-          double u;
-          miss = !std_geno(i, &u);
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, miss);
-        if (lane == 0) warp_cnt[warp] = __popc(bal);
-        __syncthreads();
-        int before = cnt;
-        for (int w = 0; w < warp; ++w) before += warp_cnt[w];
-        if (miss) list[before + __popc(bal & ((1u << lane) - 1u))] = i;
-#pragma unroll
-        for (int w = 0; w < kT / 32; ++w) cnt += warp_cnt[w];
-        __syncthreads();
-      }
-      for (int c0 = 0; c0 < cnt; c0 += 8) {
-        const int who = c0 + warp;
-        for (int b2 = lane; b2 < q0p; b2 += 32)
-          rowbuf[warp * q0p + b2] = who < cnt ? mp.sc0[(int64_t)list[who] * q0p + b2] : 0.0;
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < kMaxOwn; ++k) {
-          const int e = tid + k * kT;
-          if (e < n_el) {
-            double v = 0.0;
-            if (e < q0 * q0) {
-              const int r1 = e / q0, r2 = e - r1 * q0;
-#pragma unroll
-              for (int w = 0; w < 8; ++w) v = fma(rowbuf[w * q0p + r1], rowbuf[w * q0p + r2], v);
-            } else {
-#pragma unroll
-              for (int w = 0; w < 8; ++w) v += rowbuf[w * q0p + (e - q0 * q0)];
-            }
-            macc[k] += v;
-          }
-        }
-        __syncthreads();
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < kMaxOwn; ++k) {
-      const int e = tid + k * kT;
-      if (e < q0 * q0) out[mp.o_mmat + e] = macc[k];
-      else if (e < n_el) out[mp.o_msum + (e - q0 * q0)] = macc[k];
-    }
-    __syncthreads();
-  }
+  // A missing call drops the person from every statistic of this SNP (naAction = 'omit'), the items' own
+  // included: nothing on the item side is SNP-independent any more, and marg_exact_kernel recomputes the lot.
+  if (n < mp.n_incl) return;
 
   // ---- stage 2: Newton on the score of every rho_j (exact second derivative; the outer-product
   // information stands in when the curvature estimate is not negative)
@@ -300,7 +237,11 @@ __global__ void __launch_bounds__(kT, 2)
   // within O(rho^3) of the estimate; when it is below kSeriesMax the loop ends there, otherwise
   // exact Newton passes follow until a step is below kNewtonStop.  The Gamma pass below evaluates
   // one more exact Newton step at no extra cost and applies it.
-  constexpr double kNewtonStop = 3e-4, kSeriesMax = 0.04;
+  // (the score rows of the Gamma pass are evaluated before that last step: its size bounds the relative error of
+  // the weight matrix, and with it the estimates' distance from the oracle's in units of their standard errors)
+  // The series root is O(rho^3) from the estimate: accepted below 0.012 (2e-6), so that the scores of the Gamma pass,
+  // taken at the accepted point, stand within 1e-5 of an SE of those at the estimate.
+  constexpr double kNewtonStop = 3e-5, kFinalClamp = 3e-4, kSeriesMax = 0.012;
   for (int iter = 0; iter < 30; ++iter) {
     double s1[J], s2[J], s3[J], rh[J];
 #pragma unroll
@@ -529,7 +470,7 @@ __global__ void __launch_bounds__(kT, 2)
   for (int j = 0; j < J; ++j) {
     const double a = block_sum(a21snp[2 * j], red, tid), b = block_sum(a21snp[2 * j + 1], red, tid);
     const double score = block_sum(ns1[j], red, tid), curv = block_sum(ns2[j], red, tid);
-    const double step = curv < 0.0 ? fmax(-kNewtonStop, fmin(kNewtonStop, -score / curv)) : 0.0;
+    const double step = curv < 0.0 ? fmax(-kFinalClamp, fmin(kFinalClamp, -score / curv)) : 0.0;
     if (tid == 0) { out[mp.o_a21snp + 2 * j] = a; out[mp.o_a21snp + 2 * j + 1] = b; out[mp.o_rho + j] = rh[j] + step; }
   }
   {

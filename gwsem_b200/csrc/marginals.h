@@ -77,6 +77,38 @@ struct MargProgram {
   // summary record per SNP (doubles)
   int sum_stride = 0, o_rho = 0, o_a22 = 0, o_a21snp = 0, o_a21item = 0, o_bdd = 0, o_bd0 = 0;
   int o_msum = 0, o_mmat = 0;  // missing-call people: sum of their item-side score rows, and of the outer products
+  // Full records (marg_exact.cu): SNPs whose every stage-1 / stage-2 estimate and score was recomputed over the people
+  // retained for that SNP carry (theta, A21, B) themselves; marg_fit reads those instead of assembling them from the
+  // SNP-independent item side.  full_all: every SNP of the launch has one (models without a static item side);
+  // otherwise the SNPs with a missing call do (exact naAction = 'omit').  The theta layout is the oracle's: stage-1
+  // blocks of the manifest variables in order (continuous: intercept, slopes, variance; ordinal: thresholds, slopes),
+  // then one correlation per pair, column-major lower triangle.
+  int full_all = 0, exact_missing = 0;
+  int p = 0, nt = 0, n1t = 0;                // manifest variables, length of theta, stage-1 parameters in it
+  int vcat[kMargMaxItems + 2] = {0};         // categories per manifest variable (0 = continuous)
+  int voff[kMargMaxItems + 3] = {0};         // first theta index of each manifest variable's block
+  int full_stride = 0, fo_theta = 0, fo_a21 = 0, fo_B = 0;
+  const double* full = nullptr;              // [snp][full_stride]: n, catch code, catch variable, theta, A21, B
+};
+
+// The generic per-SNP marginals kernel (marg_exact.cu): every variable and covariate may depend on the SNP.
+constexpr int kExMaxVars = kMargMaxItems + 2;
+constexpr int kExMaxCov = 12;
+struct ExactProgram {
+  int p = 0, K = 0, Kp = 1, nt = 0, n1 = 0, npairs = 0, T = 256, only_missing = 0, n_incl = 0, snp_exo = 0;
+  double min_variance = 0.0;
+  int vkind[kExMaxVars] = {0};               // 0 static continuous, 1 static ordinal, 2 snp, 3 snp x static column
+  int ncat[kExMaxVars] = {0};
+  int voff[kExMaxVars + 1] = {0};
+  int nx[kExMaxVars] = {0};                  // free covariates of each variable
+  int xidx[kExMaxVars][kExMaxCov] = {{0}};
+  int xkind[kExMaxCov] = {0};                // 0 static column, 1 snp, 2 snp x static column
+  const double* V = nullptr;                 // [n_pad][p]: value / category code / moderator of each variable
+  const double* X = nullptr;                 // [n_pad][Kp]
+  const double* theta0 = nullptr;            // nt: starting point (the SNP-independent estimates where there are any)
+  int gl_n[3] = {0, 0, 0};                   // Gauss-Legendre rules for the bivariate normal integral
+  const double* gl = nullptr;                // nodes then weights of each rule, back to back
+  int full_stride = 0, fo_theta = 0, fo_a21 = 0, fo_B = 0;
 };
 
 }  // namespace gwsem

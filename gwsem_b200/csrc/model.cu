@@ -96,40 +96,54 @@ gwsem_model::gwsem_model(gwsem_engine* e, const gwsem_model_spec* s) : engine(e)
     for (int r = 0; r < n_rows; ++r)
       if (!std::isfinite(col[r])) row_ok[r] = 0;
   if (fit_kind == 1) {
-    marg_mode = kind[0] == 1 ? 0 : 1;
-    for (int v = 1; v < p; ++v)
-      if (kind[v] != 0) fail("marginals: gxe product columns are not implemented yet");
-    if (p - 1 > gwsem::kMargMaxItems) fail("marginals: at most %d items", gwsem::kMargMaxItems);
+    // marg_mode 0: snp is the first manifest variable and nothing else carries the genotype (buildOneFac /
+    //              buildOneFacRes / buildTwoFac): SNP-independent item side + marg_stats_kernel, and
+    //              marg_exact_kernel for the SNPs with a missing call
+    //           1: one ordinal item regressed on snp (+ gxe products) and covariates (probit.cu)
+    //           2: one continuous item regressed on the same (linreg.cu)
+    //           3: anything else (several items with an exogenous snp, gxe products as manifest variables, snp
+    //              elsewhere in the manifest list): marg_exact_kernel for every SNP
     n_categories.assign(s->n_categories, s->n_categories + p);
     exo_latent.assign(s->exo_latent, s->exo_latent + s->n_exo);
     exo_free.assign(s->exo_free, s->exo_free + (size_t)p * s->n_exo);
     exo_kind.assign(s->n_exo, 0);
+    bool geno_in_exo = false, geno_elsewhere = false;
+    for (int v = 1; v < p; ++v)
+      if (kind[v] != 0) geno_elsewhere = true;
     for (int k = 0; k < s->n_exo; ++k) {
       const int ek = s->exo_kind ? s->exo_kind[k] : (s->exo_data[k] ? 0 : 1);
       exo_kind[k] = ek;
+      if (ek != 0) geno_in_exo = true;
       if (ek == 1) {  // the genotype column as an exogenous predictor (buildItem with exogenous = TRUE)
-        if (marg_mode != 1 || snp_exo >= 0) fail("marginals: unexpected exogenous covariate without data");
+        if (snp_exo >= 0) fail("marginals: more than one exogenous covariate without data");
         snp_exo = k;
         exo_cols.emplace_back();
         continue;
       }
       if (!s->exo_data[k]) fail("marginals: exogenous covariate %d has no data column", k);
-      if (ek == 2 && marg_mode != 1) fail("marginals: a gxe product can only be a definition variable next to an exogenous snp");
       exo_cols.emplace_back(s->exo_data[k], s->exo_data[k] + n_rows);
       for (int r = 0; r < n_rows; ++r)
         if (!std::isfinite(exo_cols[k][r])) row_ok[r] = 0;
     }
-    if (marg_mode == 1) {
-      if (kind[0] != 0 || p != 1 || snp_exo < 0)
-        fail("marginals with an exogenous snp is implemented for a single item (buildItem with exogenous = TRUE)");
-      if (n_categories[0] == 1) fail("marginals: the item has a single category");
-      if (n_categories[0] == 0) marg_mode = 2;   // continuous item: per-SNP linear regression (linreg.cu)
-      if (s->n_exo > gwsem::kLinregMaxX) fail("marginals: at most %d definition variables", gwsem::kLinregMaxX);
+    for (int v = 0; v < p; ++v) {
+      if (n_categories[v] == 1) fail("marginals: manifest variable %d has a single category", v);
+      if (n_categories[v] > 0 && kind[v] != 0) fail("marginals: the genotype cannot be an ordinal variable (src/loader.cpp:395-397)");
     }
+    bool std_free = true;   // every item regressed on every covariate, snp on none
     for (int v = 0; v < p; ++v)
       for (int k = 0; k < s->n_exo; ++k)
-        if (exo_free[(size_t)v * s->n_exo + k] != (marg_mode >= 1 || v > 0))
-          fail("marginals: every item must be regressed on every exogenous covariate and snp on none");
+        if (exo_free[(size_t)v * s->n_exo + k] != (kind[v] == 0)) std_free = false;
+    if (kind[0] == 1 && !geno_elsewhere && !geno_in_exo && std_free && p - 1 <= gwsem::kMargMaxItems && p >= 2) marg_mode = 0;
+    else if (p == 1 && kind[0] == 0 && snp_exo >= 0 && std_free && s->n_exo <= gwsem::kLinregMaxX)
+      marg_mode = n_categories[0] > 0 ? 1 : 2;
+    else marg_mode = 3;
+    if (marg_mode == 3) {
+      if (p > gwsem::kExMaxVars) fail("marginals: at most %d manifest variables", gwsem::kExMaxVars);
+      if (s->n_exo > gwsem::kExMaxCov) fail("marginals: at most %d exogenous covariates", gwsem::kExMaxCov);
+      bool any = geno_in_exo;
+      for (int v = 0; v < p; ++v) any = any || kind[v] != 0;
+      if (!any) fail("marginals: the model does not use the genotype");
+    }
     thresholds.assign(s->thresholds, s->thresholds + 4 * (size_t)s->n_thresholds);
     q = p * (p + 1) / 2;
     nf = 1;

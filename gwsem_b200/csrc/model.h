@@ -49,7 +49,7 @@ struct gwsem_model {
   int fit_kind = 0;
   void prepare_ml();
   void prepare_warm();
-  int marg_mode = 0;   // 0: snp is a manifest variable; 1: snp is an exogenous predictor of one ordinal item
+  int marg_mode = 0;   // see the constructor (model.cu)
   int snp_exo = -1;    // which exogenous covariate is the genotype column (mode 1)
   gwsem::ProbitProgram pp;
   gwsem::LinregProgram lp;   // marg_mode 2: one continuous item on definition variables that include the snp
@@ -60,7 +60,8 @@ struct gwsem_model {
   std::vector<double> thresholds;  // n x 4
   gwsem::MarginalsHost mh;
   gwsem::MargProgram mp;
-  gwsem::DeviceBuffer<double> d_summary, d_cs_sums;
+  gwsem::ExactProgram ex;   // marg_exact_kernel: SNPs with a missing call (marg_mode 0), every SNP (marg_mode 3)
+  gwsem::DeviceBuffer<double> d_summary, d_cs_sums, d_full;
   const int8_t* d_csq = nullptr;          // marginals: digits of the series products (tcgen05 layout)
   const double* d_cs_inv_scale = nullptr;
   void prepare_marginals(const std::vector<int>& dest_of);

@@ -13,7 +13,38 @@
 
 using namespace gwsem;
 
+namespace gwsem {
+size_t marg_exact_smem_bytes(const ExactProgram& ex);
+void launch_marg_exact(gwsem_engine* e, const ExactProgram& ex, const uint8_t* d_rows, int64_t pitch, int n_snps, int n_src,
+                       const uint8_t* d_inc8, const int32_t* d_counts, int plink1, const double* d_geno, int n_pad,
+                       double* d_records);
+}
+
 namespace {
+// Gauss-Legendre nodes and weights on [-1, 1] (Newton on the Legendre polynomial)
+void gauss_legendre(int n, std::vector<double>& x, std::vector<double>& w) {
+  x.assign(n, 0.0);
+  w.assign(n, 0.0);
+  for (int i = 0; i < (n + 1) / 2; ++i) {
+    double z = std::cos(M_PI * (i + 0.75) / (n + 0.5)), pp = 0.0;
+    for (int it = 0; it < 100; ++it) {
+      double p1 = 1.0, p2 = 0.0;
+      for (int j = 0; j < n; ++j) {
+        const double p3 = p2;
+        p2 = p1;
+        p1 = ((2.0 * j + 1.0) * z * p2 - j * p3) / (j + 1.0);
+      }
+      pp = n * (z * p1 - p2) / (z * z - 1.0);
+      const double z1 = z;
+      z = z1 - p1 / pp;
+      if (std::fabs(z - z1) < 1e-16) break;
+    }
+    x[i] = -z;
+    x[n - 1 - i] = z;
+    w[i] = w[n - 1 - i] = 2.0 / ((1.0 - z * z) * pp * pp);
+  }
+}
+
 template <typename T>
 const T* up(std::vector<DeviceBuffer<uint8_t>>& pool, const std::vector<T>& v, cudaStream_t st) {
   pool.emplace_back();
@@ -154,7 +185,16 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
     pp.par_start = fp.par_start;
     return;
   }
-  const int J = p - 1, K = (int)exo_cols.size();
+  // ---- the SNP-independent variables (no genotype in them) given the SNP-independent covariates: stage 1, stage 2
+  // among them and their scores, once per model.  marg_mode 0 uses them as they are for every SNP without a
+  // missing call; otherwise they are marg_exact_kernel's starting point.
+  const int K = (int)exo_cols.size();
+  std::vector<int> svars, scov, spos(p, -1), cpos(K, -1);
+  for (int v = 0; v < p; ++v)
+    if (kind[v] == 0) { spos[v] = (int)svars.size(); svars.push_back(v); }
+  for (int k = 0; k < K; ++k)
+    if (exo_kind[k] == 0) { cpos[k] = (int)scov.size(); scov.push_back(k); }
+  const int J = (int)svars.size();
   std::vector<int> rows;
   for (int r = 0; r < n_rows; ++r)
     if (row_ok[r]) rows.push_back(r);
@@ -162,20 +202,108 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
   mh.items.resize(J);
   for (int j = 0; j < J; ++j) {
     MargItem& it = mh.items[j];
-    it.n_cat = n_categories[j + 1];
-    it.values = base[var_base[j + 1]].data();
+    it.n_cat = n_categories[svars[j]];
+    it.values = base[var_base[svars[j]]].data();
     it.n_values = n_rows;
-    if (it.n_cat == 1) fail("marginals: item %d has a single category", j + 1);
     if (it.n_cat > 0)
       for (int r : rows) {
         const double c = it.values[r];
-        if (c < 0 || c >= it.n_cat || c != std::floor(c)) fail("marginals: item %d holds a code outside 0..%d", j + 1, it.n_cat - 1);
+        if (c < 0 || c >= it.n_cat || c != std::floor(c)) fail("marginals: manifest variable %d holds a code outside 0..%d", svars[j], it.n_cat - 1);
       }
+    bool uses_any = false, uses_all = true;
+    for (int k : scov) (exo_free[(size_t)svars[j] * K + k] ? uses_any : uses_all) = exo_free[(size_t)svars[j] * K + k] != 0;
+    if (uses_any && !uses_all) fail("marginals: a variable regressed on some but not all exogenous covariates is not implemented");
+    if (!uses_any && !scov.empty() && marg_mode == 3) fail("marginals: a data variable that is not regressed on the exogenous covariates is not implemented");
   }
-  for (int k = 0; k < K; ++k) mh.X.push_back(exo_cols[k].data());
+  for (int k : scov) mh.X.push_back(exo_cols[k].data());
   mh.build(rows);
 
+  // ---- theta layout shared by both kernels and the oracle: per manifest variable (continuous: intercept, slopes,
+  // variance; ordinal: thresholds, slopes), then one correlation per pair (column-major lower triangle)
+  ex = ExactProgram();
+  ex.p = p; ex.K = K; ex.Kp = std::max(K, 1); ex.n_incl = n_incl; ex.min_variance = min_variance;
+  static const bool exact_all = getenv("GWSEM_MARG_EXACT_ALL") != nullptr;   // A/B aid: every SNP through marg_exact_kernel
+  ex.only_missing = marg_mode == 0 && !exact_all;
+  ex.snp_exo = snp_exo >= 0;
+  for (int k = 0; k < K; ++k) ex.xkind[k] = exo_kind[k];
+  for (int v = 0; v < p; ++v) {
+    ex.vkind[v] = kind[v] == 0 ? (n_categories[v] > 0 ? 1 : 0) : (kind[v] == 1 ? 2 : 3);
+    ex.ncat[v] = n_categories[v];
+    int nx = 0;
+    for (int k = 0; k < K; ++k)
+      if (exo_free[(size_t)v * K + k]) ex.xidx[v][nx++] = k;
+    ex.nx[v] = nx;
+    ex.voff[v + 1] = ex.voff[v] + (n_categories[v] > 0 ? n_categories[v] - 1 + nx : nx + 2);
+  }
+  ex.n1 = ex.voff[p];
+  ex.npairs = p * (p - 1) / 2;
+  ex.nt = ex.n1 + ex.npairs;
+  auto pair_index = [&](int a, int b) {   // a > b
+    int k = 0;
+    for (int bb = 0; bb < b; ++bb) k += p - 1 - bb;
+    return k + (a - b - 1);
+  };
+  {
+    std::vector<double> theta0(ex.nt, 0.0);
+    for (int v = 0; v < p; ++v) {
+      const int o = ex.voff[v], nx = ex.nx[v];
+      if (kind[v] != 0) { theta0[o + 1 + nx] = 1.0; continue; }
+      const MargItem& it = mh.items[spos[v]];
+      const bool uses = nx > 0;
+      if (it.n_cat > 0) {
+        for (int c = 0; c + 1 < it.n_cat; ++c) theta0[o + c] = it.th[c];
+        for (int m = 0; m < nx; ++m) {
+          const int k = ex.xidx[v][m];
+          theta0[o + it.n_cat - 1 + m] = (uses && cpos[k] >= 0) ? it.beta[cpos[k]] : 0.0;
+        }
+      } else {
+        theta0[o] = it.beta[0];
+        for (int m = 0; m < nx; ++m) {
+          const int k = ex.xidx[v][m];
+          theta0[o + 1 + m] = (uses && cpos[k] >= 0) ? it.beta[1 + cpos[k]] : 0.0;
+        }
+        theta0[o + 1 + nx] = it.var;
+      }
+    }
+    for (size_t k = 0; k < mh.pairs.size(); ++k)
+      theta0[ex.n1 + pair_index(svars[mh.pairs[k].first], svars[mh.pairs[k].second])] = mh.rho[k];
+    ex.theta0 = up(pool, theta0, st);
+    std::vector<double> V((size_t)n_pad * p, 0.0), Xg((size_t)n_pad * ex.Kp, 0.0);
+    for (int s2 = 0; s2 < n_src; ++s2) {
+      const int r = dest_of[s2];
+      if (r < 0 || !row_ok[r]) continue;
+      for (int v = 0; v < p; ++v)
+        if (var_base[v] >= 0) V[(size_t)s2 * p + v] = base[var_base[v]][r];
+      for (int k = 0; k < K; ++k)
+        if (exo_kind[k] != 1) Xg[(size_t)s2 * ex.Kp + k] = exo_cols[k][r];
+    }
+    ex.V = up(pool, V, st);
+    ex.X = up(pool, Xg, st);
+    std::vector<double> gl, x, w;
+    const int rules[3] = {12, 20, 32};
+    for (int rr = 0; rr < 3; ++rr) {
+      gauss_legendre(rules[rr], x, w);
+      ex.gl_n[rr] = rules[rr];
+      gl.insert(gl.end(), x.begin(), x.end());
+      gl.insert(gl.end(), w.begin(), w.end());
+    }
+    ex.gl = up(pool, gl, st);
+    ex.fo_theta = 3;
+    ex.fo_a21 = ex.fo_theta + ex.nt;
+    ex.fo_B = ex.fo_a21 + ex.npairs * ex.n1;
+    ex.full_stride = ex.fo_B + ex.nt * ex.nt;
+    ex.T = 256;
+    while (ex.T > 32 && marg_exact_smem_bytes(ex) > 227 * 1024) ex.T /= 2;
+    if (marg_exact_smem_bytes(ex) > 227 * 1024) fail("marginals: model too large for the per-SNP statistics kernel");
+  }
+
   mp = MargProgram();
+  mp.p = p; mp.nt = ex.nt; mp.n1t = ex.n1;
+  for (int v = 0; v < p; ++v) mp.vcat[v] = n_categories[v];
+  for (int v = 0; v <= p; ++v) mp.voff[v] = ex.voff[v];
+  mp.full_stride = ex.full_stride; mp.fo_theta = ex.fo_theta; mp.fo_a21 = ex.fo_a21; mp.fo_B = ex.fo_B;
+  mp.full_all = marg_mode == 3; mp.exact_missing = marg_mode == 0;
+  if (marg_mode == 0) {
   mp.J = J; mp.K = K; mp.Kp = std::max(K, 1); mp.q0 = mh.q0; mp.q0p = mh.q0 <= 32 ? 32 : 64;
   if (mh.q0 > 64) fail("marginals: %d item-side score columns (at most 64 supported)", mh.q0);
   mp.n1 = mh.n1; mp.npii = (int)mh.pairs.size(); mp.n_incl = n_incl;
@@ -227,48 +355,6 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
       theta1.push_back(it.var);
     }
   }
-  // statistic vector: (mean | thresholds per variable), slopes, variances, covariances
-  std::vector<int32_t> kind_, a_, b_, th_, tpar;
-  std::vector<double> tval;
-  auto push = [&](int kd, int a, int b, int th) { kind_.push_back(kd); a_.push_back(a); b_.push_back(b); th_.push_back(th); tpar.push_back(-1); tval.push_back(0.0); };
-  const int ir = 2 + mh.n1, ii = ir + J;
-  push(0, 0, 0, 0);  // snp mean
-  for (int j = 0; j < J; ++j) {
-    const MargItem& it = mh.items[j];
-    if (it.n_cat == 0) push(0, j + 1, 0, 2 + mh.col_of[j]);
-    else
-      for (int c = 0; c + 1 < it.n_cat; ++c) {
-        push(1, j + 1, c, 2 + mh.col_of[j] + c);
-        bool found = false;
-        for (size_t t = 0; t < thresholds.size() / 4; ++t)
-          if ((int)thresholds[4 * t] == j + 1 && (int)thresholds[4 * t + 1] == c) {
-            tpar.back() = (int)thresholds[4 * t + 2];
-            tval.back() = thresholds[4 * t + 3];
-            found = true;
-          }
-        if (!found) fail("marginals: no threshold %d given for ordinal item %d", c + 1, j + 1);
-      }
-  }
-  for (int j = 0; j < J; ++j) {
-    const MargItem& it = mh.items[j];
-    for (int k = 0; k < K; ++k) push(2, j + 1, k, 2 + mh.col_of[j] + (it.n_cat > 0 ? it.n_cat - 1 : 1) + k);
-  }
-  push(3, 0, 0, 1);  // snp variance
-  for (int j = 0; j < J; ++j)
-    if (mh.items[j].n_cat == 0) push(3, j + 1, j + 1, 2 + mh.col_of[j + 1] - 1);
-  for (int b = 0; b < p; ++b)
-    for (int a = b + 1; a < p; ++a) {
-      int th;
-      if (b == 0) th = ir + (a - 1);
-      else {
-        th = -1;
-        for (size_t k = 0; k < mh.pairs.size(); ++k)
-          if (mh.pairs[k].first == a - 1 && mh.pairs[k].second == b - 1) th = ii + (int)k;
-      }
-      push(4, a, b, th);
-    }
-  mp.n_stat = (int)kind_.size();
-  if (mp.n_stat > 128 || 2 + mh.n1 + J + (int)mh.pairs.size() > 128) fail("marginals: model too large");
   // summary record layout
   const int D = 2 + J;
   int o = 3;
@@ -278,8 +364,6 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
   mp.o_a21item = o; o += mh.n1;
   mp.o_bdd = o; o += D * D;
   mp.o_bd0 = o; o += D * mh.q0;
-  mp.o_msum = o; o += mh.q0;
-  mp.o_mmat = o; o += mh.q0 * mh.q0;
   mp.sum_stride = o;
   mp.sc0 = up(pool, sc0, st);
   mp.zz = up(pool, zz, st);
@@ -352,6 +436,35 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
     mp.h11_of[J] = (int)h11.size();
     mp.H11 = up(pool, h11, st);
   }
+  }  // marg_mode == 0
+  // statistic vector: (mean | thresholds per variable), slopes, variances, covariances
+  std::vector<int32_t> kind_, a_, b_, th_, tpar;
+  std::vector<double> tval;
+  auto push = [&](int kd, int a, int b, int th) { kind_.push_back(kd); a_.push_back(a); b_.push_back(b); th_.push_back(th); tpar.push_back(-1); tval.push_back(0.0); };
+  for (int v = 0; v < p; ++v) {
+    if (n_categories[v] == 0) push(0, v, 0, ex.voff[v]);
+    else
+      for (int c = 0; c + 1 < n_categories[v]; ++c) {
+        push(1, v, c, ex.voff[v] + c);
+        bool found = false;
+        for (size_t t = 0; t < thresholds.size() / 4; ++t)
+          if ((int)thresholds[4 * t] == v && (int)thresholds[4 * t + 1] == c) {
+            tpar.back() = (int)thresholds[4 * t + 2];
+            tval.back() = thresholds[4 * t + 3];
+            found = true;
+          }
+        if (!found) fail("marginals: no threshold %d given for ordinal variable %d", c + 1, v);
+      }
+  }
+  for (int v = 0; v < p; ++v)
+    for (int m = 0; m < ex.nx[v]; ++m)
+      push(2, v, ex.xidx[v][m], ex.voff[v] + (n_categories[v] > 0 ? n_categories[v] - 1 : 1) + m);
+  for (int v = 0; v < p; ++v)
+    if (n_categories[v] == 0) push(3, v, v, ex.voff[v + 1] - 1);
+  for (int b = 0; b < p; ++b)
+    for (int a = b + 1; a < p; ++a) push(4, a, b, ex.n1 + pair_index(a, b));
+  mp.n_stat = (int)kind_.size();
+  if (mp.n_stat > 128 || ex.nt > 128) fail("marginals: model too large");
   mp.stat_kind = up(pool, kind_, st);
   mp.stat_a = up(pool, a_, st);
   mp.stat_b = up(pool, b_, st);
@@ -445,7 +558,6 @@ void gwsem_model::run_marginals(const uint8_t* d_packed, int64_t pitch, const do
     launch_linreg_snp(engine, lp, d_packed, pitch, n, n_src, layout.d_inc8, plink1, d_geno, n_pad, maf1, r);
     return;
   }
-  d_summary.ensure((size_t)n * mp.sum_stride);
   const double* maf = d_maf_in;
   if (!d_geno) {
     d_counts.ensure(8 * (size_t)n);
@@ -456,6 +568,16 @@ void gwsem_model::run_marginals(const uint8_t* d_packed, int64_t pitch, const do
     maf = d_mafs.p;
   }
   MargProgram mpl = mp;
+  d_full.ensure((size_t)n * ex.full_stride);
+  mpl.full = d_full.p;
+  if (marg_mode == 3) {
+    // nothing is SNP-independent: every statistic of every SNP from marg_exact_kernel
+    launch_marg_exact(engine, ex, d_packed, pitch, n, n_src, layout.d_inc8, d_geno ? nullptr : d_counts.p, plink1, d_geno,
+                      n_pad, d_full.p);
+    launch_marg_fit(engine, fp, mpl, n, nullptr, maf, r);
+    return;
+  }
+  d_summary.ensure((size_t)n * mp.sum_stride);
   mpl.cs_sums = nullptr;
   if (!d_geno && mp.cs_nf > 0) {
     d_cs_sums.ensure((size_t)n * 2 * mp.cs_nf);
@@ -464,5 +586,8 @@ void gwsem_model::run_marginals(const uint8_t* d_packed, int64_t pitch, const do
   }
   launch_marg_stats(engine, mpl, d_packed, pitch, n, n_src, layout.d_inc8, d_geno ? nullptr : d_counts.p, plink1, d_geno,
                     n_pad, d_summary.p);
-  launch_marg_fit(engine, fp, mp, n, d_summary.p, maf, r);
+  // SNPs with a missing call: the people retained differ from the model's, so every statistic is recomputed over them
+  launch_marg_exact(engine, ex, d_packed, pitch, n, n_src, layout.d_inc8, d_geno ? nullptr : d_counts.p, plink1, d_geno, n_pad,
+                    d_full.p);
+  launch_marg_fit(engine, fp, mpl, n, d_summary.p, maf, r);
 }

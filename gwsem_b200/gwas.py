@@ -253,12 +253,6 @@ def GWAS(model, snpData, out="out.log", *dots, SNP=None, startFrom=1, rowFilter=
     if flat["fitfun"] != "WLS":
         if any(n_categories.get(m, 0) > 0 for m in flat["manifest"]):
             raise NotImplementedError("fitfun='ML' with ordinal items is not implemented (continuous items only)")
-    elif flat["continuous_type"] == "marginals":
-        snp_exo_item = "snp" in flat["exo_pred"] and len(flat["manifest"]) == 1
-        if not (flat["manifest"][0] == "snp" or snp_exo_item) or (model.gxe and not snp_exo_item):
-            raise NotImplementedError("WLS marginals is implemented for models whose first manifest variable is snp "
-                                      "(buildOneFac / buildOneFacRes / buildTwoFac, no gxe) and for buildItem with one "
-                                      "depVar and exogenous = TRUE (gxe allowed)")
     eng = _engine(device)
     with Source(snpData, method, src_rows) as src:
         gm = Model(eng, flat, data, n_categories)
@@ -273,7 +267,7 @@ def GWAS(model, snpData, out="out.log", *dots, SNP=None, startFrom=1, rowFilter=
             c_manifest = (C.c_char_p * flat["nm"])(*[n.encode() for n in flat["manifest"]])
             c_pairs = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1))
             job = _lib.Job(snp_arr.ctypes.data_as(C.POINTER(C.c_int32)) if snp_arr is not None else None,
-                           0 if snp_arr is None else len(snp_arr), int(startFrom), os.fsencode(out), c_names,
+                           -1 if snp_arr is None else len(snp_arr), int(startFrom), os.fsencode(out), c_names,
                            os.fsencode(ctx) if ctx else None,
                            c_pairs.ctypes.data_as(C.POINTER(C.c_int32)) if len(pairs) else None, len(pairs),
                            int(batch_snps), model.name.encode(), c_manifest)
@@ -281,7 +275,7 @@ def GWAS(model, snpData, out="out.log", *dots, SNP=None, startFrom=1, rowFilter=
             check(lib().gwsem_gwas_run(gm.h, src.h, C.byref(job), C.byref(written)))
             last = None
             if written.value:
-                last_idx = int(snp_arr[-1]) - 1 if snp_arr is not None else src.num_variants - 1
+                last_idx = int(snp_arr[-1]) - 1 if snp_arr is not None and len(snp_arr) else src.num_variants - 1
                 last = src.load_rows(eng, [last_idx], rowFilter)[0][0]
             counter = src.load_counter
         finally:

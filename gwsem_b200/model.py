@@ -249,7 +249,9 @@ def endogenousCovariatePaths(phenoData, covariates, depVar):  # R/model.R:459-47
 def postprocessModel(model, indicators, exogenous):  # R/model.R:482-512
     import warnings
     model = setupThresholds(model)
-    isInt = [c for c in model.data.columns if pd.api.types.is_integer_dtype(model.data[c].dtype)]
+    # R: typeof(x) == 'integer' -- true for integer vectors and for factors alike
+    isInt = [c for c in model.data.columns
+             if pd.api.types.is_integer_dtype(model.data[c].dtype) or _is_factor(model.data[c])]
     if not exogenous and not model.thresholds and model.fitfun == "WLS":
         if isInt:
             warnings.warn("Cumulants method prevented by integer observed columns: " +

@@ -8,10 +8,19 @@ import os
 import numpy as np
 
 
-def snp_shard(snps, rank, world):
-    """Contiguous slice of the 1-based SNP list `snps` owned by `rank` of `world` (sizes differ by <= 1)."""
+VBLOCK = 65536   # variants per .pgen vblock (src/pgenlib_misc.h:614-698): each one has its own file offset
+
+
+def snp_shard(snps, rank, world, align=VBLOCK):
+    """Contiguous slice of the 1-based SNP list `snps` owned by `rank` of `world` (sizes differ by <= 1).
+    When every rank gets at least two vblocks the cuts move to vblock boundaries, so that a shard of a
+    variable-width .pgen starts where the file has an offset for it (and never inside an LD-compressed run)."""
     snps = np.asarray(snps)
     bounds = np.linspace(0, len(snps), world + 1).round().astype(int)
+    if align and len(snps) >= 2 * align * world and np.all(np.diff(snps) == 1):
+        first = int(snps[0]) - 1                      # 0-based variant index of the first SNP
+        inner = ((first + bounds[1:-1] + align // 2) // align) * align - first
+        bounds[1:-1] = np.clip(inner, 0, len(snps))
     return snps[bounds[rank]:bounds[rank + 1]]
 
 
@@ -53,8 +62,21 @@ def GWAS_distributed(model, snpData, out="out.log", *, SNP=None, startFrom=1, ro
         from .gwas import GWAS
         local = int(os.environ.get("LOCAL_RANK", rank))
         run = lambda m, s, o, **kw: GWAS(m, s, o, device=local, **kw)
-    run(model, snpData, rank_log_path(out, rank), SNP=mine, rowFilter=rowFilter)
-    dist.barrier()
+    # `out` must be on a filesystem every rank sees (one node: any local path).  A rank that fails tells the
+    # others before anybody waits at a barrier, so the job ends with an error instead of hanging.
+    import torch
+    err = None
+    try:
+        run(model, snpData, rank_log_path(out, rank), SNP=mine, rowFilter=rowFilter)
+    except Exception as exc:   # noqa: BLE001 -- reported below on every rank
+        err = exc
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank))) if dist.get_backend() == "nccl" else torch.device("cpu")
+    failed = torch.tensor([0 if err is None else 1], dtype=torch.int32, device=dev)
+    dist.all_reduce(failed, op=dist.ReduceOp.SUM)
+    if int(failed.item()):
+        if err is not None:
+            raise err
+        raise RuntimeError(f"GWAS_distributed: {int(failed.item())} rank(s) failed; see their messages")
     rows = gather_logs(out, world) if rank == 0 else None
     dist.barrier()
     return rows

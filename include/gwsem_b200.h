@@ -153,9 +153,9 @@ int gwsem_fit_rows_device(gwsem_model* m, const double* d_geno, int n_snps, cons
 
 /* -------------------------------------------------------------- the whole loop (GWAS()) */
 typedef struct {
-  const int32_t* snp;         /* 1-based SNP numbers (the SNP= argument) or NULL */
-  int32_t n_snp;
-  int32_t start_from;         /* 1-based, used when snp == NULL */
+  const int32_t* snp;         /* 1-based SNP numbers (the SNP= argument) */
+  int32_t n_snp;              /* length of snp; 0 = no SNP at all (header-only log); -1 = every SNP from start_from */
+  int32_t start_from;         /* 1-based, used when n_snp == -1 */
   const char* out_path;       /* checkpoint log */
   const char* const* par_names;     /* n_params labels for the header */
   const char* context_path;   /* .pvar / .bim (mxComputeLoadContext), or NULL for bgen */

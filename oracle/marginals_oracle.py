@@ -390,7 +390,14 @@ def fit_snp_marginals(flat, pheno_cols, snp, n_cats):
     out = dict(est=np.array(flat["par_start"], float), vcov=np.full((P, P), np.nan), status="NA", catch1="",
                fit=np.nan, n=0, iterations=0)
     names = flat["manifest"]
-    cols = [snp if m == "snp" else pheno_cols[m] for m in names]
+    def manifest_column(m):   # `snp_<moderator>` as a manifest variable: the gxe algebra column (R/model.R:427-434)
+        if m == "snp":
+            return snp
+        if m.startswith("snp_") and m[4:] in flat["gxe"] and m not in pheno_cols:
+            with np.errstate(invalid="ignore"):
+                return snp * pheno_cols[m[4:]]
+        return pheno_cols[m]
+    cols = [manifest_column(m) for m in names]
     # buildItem with an ordered phenotype: `snp` itself is an exogenous predictor (R/model.R:560-576)
     def exo_column(c):   # `snp_<moderator>`: the gxe product as a definition variable (R/model.R:427-434)
         if c == "snp":

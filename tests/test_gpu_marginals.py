@@ -91,29 +91,79 @@ def test_marginals_matches_oracle(engine, case):
     gm.close()
 
 
-def test_marginals_with_missing_calls(engine):
-    """Missing calls drop people from every statistic (naAction='omit').  The device path takes the
-    item-side estimates from the full sample to the retained subset with one Newton step (exact
-    full-sample information, outer-product down-date) instead of re-estimating; at 1% missingness
-    that agrees with the oracle's full re-estimation to well under the SE-level tolerance."""
+@pytest.mark.parametrize("rate,n", [(0.01, 4000), (0.04, 600), (0.3, 900)])
+def test_marginals_with_missing_calls(engine, rate, n):
+    """Missing calls drop people from every statistic of that SNP (naAction='omit', R/model.R:435-436):
+    marg_exact_kernel re-estimates every stage-1 / stage-2 quantity and every score product over the
+    retained people, so the north-star tolerances hold at any missing rate (1 %, the 4 % of the
+    reference's example.bed, 30 %)."""
     import marginals_oracle as mo
     from gwsem_b200.engine import Model
-    n = 4000
-    ph = cohort(n, 21, 3, 3, [True, True, True])
+    ph = cohort(n, 21, 3, 3, [True, False, True])
     items = ["i1", "i2", "i3"]
     model = buildOneFac(ph, items, covariates=["pc1", "pc2", "pc3"])
     flat = flatten(model)
     data, ncat = model_columns(model)
-    codes = synth.simulate_hardcalls(n, 5, seed=9, maf_range=(0.2, 0.5), missing_rate=0.01)
+    codes = synth.simulate_hardcalls(n, 5, seed=9, maf_range=(0.2, 0.5), missing_rate=rate)
+    codes[3] = np.where(codes[3] == 3, 0, codes[3])          # one call-complete SNP in the same batch
     geno = np.array([0.0, 1.0, 2.0, np.nan])[codes]
     want = [mo.fit_snp_marginals(flat, data, g, ncat) for g in geno]
     gm = Model(engine, flat, data, ncat)
     res = gm.fit_2bit(synth.pack_2bit(codes))
-    for i, w in enumerate(want):
-        assert res.n_used[i] == w["n"] and res.catch_code[i] == 0 and res.status[i] == 0
-        se = np.sqrt(np.diag(w["vcov"]))
-        assert np.all(np.abs(res.est[i] - w["est"]) <= 1e-2 * np.maximum(np.abs(w["est"]), se))  # second-order terms, n = 4000
-        assert np.allclose(np.sqrt(np.diag(res.vcov[i])), se, rtol=3e-3)
+    compare(res, want, flat["par_names"])
+    bed = np.array([3, 2, 0, 1], np.uint8)[codes]
+    res2 = gm.fit_2bit(synth.pack_2bit(bed), plink1=True)
+    assert np.array_equal(res2.est.view(np.uint64), res.est.view(np.uint64))
+    # a row does not depend on its neighbours: any sub-batch, any order, the same bits
+    res3 = gm.fit_2bit(synth.pack_2bit(codes[[4, 0]]))
+    assert np.array_equal(res3.est.view(np.uint64), res.est[[4, 0]].view(np.uint64))
+    gm.close()
+
+
+def test_items_with_exogenous_snp_match_oracle(engine):
+    """buildItem with several depVars, one of them ordinal (tests/testthat/test-model.R:86): exogenous defaults
+    to TRUE, snp is a definition variable of every item and of their residual correlation."""
+    import marginals_oracle as mo
+    from gwsem_b200.engine import Model
+    from gwsem_b200.model import buildItem
+    n = 1200
+    ph = cohort(n, 31, 3, 2, [True, False, True])
+    model = buildItem(ph, ["i1", "i2", "i3"], covariates=["pc1", "pc2"])
+    flat = flatten(model)
+    assert flat["exo_pred"][0] == "snp" and flat["manifest"] == ["i1", "i2", "i3"]
+    data, ncat = model_columns(model)
+    codes = synth.simulate_hardcalls(n, 5, seed=3, maf_range=(0.2, 0.5))
+    codes[1, ::9] = 3
+    codes[2] = 0
+    geno = np.array([0.0, 1.0, 2.0, np.nan])[codes]
+    want = [mo.fit_snp_marginals(flat, data, g, ncat) for g in geno]
+    assert [bool(w["catch1"]) for w in want] == [False, False, True, False, False]
+    gm = Model(engine, flat, data, ncat)
+    res = gm.fit_2bit(synth.pack_2bit(codes))
+    compare(res, want, flat["par_names"])
+    gm.close()
+
+
+def test_gxe_product_as_manifest_variable_matches_oracle(engine):
+    """A factor model with ordinal items and a gxe term: `snp_<moderator>` is a manifest variable filled per SNP
+    with snp * moderator (R/model.R:427-434, tests/testthat/test-gxe.R:67-77)."""
+    import marginals_oracle as mo
+    from gwsem_b200.engine import Model
+    n = 1500
+    ph = cohort(n, 41, 3, 1, [True, False, True])
+    ph["mod"] = np.random.default_rng(2).normal(size=n) + 1.0
+    model = buildOneFac(ph, ["i1", "i2", "i3"], covariates=["pc1"], gxe="mod")
+    flat = flatten(model)
+    assert flat["manifest"] == ["snp", "i1", "i2", "i3", "snp_mod"]
+    data, ncat = model_columns(model)
+    codes = synth.simulate_hardcalls(n, 4, seed=6, maf_range=(0.25, 0.5))
+    codes[1, ::13] = 3
+    geno = np.array([0.0, 1.0, 2.0, np.nan])[codes]
+    want = [mo.fit_snp_marginals(flat, data, g, ncat) for g in geno]
+    assert all(w["status"] == "OK" for w in want)
+    gm = Model(engine, flat, data, ncat)
+    res = gm.fit_2bit(synth.pack_2bit(codes))
+    compare(res, want, flat["par_names"])
     gm.close()
 
 
@@ -147,11 +197,8 @@ def test_gwas_ordinal_one_factor_on_fixtures(engine, tmp_path):
                 continue
             assert row["statusCode"] == w["status"]
             se = np.sqrt(np.diag(w["vcov"]))
-            # Missing calls use a one-step down-date of the item-side estimates: exact
-            # to first order in n_missing / n.  example.bed has ~4% missing calls on 500 people, far
-            # outside the regime that is first-order small, so only SE-level agreement is asserted there.
             n_miss = int(np.isnan(gold["geno"][snp]).sum())
-            est_tol, var_tol = (1e-4, 2e-3) if n_miss == 0 else (0.5, 0.2)
+            est_tol, var_tol = 1e-4, 2e-3     # with or without missing calls (example.bed: ~4 % of 500 people)
             for k, nme in enumerate(flat["par_names"]):
                 assert abs(row[nme] - w["est"][k]) <= est_tol * max(abs(w["est"][k]), se[k]), (fname, snp, nme, n_miss)
                 assert row[f"V{nme}:{nme}"] == pytest.approx(w["vcov"][k, k], rel=var_tol), (fname, snp, nme, n_miss)
