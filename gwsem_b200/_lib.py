@@ -51,6 +51,7 @@ SYMBOLS = {
     "gwsem_engine_launch_count": (C.c_int64, [C.c_void_p]),
     "gwsem_engine_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "gwsem_engine_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "gwsem_engine_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "gwsem_source_open": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
     "gwsem_source_close": (None, [C.c_void_p]),
     "gwsem_source_num_variants": (C.c_int, [C.c_void_p]),

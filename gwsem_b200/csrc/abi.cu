@@ -1,4 +1,5 @@
 // extern "C" surface of libgwsem_b200.so (include/gwsem_b200.h).
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 
@@ -41,6 +42,24 @@ void fail(const char* fmt, ...) {
 
 using namespace gwsem;
 
+// FP64 FMA issue-rate probe (the roofline of the statistics kernels of the WLS marginals path): NACC independent
+// dependent chains of DFMAs per thread, no memory traffic.
+template <int NACC>
+__global__ void fp64_peak_kernel(double* out, int iters, double w) {
+  double acc[NACC];
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) acc[k] = k + threadIdx.x;
+  const double h = 1.0 + threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = fma(w, h, acc[k]);
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) s += acc[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 void gwsem_engine::prof_begin(int fam) {
   if (!profiling) return;
   std::pair<cudaEvent_t, cudaEvent_t> ev;
@@ -67,7 +86,7 @@ int gwsem_engine_profile(gwsem_engine* e, int enable) {
 }
 
 // Collects (and clears) the per-family launch statistics gathered since the last call:
-// launches[f], total_ms[f] for f in {class_sums, count_missing, fit, decode}.  Synchronises.
+// launches[f], total_ms[f] for the eight families of include/gwsem_b200.h.  Synchronises.
 int gwsem_engine_profile_read(gwsem_engine* e, int64_t* launches, double* total_ms) {
   return guarded([&] {
     GW_CUDA(cudaSetDevice(e->device));
@@ -83,6 +102,40 @@ int gwsem_engine_profile_read(gwsem_engine* e, int64_t* launches, double* total_
       }
       e->prof_events[f].clear();
     }
+  });
+}
+
+// Best of a few launch shapes of the DFMA probe, in TFLOP/s (2 flops per DFMA), timed with CUDA events on the
+// engine's stream at whatever clocks the GPU runs at right now.
+int gwsem_engine_fp64_peak(gwsem_engine* e, double* tflops) {
+  return guarded([&] {
+    GW_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    constexpr int kAcc = 16, kIters = 40000;
+    DeviceBuffer<double> out;
+    out.ensure((size_t)e->sm_count * 4 * 1024);
+    cudaEvent_t a, b;
+    GW_CUDA(cudaEventCreate(&a));
+    GW_CUDA(cudaEventCreate(&b));
+    double best = 0.0;
+    for (int warps : {8, 16, 32}) {
+      for (int rep = 0; rep < 3; ++rep) {
+        const int grid = e->sm_count * (warps > 16 ? 2 : 1), block = 32 * (warps > 16 ? warps / 2 : warps);
+        fp64_peak_kernel<kAcc><<<grid, block, 0, st>>>(out.p, rep == 0 ? 200 : kIters, 1.0);
+        if (rep == 0) continue;
+        GW_CUDA(cudaEventRecord(a, st));
+        fp64_peak_kernel<kAcc><<<grid, block, 0, st>>>(out.p, kIters, 1.0);
+        GW_CUDA(cudaEventRecord(b, st));
+        GW_CUDA(cudaEventSynchronize(b));
+        float ms = 0;
+        GW_CUDA(cudaEventElapsedTime(&ms, a, b));
+        const double flops = 2.0 * (double)grid * block * kIters * kAcc;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+      }
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *tflops = best;
   });
 }
 

@@ -37,7 +37,7 @@ __device__ __forceinline__ double ndiff(double a1, double a0) {
 
 // shared-memory layout (doubles)
 struct ExLayout {
-  int th, rho_ok, acc, g, x, y, st, sc, ps, etab, total;
+  int th, rho_ok, acc, part, g, x, y, st, sc, ps, etab, gtab, total;
 };
 __host__ __device__ inline int ex_acc_entries(const ExactProgram& ex) {
   int w = 1 + ex.K, hb = 0;
@@ -63,6 +63,7 @@ __host__ __device__ inline ExLayout ex_layout(const ExactProgram& ex) {
   l.th = take(ex.nt);
   l.rho_ok = take(ex.npairs > 0 ? ex.npairs : 1);
   l.acc = take(ex_acc_entries(ex));
+  l.part = take(1024);   // partial sums of the chunked accumulations (entries x chunks <= 2 x threads)
   l.g = take(T);
   l.x = take(T * ex.Kp);
   l.y = take(T * ex.p);
@@ -70,10 +71,20 @@ __host__ __device__ inline ExLayout ex_layout(const ExactProgram& ex) {
   const int w = 1 + ex.K + ex.p;
   l.sc = take(T * (ex.nt > w ? ex.nt : w));
   l.ps = take(T * (ex.npairs > 0 ? ex.npairs : 1) * 4);
-  l.etab = take((ex.nt * (ex.nt + 1) / 2 + 1) / 2 + 1);   // int16 pairs (a, b) of the B entries, packed as int32
+  l.etab = take((ex_acc_entries(ex) + 1) / 2 + 1);   // int32 entry tables (Hessian entries; then B entries and A21 entries)
+  l.gtab = take((ex.npairs > 0 ? ex.npairs : 1) * (1 + 3 * 32));
   l.total = o;
   return l;
 }
+
+// The small lookup tables of the program, copied to shared memory once per CTA: indexed dynamically in every inner
+// loop, they would otherwise live in per-thread local memory (kernel parameters and local arrays alike), which
+// the shared-memory carve-out leaves almost no L1 for.
+struct ExShared {
+  int voff[kExMaxVars + 1], ncat[kExMaxVars], nx[kExMaxVars], xidx[kExMaxVars][kExMaxCov];
+  int ord_of[kExMaxVars], hoff[kExMaxVars + 1], cont_of[kExMaxVars], n_ord, n_cont;
+  unsigned char powner[kExMaxVars * (kExMaxVars - 1) / 2];
+};
 
 struct Pair { int a, b; };   // a > b
 __device__ __forceinline__ Pair pair_of(int k, int p) {
@@ -85,7 +96,7 @@ __device__ __forceinline__ Pair pair_of(int k, int p) {
 // Standardised quantities of variable j for one person at the current theta:
 //   continuous: s.a = u = e / sd, s.b = e ;  ordinal: s.a = z1, s.b = z0 (sentinels +-12 at the open ends)
 struct VState { double a, b; };
-__device__ __forceinline__ VState var_state(const ExactProgram& ex, const double* th, int j, const double* xr, double yv) {
+__device__ __forceinline__ VState var_state(const ExShared& ex, const double* th, int j, const double* xr, double yv) {
   const int o = ex.voff[j], nx = ex.nx[j];
   VState s;
   if (ex.ncat[j] == 0) {
@@ -106,11 +117,13 @@ __device__ __forceinline__ VState var_state(const ExactProgram& ex, const double
 // Rectangle probability of the standard bivariate normal and what the polychoric score needs:
 //   P = Phi2-rectangle([a0,a1] x [b0,b1]; rho), Dn = sum of +-phi2 at the finite corners, dDn = d Dn / d rho
 struct Poly { double P, Dn, dDn; };
+constexpr int kGlMax = 32, kGlStride = 1 + 3 * kGlMax;
+// tb: {nodes, then per node sin t, 1 / (2 cos^2 t), weight * asin(rho) / 2} (marg_exact_kernel's fill_gl_tables)
 __device__ Poly polychoric_terms(double a1, double a0, double b1, double b0, bool au, bool al, bool bu, bool bl,
-                                 double rho, const double* glx, const double* glw, int gln) {
+                                 double rho, const double* tb) {
   Poly r;
   const double s2 = 1.0 - rho * rho, is2 = 1.0 / s2, nrm = kInv2Pi * rsqrt(s2);
-  const double asr = asin(rho);
+  const int gln = (int)tb[0];
   double integral = 0.0;
   r.Dn = 0.0;
   r.dDn = 0.0;
@@ -122,21 +135,16 @@ __device__ Poly polychoric_terms(double a1, double a0, double b1, double b0, boo
     for (int cj = 0; cj < 2; ++cj) {
       if (!hf[ci] || !kf[cj]) continue;   // a corner on an open bound: no density, no correlation-dependent mass
       const double h = hs[ci], k = ks[cj], sgn = (ci == cj) ? 1.0 : -1.0;
-      const double hk = h * k, hh = h * h + k * k;
+      const double hk2 = 2.0 * h * k, hh = h * h + k * k;
       double acc = 0.0;
-      for (int i = 0; i < gln; ++i) {
-        const double t = 0.5 * asr * (glx[i] + 1.0);
-        double st, ct;
-        sincos(t, &st, &ct);
-        acc += glw[i] * exp(-(hh - 2.0 * hk * st) / (2.0 * ct * ct));
-      }
+      for (int i = 0; i < gln; ++i) acc += tb[3 + 3 * i] * exp((hk2 * tb[1 + 3 * i] - hh) * tb[2 + 3 * i]);
       integral += sgn * acc;
-      const double q = hh - 2.0 * rho * hk;
+      const double q = hh - rho * hk2;
       const double dens = nrm * exp(-0.5 * q * is2);
       r.Dn += sgn * dens;
-      r.dDn += sgn * dens * (rho * is2 + (hk * s2 - rho * q) * is2 * is2);
+      r.dDn += sgn * dens * (rho * is2 + (0.5 * hk2 * s2 - rho * q) * is2 * is2);
     }
-  r.P = ndiff(a1, a0) * ndiff(b1, b0) + 0.5 * asr * integral * kInv2Pi;
+  r.P = ndiff(a1, a0) * ndiff(b1, b0) + integral * kInv2Pi;
   if (!(r.P > 1e-300)) r.P = 1e-300;
   return r;
 }
@@ -149,8 +157,8 @@ struct PairEval {
 
 // One person's contribution to pair (a > b); sa / sb from var_state.  need_sides: also the derivatives with
 // respect to the two variables' standardised quantities (phase D only).
-__device__ PairEval pair_eval(const ExactProgram& ex, int a, int b, VState sa, VState sb, int ca, int cb, double rho,
-                              const double* gl, bool need_sides) {
+__device__ PairEval pair_eval(const ExShared& ex, int a, int b, VState sa, VState sb, int ca, int cb, double rho,
+                              const double* gl /* this pair's node table */, bool need_sides) {
   PairEval r;
   r.a0 = r.a1 = r.b0 = r.b1 = 0.0;
   const bool oa = ex.ncat[a] > 0, ob = ex.ncat[b] > 0;
@@ -189,12 +197,7 @@ __device__ PairEval pair_eval(const ExactProgram& ex, int a, int b, VState sa, V
   // polychoric
   const int Ca = ex.ncat[a], Cb = ex.ncat[b];
   const bool au = ca < Ca - 1, al = ca > 0, bu = cb < Cb - 1, bl = cb > 0;
-  const double ar = fabs(rho);
-  const int rule = ar < 0.35 ? 0 : (ar < 0.75 ? 1 : 2);
-  int off = 0;
-  for (int k = 0; k < rule; ++k) off += 2 * ex.gl_n[k];
-  const int gln = ex.gl_n[rule];
-  const Poly t = polychoric_terms(sa.a, sa.b, sb.a, sb.b, au, al, bu, bl, rho, gl + off, gl + off + gln, gln);
+  const Poly t = polychoric_terms(sa.a, sa.b, sb.a, sb.b, au, al, bu, bl, rho, gl);
   const double ip = 1.0 / t.P;
   r.psi = t.Dn * ip;
   r.dpsi = t.dDn * ip - r.psi * r.psi;
@@ -212,7 +215,7 @@ __device__ PairEval pair_eval(const ExactProgram& ex, int a, int b, VState sa, V
 // d loglik2_i / d theta_c for stage-1 parameter `l` (local index in variable v's block), from the two staged
 // scalars of that side (already multiplied by the pair's score): ordinal (s0 = psi d/dz1, s1 = psi d/dz0),
 // continuous (s0 = psi * (-d/du / sd), s1 = psi * (-1/(2 var) - d/du * u / (2 var))).
-__device__ __forceinline__ double side_entry(const ExactProgram& ex, int v, int l, double s0, double s1, double yv,
+__device__ __forceinline__ double side_entry(const ExShared& ex, int v, int l, double s0, double s1, double yv,
                                              const double* xr) {
   const int nx = ex.nx[v];
   if (ex.ncat[v] > 0) {
@@ -257,13 +260,39 @@ __global__ void marg_exact_kernel(ExactProgram ex, const uint8_t* __restrict__ r
                                   const double* __restrict__ geno, int n_pad, double* __restrict__ records) {
   extern __shared__ __align__(16) double sm[];
   __shared__ int flag_sh, nlive_sh;
-  const int snp = blockIdx.x, tid = threadIdx.x, T = ex.T, p = ex.p, K = ex.K, Kp = ex.Kp, nt = ex.nt, np = ex.npairs;
+  __shared__ ExShared S;
+  const int snp = blockIdx.x, tid = threadIdx.x, NT = blockDim.x, T = ex.T, pt = tid % T, sub = tid / T, R = NT / T, p = ex.p, K = ex.K, Kp = ex.Kp, nt = ex.nt, np = ex.npairs;
   double* rec = records + (int64_t)snp * ex.full_stride;
   // only_missing: SNPs without a missing call keep the fast path's record
   if (ex.only_missing && counts && counts[8 * (int64_t)snp + 2] == 0) {
     if (tid == 0) rec[0] = -1.0;
     return;
   }
+  if (tid == 0) {
+    S.n_ord = S.n_cont = 0;
+    S.hoff[0] = 0;
+    for (int j = 0; j <= ex.p; ++j) S.voff[j] = ex.voff[j];
+    for (int j = 0; j < ex.p; ++j) {
+      S.ncat[j] = ex.ncat[j];
+      S.nx[j] = ex.nx[j];
+      for (int m = 0; m < ex.nx[j]; ++m) S.xidx[j][m] = ex.xidx[j][m];
+      if (ex.ncat[j] == 0) S.cont_of[S.n_cont++] = j;
+      else {
+        const int d = ex.voff[j + 1] - ex.voff[j];
+        S.ord_of[S.n_ord] = j;
+        S.hoff[S.n_ord + 1] = S.hoff[S.n_ord] + d + d * d;
+        ++S.n_ord;
+      }
+    }
+    int n_poly = 0, n_other = 0;
+    const int R0 = blockDim.x / ex.T;
+    for (int k2 = 0, b2 = 0; b2 < ex.p; ++b2)
+      for (int a2 = b2 + 1; a2 < ex.p; ++a2, ++k2) {
+        const bool poly = ex.ncat[a2] > 0 && ex.ncat[b2] > 0;
+        S.powner[k2] = (unsigned char)((poly ? n_poly++ : n_other++) % R0);
+      }
+  }
+  __syncthreads();
   const ExLayout L = ex_layout(ex);
   double *th = sm + L.th, *rho_ok = sm + L.rho_ok, *acc = sm + L.acc, *gs = sm + L.g, *xs = sm + L.x, *ys = sm + L.y;
   double *st = sm + L.st, *sc = sm + L.sc, *ps = sm + L.ps;
@@ -274,7 +303,8 @@ __global__ void marg_exact_kernel(ExactProgram ex, const uint8_t* __restrict__ r
 
   // stage one tile of people: genotype, covariates, variables (NaN genotype = not retained)
   auto load_tile = [&](int t0) {
-    const int i = t0 + tid;
+    if (sub == 0) {
+    const int i = t0 + pt;
     double g = nan;
     if (i < n_src && inc8[i]) {
       if (grow) g = grow[i];
@@ -284,7 +314,7 @@ __global__ void marg_exact_kernel(ExactProgram ex, const uint8_t* __restrict__ r
         if (code != 3u) g = (double)code;
       }
     }
-    gs[tid] = g;
+    gs[pt] = g;
     const bool live = g == g;
     for (int k = 0; k < K; ++k) {
       double x = 0.0;
@@ -292,7 +322,7 @@ __global__ void marg_exact_kernel(ExactProgram ex, const uint8_t* __restrict__ r
         const int kd = ex.xkind[k];
         x = kd == 1 ? g : (kd == 2 ? g * ex.X[(int64_t)i * Kp + k] : ex.X[(int64_t)i * Kp + k]);
       }
-      xs[tid * Kp + k] = x;
+      xs[pt * Kp + k] = x;
     }
     for (int j = 0; j < p; ++j) {
       double y = 0.0;
@@ -300,38 +330,73 @@ __global__ void marg_exact_kernel(ExactProgram ex, const uint8_t* __restrict__ r
         const int kd = ex.vkind[j];
         y = kd == 2 ? g : (kd == 3 ? g * ex.V[(int64_t)i * p + j] : ex.V[(int64_t)i * p + j]);
       }
-      ys[tid * p + j] = y;
+      ys[pt * p + j] = y;
     }
+    }
+    __syncthreads();
   };
   auto zero_acc = [&]() {
-    for (int e = tid; e < n_acc; e += T) acc[e] = 0.0;
+    for (int e = tid; e < n_acc; e += NT) acc[e] = 0.0;
+  };
+  // acc[dst(e)] += sum over the tile's people of f(e, t) for e < n_e: when there are fewer entries than threads the
+  // people are split into chunks (one thread per entry and chunk), partial sums combined in chunk order
+  double* part = sm + L.part;
+  auto chunked = [&](int n_e, auto f, auto dst) {
+    int CH = n_e > 0 ? NT / n_e : 1;
+    if (CH < 1) CH = 1;
+    if (CH > 8) CH = 8;
+    if (n_e * CH > 1024) CH = 1;
+    if (CH == 1) {
+      for (int e = tid; e < n_e; e += NT) {
+        double v = 0.0;
+        for (int t = 0; t < T; ++t) v += f(e, t);
+        dst(e, v);
+      }
+      return;
+    }
+    for (int w = tid; w < n_e * CH; w += NT) {
+      const int e = w % n_e, c = w / n_e;
+      double v = 0.0;
+      for (int t = c * T / CH; t < (c + 1) * T / CH; ++t) v += f(e, t);
+      part[w] = v;
+    }
+    __syncthreads();
+    for (int e = tid; e < n_e; e += NT) {
+      double v = 0.0;
+      for (int c = 0; c < CH; ++c) v += part[c * n_e + e];
+      dst(e, v);
+    }
   };
   auto finish = [&](int code, int var) {
     if (tid == 0) { rec[1] = (double)code; rec[2] = (double)var; }
   };
 
-  for (int e = tid; e < nt; e += T) th[e] = ex.theta0[e];
-  for (int e = tid; e < ex.full_stride; e += T) rec[e] = 0.0;
+  long long clk0 = clock64();
+  double diag[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // cycles of phases A..D, Newton iterations of B and C (development aid)
+  auto lap = [&](int slot) { const long long c = clock64(); diag[slot] += (double)(c - clk0); clk0 = c; };
+  for (int e = tid; e < nt; e += NT) th[e] = ex.theta0[e];
+  for (int e = tid; e < ex.full_stride; e += NT) rec[e] = 0.0;
   if (tid == 0) { flag_sh = 0; nlive_sh = 0; }
   zero_acc();
   __syncthreads();
 
   // ---------------- phase A: Gram of w = [1, x_1..x_K, continuous variables] over the retained people
-  int cont_of[kExMaxVars], n_cont = 0;
-  for (int j = 0; j < p; ++j)
-    if (ex.ncat[j] == 0) cont_of[n_cont++] = j;
+  const int n_cont = S.n_cont;
+  const int* cont_of = S.cont_of;
   const int W = 1 + K + n_cont, nW = W * (W + 1) / 2;
   int n_live_local = 0;
   for (int t0 = 0; t0 < n_src; t0 += T) {
     load_tile(t0);
-    const bool live = gs[tid] == gs[tid];
-    n_live_local += live;
-    double* w = sc + tid * W;
-    w[0] = live ? 1.0 : 0.0;
-    for (int k = 0; k < K; ++k) w[1 + k] = xs[tid * Kp + k];
-    for (int c = 0; c < n_cont; ++c) w[1 + K + c] = ys[tid * p + cont_of[c]];
+    if (sub == 0) {
+      const bool live = gs[pt] == gs[pt];
+      n_live_local += live;
+      double* w = sc + pt * W;
+      w[0] = live ? 1.0 : 0.0;
+      for (int k = 0; k < K; ++k) w[1 + k] = xs[pt * Kp + k];
+      for (int c = 0; c < n_cont; ++c) w[1 + K + c] = ys[pt * p + cont_of[c]];
+    }
     __syncthreads();
-    for (int e = tid; e < nW; e += T) {
+    for (int e = tid; e < nW; e += NT) {
       int a = 0, rem = e;
       while (rem >= W - a) { rem -= W - a; ++a; }
       const int b = a + rem;
@@ -372,16 +437,17 @@ __global__ void marg_exact_kernel(ExactProgram ex, const uint8_t* __restrict__ r
   if (flag_sh) return;
   // OLS of each continuous variable (thread c solves variable cont_of[c]); scratch after the Gram in acc
   if (tid < n_cont) {
-    const int j = cont_of[tid], d = 1 + ex.nx[j];
-    double H[(kExMaxCov + 1) * (kExMaxCov + 1)], gv[kExMaxCov + 1];
-    auto col = [&](int l) { return l == 0 ? 0 : 1 + ex.xidx[j][l - 1]; };
+    const int j = cont_of[tid], d = 1 + S.nx[j];
+    double* H = sc + tid * ((kExMaxCov + 1) * (kExMaxCov + 2));   // scratch: the tile buffers are idle here
+    double* gv = H + (kExMaxCov + 1) * (kExMaxCov + 1);
+    auto col = [&](int l) { return l == 0 ? 0 : 1 + S.xidx[j][l - 1]; };
     for (int a = 0; a < d; ++a) {
       gv[a] = gram(col(a), 1 + K + tid);
       for (int b = 0; b < d; ++b) H[a * d + b] = gram(col(a), col(b));
     }
     if (!thread_chol_solve(H, gv, d)) atomicExch(&flag_sh, 2);
-    for (int a = 0; a < d; ++a) th[ex.voff[j] + a] = gv[a];
-    th[ex.voff[j] + d] = 1.0;   // variance: second pass
+    for (int a = 0; a < d; ++a) th[S.voff[j] + a] = gv[a];
+    th[S.voff[j] + d] = 1.0;   // variance: second pass
   }
   __syncthreads();
   if (flag_sh) { finish(GWSEM_CATCH_ACOV_NOT_PD, -1); return; }
@@ -390,17 +456,17 @@ __global__ void marg_exact_kernel(ExactProgram ex, const uint8_t* __restrict__ r
   __syncthreads();
   for (int t0 = 0; t0 < n_src; t0 += T) {
     load_tile(t0);
-    const bool live = gs[tid] == gs[tid];
-    for (int c = 0; c < n_cont; ++c) {
+    const bool live = gs[pt] == gs[pt];
+    for (int c = sub; c < n_cont; c += R) {
       double e2 = 0.0;
       if (live) {
-        const VState s = var_state(ex, th, cont_of[c], xs + tid * Kp, ys[tid * p + cont_of[c]]);
+        const VState s = var_state(S, th, cont_of[c], xs + pt * Kp, ys[pt * p + cont_of[c]]);
         e2 = s.b * s.b;
       }
-      sc[tid * n_cont + c] = e2;
+      sc[pt * n_cont + c] = e2;
     }
     __syncthreads();
-    for (int e = tid; e < n_cont; e += T) {
+    for (int e = tid; e < n_cont; e += NT) {
       double v = 0.0;
       for (int t = 0; t < T; ++t) v += sc[t * n_cont + e];
       acc[e] += v;
@@ -410,114 +476,164 @@ __global__ void marg_exact_kernel(ExactProgram ex, const uint8_t* __restrict__ r
   if (tid < n_cont) {
     const int j = cont_of[tid];
     const double var = acc[tid] / dn;
-    th[ex.voff[j] + 1 + ex.nx[j]] = var;
+    th[S.voff[j] + 1 + S.nx[j]] = var;
     if (!(var > 0.0)) atomicExch(&flag_sh, 2);
   }
   __syncthreads();
   if (flag_sh) { finish(GWSEM_CATCH_ACOV_NOT_PD, -1); return; }
 
+  lap(0);
   // ---------------- phase B: ordered probit of every ordinal variable, Newton with the exact Hessian
-  int ord_of[kExMaxVars], hoff[kExMaxVars + 1], n_ord = 0;
-  hoff[0] = 0;
-  for (int j = 0; j < p; ++j)
-    if (ex.ncat[j] > 0) {
-      const int d = ex.voff[j + 1] - ex.voff[j];
-      ord_of[n_ord] = j;
-      hoff[n_ord + 1] = hoff[n_ord] + d + d * d;
-      ++n_ord;
+  const int n_ord = S.n_ord;
+  const int *ord_of = S.ord_of, *hoff = S.hoff;
+  // entries of every ordinal variable's gradient and Hessian (lower triangle): (variable, a, b), b = 255 for the gradient
+  int* htab = reinterpret_cast<int*>(sm + L.etab);
+  int n_h = 0;
+  for (int o = 0; o < n_ord; ++o) {
+    const int d = S.voff[ord_of[o] + 1] - S.voff[ord_of[o]];
+    n_h += d + d * (d + 1) / 2;
+  }
+  for (int e = tid; e < n_h; e += NT) {
+    int o = 0, le = e;
+    for (;; ++o) {
+      const int d = S.voff[ord_of[o] + 1] - S.voff[ord_of[o]], cnt = d + d * (d + 1) / 2;
+      if (le < cnt) break;
+      le -= cnt;
     }
+    const int d = S.voff[ord_of[o] + 1] - S.voff[ord_of[o]];
+    int a2, b2;
+    if (le < d) { a2 = le; b2 = 255; }
+    else {
+      le -= d;
+      a2 = 0;
+      while (le > a2) { le -= a2 + 1; ++a2; }
+      b2 = le;
+    }
+    htab[e] = (o << 16) | (a2 << 8) | b2;
+  }
+  __syncthreads();
   for (int iter = 0; iter < 100 && n_ord > 0; ++iter) {
     zero_acc();
     __syncthreads();
     for (int t0 = 0; t0 < n_src; t0 += T) {
       load_tile(t0);
-      const bool live = gs[tid] == gs[tid];
-      for (int o = 0; o < n_ord; ++o) {
-        const int j = ord_of[o], C = ex.ncat[j];
+      const bool live = gs[pt] == gs[pt];
+      for (int o = sub; o < n_ord; o += R) {
+        const int j = ord_of[o], C = S.ncat[j];
         double r1 = 0.0, r0 = 0.0, D1 = 0.0, D0 = 0.0;
         if (live) {
-          const int c = (int)ys[tid * p + j];
-          const VState s = var_state(ex, th, j, xs + tid * Kp, ys[tid * p + j]);
+          const int c = (int)ys[pt * p + j];
+          const VState s = var_state(S, th, j, xs + pt * Kp, ys[pt * p + j]);
           double pi = ndiff(s.a, s.b);
           if (!(pi > 1e-300)) pi = 1e-300;
           const double p1 = c < C - 1 ? nphi(s.a) : 0.0, p0 = c > 0 ? nphi(s.b) : 0.0;
           r1 = p1 / pi; r0 = p0 / pi; D1 = -s.a * r1; D0 = -s.b * r0;
         }
-        double* q = st + (tid * p + o) * 4;
+        double* q = st + (pt * p + o) * 4;
         q[0] = r1; q[1] = r0; q[2] = D1; q[3] = D0;
       }
       __syncthreads();
-      for (int e = tid; e < hoff[n_ord]; e += T) {
-        int o = 0;
-        while (e >= hoff[o + 1]) ++o;
-        const int j = ord_of[o], d = ex.voff[j + 1] - ex.voff[j], C1 = ex.ncat[j] - 1, le = e - hoff[o];
-        const bool is_g = le < d;
-        const int a = is_g ? le : (le - d) / d, b = is_g ? 0 : (le - d) % d;
-        const int xa = a >= C1 ? ex.xidx[j][a - C1] : 0, xb = b >= C1 ? ex.xidx[j][b - C1] : 0;
-        double v = 0.0;
-        for (int t = 0; t < T; ++t) {
-          const double* q = st + (t * p + o) * 4;
-          const int c = (int)ys[t * p + j];
-          const double j1a = a < C1 ? (a == c ? 1.0 : 0.0) : -xs[t * Kp + xa];
-          const double j0a = a < C1 ? (a == c - 1 ? 1.0 : 0.0) : -xs[t * Kp + xa];
-          const double ga = q[0] * j1a - q[1] * j0a;
-          if (is_g) v += ga;
-          else {
-            const double j1b = b < C1 ? (b == c ? 1.0 : 0.0) : -xs[t * Kp + xb];
-            const double j0b = b < C1 ? (b == c - 1 ? 1.0 : 0.0) : -xs[t * Kp + xb];
-            const double gb = q[0] * j1b - q[1] * j0b;
-            v += ga * gb - (q[2] * j1a * j1b - q[3] * j0a * j0b);
-          }
-        }
-        acc[e] += v;
-      }
+      chunked(n_h,
+              [&](int e, int t) -> double {
+                const int code = htab[e], o = code >> 16, a = (code >> 8) & 255, b = code & 255;
+                const int j = ord_of[o], C1 = S.ncat[j] - 1;
+                const double* q = st + (t * p + o) * 4;
+                const int c = (int)ys[t * p + j];
+                const double xa = a >= C1 ? xs[t * Kp + S.xidx[j][a - C1]] : 0.0;
+                const double j1a = a < C1 ? (a == c ? 1.0 : 0.0) : -xa, j0a = a < C1 ? (a == c - 1 ? 1.0 : 0.0) : -xa;
+                const double ga = q[0] * j1a - q[1] * j0a;
+                if (b == 255) return ga;
+                const double xb = b >= C1 ? xs[t * Kp + S.xidx[j][b - C1]] : 0.0;
+                const double j1b = b < C1 ? (b == c ? 1.0 : 0.0) : -xb, j0b = b < C1 ? (b == c - 1 ? 1.0 : 0.0) : -xb;
+                const double gb = q[0] * j1b - q[1] * j0b;
+                return ga * gb - (q[2] * j1a * j1b - q[3] * j0a * j0b);
+              },
+              [&](int e, double v) {
+                const int code = htab[e], o = code >> 16, a = (code >> 8) & 255, b = code & 255;
+                const int d = S.voff[ord_of[o] + 1] - S.voff[ord_of[o]];
+                if (b == 255) acc[hoff[o] + a] += v;
+                else {
+                  acc[hoff[o] + d + a * d + b] += v;
+                  if (a != b) acc[hoff[o] + d + b * d + a] += v;
+                }
+              });
       __syncthreads();
     }
     if (tid == 0) flag_sh = 0;
     __syncthreads();
     if (tid < n_ord) {
-      const int j = ord_of[tid], d = ex.voff[j + 1] - ex.voff[j];
+      const int j = ord_of[tid], d = S.voff[j + 1] - S.voff[j];
       double* gv = acc + hoff[tid];
       double* H = gv + d;
       if (!thread_chol_solve(H, gv, d)) atomicExch(&flag_sh, 2);
       else {
         double mx = 0.0;
-        for (int a = 0; a < d; ++a) { th[ex.voff[j] + a] += gv[a]; mx = fmax(mx, fabs(gv[a])); }
-        if (mx >= 1e-10) atomicMax(&flag_sh, 1);
+        for (int a = 0; a < d; ++a) { th[S.voff[j] + a] += gv[a]; mx = fmax(mx, fabs(gv[a])); }
+        if (mx >= 1e-6) atomicMax(&flag_sh, 1);   // quadratic convergence: the error left is the square of this step
       }
     }
     __syncthreads();
     const int f = flag_sh;
     __syncthreads();
+    diag[4] += 1.0;
     if (f == 2) { finish(GWSEM_CATCH_ACOV_NOT_PD, -1); return; }
     if (f == 0) break;
   }
+  lap(1);
 
   // ---------------- phase C: one correlation per pair, Newton on the score
-  for (int k = tid; k < np; k += T) rho_ok[k] = 0.0;
+  // Work split between the R threads of a person: polychoric pairs (bivariate normal integrals) and the cheap pairs
+  // are dealt out separately.  Per pair and iteration the Gauss-Legendre nodes of the bivariate normal integral
+  // (sin t, 1 / (2 cos^2 t), weight * asin(rho) / 2; they depend on rho only) are tabulated once for the CTA.
+  const unsigned char* powner = S.powner;
+  double* gtab = sm + L.gtab;
+  auto fill_gl_tables = [&]() {
+    for (int e = tid; e < np * kGlMax; e += NT) {
+      const int k = e / kGlMax, i = e % kGlMax;
+      const Pair pr = pair_of(k, p);
+      if (S.ncat[pr.a] == 0 || S.ncat[pr.b] == 0) continue;
+      const double rho = th[ex.n1 + k], ar = fabs(rho), asr = asin(rho);
+      // Genz (2004): 6 / 12 / 20 nodes reach 1e-15 in this form for |rho| < 0.3 / 0.75 / 0.925; 32 beyond
+      const int rule = ar < 0.3 ? 0 : (ar < 0.75 ? 1 : (ar < 0.925 ? 2 : 3));
+      int off = 0;
+      for (int r2 = 0; r2 < rule; ++r2) off += 2 * ex.gl_n[r2];
+      const int gln = ex.gl_n[rule];
+      double* tb = gtab + k * kGlStride;
+      if (i == 0) tb[0] = (double)gln;
+      if (i < gln) {
+        double st2, ct2;
+        sincos(0.5 * asr * (ex.gl[off + i] + 1.0), &st2, &ct2);
+        tb[1 + 3 * i] = st2;
+        tb[2 + 3 * i] = 1.0 / (2.0 * ct2 * ct2);
+        tb[3 + 3 * i] = 0.5 * asr * ex.gl[off + gln + i];
+      }
+    }
+  };
+  for (int k = tid; k < np; k += NT) rho_ok[k] = 0.0;
   __syncthreads();
   for (int iter = 0; iter < 60 && np > 0; ++iter) {
     zero_acc();
+    fill_gl_tables();
     __syncthreads();
     for (int t0 = 0; t0 < n_src; t0 += T) {
       load_tile(t0);
-      const bool live = gs[tid] == gs[tid];
-      VState vs[kExMaxVars];
-      if (live)
-        for (int j = 0; j < p; ++j) vs[j] = var_state(ex, th, j, xs + tid * Kp, ys[tid * p + j]);
+      const bool live = gs[pt] == gs[pt];
       for (int k = 0; k < np; ++k) {
+        if (powner[k] != sub) continue;
         double psi = 0.0, dpsi = 0.0;
         if (live && rho_ok[k] == 0.0) {
           const Pair pr = pair_of(k, p);
-          const PairEval ev = pair_eval(ex, pr.a, pr.b, vs[pr.a], vs[pr.b], (int)ys[tid * p + pr.a], (int)ys[tid * p + pr.b],
-                                        th[ex.n1 + k], ex.gl, false);
+          const VState va = var_state(S, th, pr.a, xs + pt * Kp, ys[pt * p + pr.a]);
+          const VState vb = var_state(S, th, pr.b, xs + pt * Kp, ys[pt * p + pr.b]);
+          const PairEval ev = pair_eval(S, pr.a, pr.b, va, vb, (int)ys[pt * p + pr.a], (int)ys[pt * p + pr.b],
+                                        th[ex.n1 + k], gtab + k * kGlStride, false);
           psi = ev.psi; dpsi = ev.dpsi;
         }
-        ps[(tid * np + k) * 4] = psi;
-        ps[(tid * np + k) * 4 + 1] = dpsi;
+        ps[(pt * np + k) * 4] = psi;
+        ps[(pt * np + k) * 4 + 1] = dpsi;
       }
       __syncthreads();
-      for (int e = tid; e < 2 * np; e += T) {
+      for (int e = tid; e < 2 * np; e += NT) {
         const int k = e >> 1, w = e & 1;
         double v = 0.0;
         for (int t = 0; t < T; ++t) v += ps[(t * np + k) * 4 + w];
@@ -527,70 +643,93 @@ __global__ void marg_exact_kernel(ExactProgram ex, const uint8_t* __restrict__ r
     }
     if (tid == 0) flag_sh = 0;
     __syncthreads();
-    for (int k = tid; k < np; k += T) {
+    for (int k = tid; k < np; k += NT) {
       if (rho_ok[k] != 0.0) continue;
       const double G = acc[2 * k], dG = acc[2 * k + 1], r = th[ex.n1 + k];
       double step = dG < 0.0 ? -G / dG : (G > 0.0 ? 0.1 : -0.1);
       step = fmax(-0.3, fmin(0.3, step));
       const double next = fmax(-0.99, fmin(0.99, r + step));
       th[ex.n1 + k] = next;
-      if (fabs(next - r) < 1e-11) rho_ok[k] = 1.0;
+      if (fabs(next - r) < 1e-6) rho_ok[k] = 1.0;   // Newton: the error left is the square of this step
       else atomicMax(&flag_sh, 1);
     }
     __syncthreads();
     const int f = flag_sh;
     __syncthreads();
+    diag[5] += 1.0;
     if (f == 0) break;
   }
+  lap(2);
 
   // ---------------- phase D: score rows at the estimates; B = sum sc sc' (lower triangle), A21 rows
   const int nB = nt * (nt + 1) / 2;
+  fill_gl_tables();
   int* etab = reinterpret_cast<int*>(sm + L.etab);
-  for (int e = tid; e < nB; e += T) {
+  for (int e = tid; e < nB; e += NT) {
     int b = 0, rem = e;
     while (rem >= nt - b) { rem -= nt - b; ++b; }
     etab[e] = ((b + rem) << 16) | b;   // (a >= b)
+  }
+  int* atab = etab + nB;
+  int n_a21 = 0;
+  for (int k = 0; k < np; ++k) {
+    const Pair pr = pair_of(k, p);
+    n_a21 += (S.voff[pr.a + 1] - S.voff[pr.a]) + (S.voff[pr.b + 1] - S.voff[pr.b]);
+  }
+  for (int e = tid; e < n_a21; e += NT) {
+    int k = 0, le = e;
+    for (;; ++k) {
+      const Pair pr = pair_of(k, p);
+      const int cnt = (S.voff[pr.a + 1] - S.voff[pr.a]) + (S.voff[pr.b + 1] - S.voff[pr.b]);
+      if (le < cnt) break;
+      le -= cnt;
+    }
+    const Pair pr = pair_of(k, p);
+    const int da = S.voff[pr.a + 1] - S.voff[pr.a];
+    atab[e] = (k << 16) | ((le < da ? 1 : 0) << 15) | (le < da ? le : le - da);
   }
   zero_acc();
   __syncthreads();
   for (int t0 = 0; t0 < n_src; t0 += T) {
     load_tile(t0);
-    const bool live = gs[tid] == gs[tid];
-    double* srow = sc + tid * nt;
-    for (int e = 0; e < nt; ++e) srow[e] = 0.0;
-    for (int e = 0; e < 4 * np; ++e) ps[tid * np * 4 + e] = 0.0;
+    const bool live = gs[pt] == gs[pt];
+    double* srow = sc + pt * nt;
+    for (int e = sub; e < nt; e += R) srow[e] = 0.0;
+    for (int e = sub; e < 4 * np; e += R) ps[pt * np * 4 + e] = 0.0;
+    __syncthreads();
     if (live) {
-      VState vs[kExMaxVars];
-      const double* xr = xs + tid * Kp;
-      for (int j = 0; j < p; ++j) {
-        const double yv = ys[tid * p + j];
-        vs[j] = var_state(ex, th, j, xr, yv);
-        const int o = ex.voff[j], nx = ex.nx[j];
-        if (ex.ncat[j] == 0) {
-          const double var = th[o + 1 + nx], e = vs[j].b;
+      const double* xr = xs + pt * Kp;
+      for (int j = sub; j < p; j += R) {
+        const double yv = ys[pt * p + j];
+        const VState vj = var_state(S, th, j, xr, yv);
+        const int o = S.voff[j], nx = S.nx[j];
+        if (S.ncat[j] == 0) {
+          const double var = th[o + 1 + nx], e = vj.b;
           srow[o] = e / var;
-          for (int m = 0; m < nx; ++m) srow[o + 1 + m] = xr[ex.xidx[j][m]] * e / var;
+          for (int m = 0; m < nx; ++m) srow[o + 1 + m] = xr[S.xidx[j][m]] * e / var;
           srow[o + 1 + nx] = (e * e - var) / (2.0 * var * var);
         } else {
-          const int C = ex.ncat[j], c = (int)yv;
-          double pi = ndiff(vs[j].a, vs[j].b);
+          const int C = S.ncat[j], c = (int)yv;
+          double pi = ndiff(vj.a, vj.b);
           if (!(pi > 1e-300)) pi = 1e-300;
-          const double r1 = c < C - 1 ? nphi(vs[j].a) / pi : 0.0, r0 = c > 0 ? nphi(vs[j].b) / pi : 0.0;
+          const double r1 = c < C - 1 ? nphi(vj.a) / pi : 0.0, r0 = c > 0 ? nphi(vj.b) / pi : 0.0;
           if (c < C - 1) srow[o + c] = r1;
           if (c > 0) srow[o + c - 1] -= r0;
-          for (int m = 0; m < nx; ++m) srow[o + C - 1 + m] = xr[ex.xidx[j][m]] * (r0 - r1);
+          for (int m = 0; m < nx; ++m) srow[o + C - 1 + m] = xr[S.xidx[j][m]] * (r0 - r1);
         }
       }
       for (int k = 0; k < np; ++k) {
+        if (powner[k] != sub) continue;
         const Pair pr = pair_of(k, p);
-        const PairEval ev = pair_eval(ex, pr.a, pr.b, vs[pr.a], vs[pr.b], (int)ys[tid * p + pr.a], (int)ys[tid * p + pr.b],
-                                      th[ex.n1 + k], ex.gl, true);
+        const VState va = var_state(S, th, pr.a, xr, ys[pt * p + pr.a]), vb = var_state(S, th, pr.b, xr, ys[pt * p + pr.b]);
+        const PairEval ev = pair_eval(S, pr.a, pr.b, va, vb, (int)ys[pt * p + pr.a], (int)ys[pt * p + pr.b],
+                                      th[ex.n1 + k], gtab + k * kGlStride, true);
         srow[ex.n1 + k] = ev.psi;
-        double* q = ps + (tid * np + k) * 4;
+        double* q = ps + (pt * np + k) * 4;
         auto side = [&](int v, double d0, double d1, double* out) {
-          if (ex.ncat[v] > 0) { out[0] = ev.psi * d0; out[1] = ev.psi * d1; }
+          if (S.ncat[v] > 0) { out[0] = ev.psi * d0; out[1] = ev.psi * d1; }
           else {
-            const double var = th[ex.voff[v] + 1 + ex.nx[v]], u = vs[v].a;
+            const double var = th[S.voff[v] + 1 + S.nx[v]], u = (v == pr.a ? va : vb).a;
             out[0] = ev.psi * (-d0 * rsqrt(var));
             out[1] = ev.psi * (-1.0 / (2.0 * var) - d0 * u / (2.0 * var));
           }
@@ -600,36 +739,31 @@ __global__ void marg_exact_kernel(ExactProgram ex, const uint8_t* __restrict__ r
       }
     }
     __syncthreads();
-    for (int e = tid; e < nB; e += T) {
+    for (int e = tid; e < nB; e += NT) {
       const int a = etab[e] >> 16, b = etab[e] & 0xffff;
       double v = 0.0;
       for (int t = 0; t < T; ++t) v = fma(sc[t * nt + a], sc[t * nt + b], v);
       acc[e] += v;
     }
-    // A21 entries: pair k, then the block of a, then the block of b
-    {
-      int base = nB;
-      for (int k = 0; k < np; ++k) {
-        const Pair pr = pair_of(k, p);
-        const int da = ex.voff[pr.a + 1] - ex.voff[pr.a], db = ex.voff[pr.b + 1] - ex.voff[pr.b];
-        for (int l = tid; l < da + db; l += T) {
-          const bool first = l < da;
-          const int v = first ? pr.a : pr.b, ll = first ? l : l - da;
-          double sum = 0.0;
-          for (int t = 0; t < T; ++t) {
-            const double* q = ps + (t * np + k) * 4 + (first ? 0 : 2);
-            sum += side_entry(ex, v, ll, q[0], q[1], ys[t * p + v], xs + t * Kp);
-          }
-          acc[base + l] += sum;
-        }
-        base += da + db;
-      }
-    }
+    // A21 entries: pair k, then the block of a, then the block of b (atab: pair << 16 | first side << 15 | local index)
+    __syncthreads();
+    chunked(n_a21,
+            [&](int e, int t) -> double {
+              const int code = atab[e], k = code >> 16, first = (code >> 15) & 1, ll = code & 0x7fff;
+              const Pair pr = pair_of(k, p);
+              const int v = first ? pr.a : pr.b;
+              const double* q = ps + (t * np + k) * 4 + (first ? 0 : 2);
+              return side_entry(S, v, ll, q[0], q[1], ys[t * p + v], xs + t * Kp);
+            },
+            [&](int e, double v) { acc[nB + e] += v; });
     __syncthreads();
   }
+  lap(3);
+  if (tid == 0)
+    for (int e = 0; e < 8; ++e) rec[ex.fo_B + nt * nt + e] = diag[e];
   // ---------------- record
-  for (int e = tid; e < nt; e += T) rec[ex.fo_theta + e] = th[e];
-  for (int e = tid; e < nB; e += T) {
+  for (int e = tid; e < nt; e += NT) rec[ex.fo_theta + e] = th[e];
+  for (int e = tid; e < nB; e += NT) {
     const int a = etab[e] >> 16, b = etab[e] & 0xffff;
     rec[ex.fo_B + a * nt + b] = acc[e];
     rec[ex.fo_B + b * nt + a] = acc[e];
@@ -638,9 +772,9 @@ __global__ void marg_exact_kernel(ExactProgram ex, const uint8_t* __restrict__ r
     int base = nB;
     for (int k = 0; k < np; ++k) {
       const Pair pr = pair_of(k, p);
-      const int da = ex.voff[pr.a + 1] - ex.voff[pr.a], db = ex.voff[pr.b + 1] - ex.voff[pr.b];
-      for (int l = tid; l < da + db; l += T) {
-        const int c = l < da ? ex.voff[pr.a] + l : ex.voff[pr.b] + (l - da);
+      const int da = S.voff[pr.a + 1] - S.voff[pr.a], db = S.voff[pr.b + 1] - S.voff[pr.b];
+      for (int l = tid; l < da + db; l += NT) {
+        const int c = l < da ? S.voff[pr.a] + l : S.voff[pr.b] + (l - da);
         rec[ex.fo_a21 + k * ex.n1 + c] = acc[base + l];
       }
       base += da + db;
@@ -659,11 +793,13 @@ void launch_marg_exact(gwsem_engine* e, const ExactProgram& ex, const uint8_t* d
   const size_t smem = marg_exact_smem_bytes(ex);
   if (smem > 227 * 1024) fail("marginals model too large for the per-SNP statistics kernel (%zu bytes of scratch)", smem);
   GW_CUDA(cudaFuncSetAttribute(marg_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  e->prof_begin(kFamClassSums);
-  marg_exact_kernel<<<n_snps, ex.T, smem, e->stream>>>(ex, d_rows, pitch, n_src, d_inc8, d_counts, plink1, d_geno, n_pad,
+  e->prof_begin(kFamMargExact);
+  // two threads per person of a tile share the per-person work (the bivariate normal integrals dominate it)
+  const int threads = ex.T <= 256 ? 2 * ex.T : ex.T;
+  marg_exact_kernel<<<n_snps, threads, smem, e->stream>>>(ex, d_rows, pitch, n_src, d_inc8, d_counts, plink1, d_geno, n_pad,
                                                        d_records);
   GW_CUDA(cudaGetLastError());
-  e->prof_end(kFamClassSums);
+  e->prof_end(kFamMargExact);
   e->launches++;
 }
 

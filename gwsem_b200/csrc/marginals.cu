@@ -24,7 +24,7 @@ void launch_marg_stats(gwsem_engine* e, const MargProgram& mp, const uint8_t* d_
   const int J = mp.J, D = 2 + J;
   const size_t smem = sizeof(double) * std::max<size_t>(std::max<size_t>((size_t)kT * (((D + 1) & ~1) + (mp.n1 | 1)) + 64, (size_t)8 * 64 * (D + 1)),
                                                          (size_t)8 * 64 + 4096 / 2);
-  e->prof_begin(kFamClassSums);
+  e->prof_begin(kFamMargStats);
 #define GW_MARG(JJ) case JJ: launch_marg_stats_j<JJ>(e, mp, d_rows, pitch, n_snps, n_src, d_inc8, d_counts, plink1, d_geno, n_pad, d_summary, smem); break;
   switch (J) {
     GW_MARG(1) GW_MARG(2) GW_MARG(3) GW_MARG(4) GW_MARG(5) GW_MARG(6) GW_MARG(7) GW_MARG(8) GW_MARG(9) GW_MARG(10)
@@ -32,7 +32,7 @@ void launch_marg_stats(gwsem_engine* e, const MargProgram& mp, const uint8_t* d_
   }
 #undef GW_MARG
   GW_CUDA(cudaGetLastError());
-  e->prof_end(kFamClassSums);
+  e->prof_end(kFamMargStats);
   e->launches++;
 }
 

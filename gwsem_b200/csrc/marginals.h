@@ -106,7 +106,7 @@ struct ExactProgram {
   const double* V = nullptr;                 // [n_pad][p]: value / category code / moderator of each variable
   const double* X = nullptr;                 // [n_pad][Kp]
   const double* theta0 = nullptr;            // nt: starting point (the SNP-independent estimates where there are any)
-  int gl_n[3] = {0, 0, 0};                   // Gauss-Legendre rules for the bivariate normal integral
+  int gl_n[4] = {0, 0, 0, 0};                // Gauss-Legendre rules for the bivariate normal integral
   const double* gl = nullptr;                // nodes then weights of each rule, back to back
   int full_stride = 0, fo_theta = 0, fo_a21 = 0, fo_B = 0;
 };

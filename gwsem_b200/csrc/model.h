@@ -65,6 +65,7 @@ struct gwsem_model {
   const int8_t* d_csq = nullptr;          // marginals: digits of the series products (tcgen05 layout)
   const double* d_cs_inv_scale = nullptr;
   void prepare_marginals(const std::vector<int>& dest_of);
+  void exact_diag(int n);
   void run_marginals(const uint8_t* d_packed, int64_t pitch, const double* d_geno, const double* d_maf_in, int n,
                      int plink1, const gwsem_result& r);
 

@@ -280,8 +280,8 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
     ex.V = up(pool, V, st);
     ex.X = up(pool, Xg, st);
     std::vector<double> gl, x, w;
-    const int rules[3] = {12, 20, 32};
-    for (int rr = 0; rr < 3; ++rr) {
+    const int rules[4] = {6, 12, 20, 32};
+    for (int rr = 0; rr < 4; ++rr) {
       gauss_legendre(rules[rr], x, w);
       ex.gl_n[rr] = rules[rr];
       gl.insert(gl.end(), x.begin(), x.end());
@@ -291,7 +291,7 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
     ex.fo_theta = 3;
     ex.fo_a21 = ex.fo_theta + ex.nt;
     ex.fo_B = ex.fo_a21 + ex.npairs * ex.n1;
-    ex.full_stride = ex.fo_B + ex.nt * ex.nt;
+    ex.full_stride = ex.fo_B + ex.nt * ex.nt + 8;   // + 8 diagnostic slots (phase cycles, Newton iterations)
     ex.T = 256;
     while (ex.T > 32 && marg_exact_smem_bytes(ex) > 227 * 1024) ex.T /= 2;
     if (marg_exact_smem_bytes(ex) > 227 * 1024) fail("marginals: model too large for the per-SNP statistics kernel");
@@ -530,6 +530,26 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
   }
 }
 
+// GWSEM_EXACT_DIAG=1 (development aid): mean cycles per phase and Newton iterations of marg_exact_kernel, on stderr
+void gwsem_model::exact_diag(int n) {
+  static const bool on = getenv("GWSEM_EXACT_DIAG") != nullptr;
+  if (!on) return;
+  std::vector<double> h((size_t)n * ex.full_stride);
+  GW_CUDA(cudaMemcpyAsync(h.data(), d_full.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, engine->stream));
+  GW_CUDA(cudaStreamSynchronize(engine->stream));
+  double d[8] = {0};
+  int cnt = 0;
+  for (int i = 0; i < n; ++i) {
+    const double* rec = &h[(size_t)i * ex.full_stride];
+    if (rec[0] < 0 || rec[1] != 0.0) continue;
+    ++cnt;
+    for (int e = 0; e < 8; ++e) d[e] += rec[ex.fo_B + ex.nt * ex.nt + e];
+  }
+  if (cnt)
+    fprintf(stderr, "marg_exact: %d SNPs, mean Mcycles A %.2f B %.2f C %.2f D %.2f, iterations B %.1f C %.1f (T = %d)\n", cnt,
+            d[0] / cnt / 1e6, d[1] / cnt / 1e6, d[2] / cnt / 1e6, d[3] / cnt / 1e6, d[4] / cnt, d[5] / cnt, ex.T);
+}
+
 void gwsem_model::run_marginals(const uint8_t* d_packed, int64_t pitch, const double* d_geno, const double* d_maf_in,
                                 int n, int plink1, const gwsem_result& r) {
   if (marg_mode == 1) {
@@ -574,6 +594,7 @@ void gwsem_model::run_marginals(const uint8_t* d_packed, int64_t pitch, const do
     // nothing is SNP-independent: every statistic of every SNP from marg_exact_kernel
     launch_marg_exact(engine, ex, d_packed, pitch, n, n_src, layout.d_inc8, d_geno ? nullptr : d_counts.p, plink1, d_geno,
                       n_pad, d_full.p);
+    exact_diag(n);
     launch_marg_fit(engine, fp, mpl, n, nullptr, maf, r);
     return;
   }
@@ -589,5 +610,6 @@ void gwsem_model::run_marginals(const uint8_t* d_packed, int64_t pitch, const do
   // SNPs with a missing call: the people retained differ from the model's, so every statistic is recomputed over them
   launch_marg_exact(engine, ex, d_packed, pitch, n, n_src, layout.d_inc8, d_geno ? nullptr : d_counts.p, plink1, d_geno, n_pad,
                     d_full.p);
+  exact_diag(n);
   launch_marg_fit(engine, fp, mpl, n, d_summary.p, maf, r);
 }

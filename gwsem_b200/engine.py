@@ -35,17 +35,23 @@ class Engine:
     def launches(self):
         return int(lib().gwsem_engine_launch_count(self.h))
 
-    KERNEL_FAMILIES = ("class_sums", "count_missing", "fit", "decode")
+    KERNEL_FAMILIES = ("class_sums", "count_missing", "fit", "decode", "marg_stats", "marg_exact", "reserved6", "reserved7")
 
     def profile(self, enable=True):
         check(lib().gwsem_engine_profile(self.h, int(enable)))
 
     def profile_read(self):
         """{family: (launches, total_ms)} since the last read (CUDA events on the launch stream)"""
-        n = (C.c_int64 * 4)()
-        ms = (C.c_double * 4)()
+        n = (C.c_int64 * 8)()
+        ms = (C.c_double * 8)()
         check(lib().gwsem_engine_profile_read(self.h, n, ms))
         return {k: (int(n[i]), float(ms[i])) for i, k in enumerate(self.KERNEL_FAMILIES)}
+
+    def fp64_peak(self):
+        """Measured DFMA throughput of this GPU right now, TFLOP/s."""
+        v = C.c_double()
+        check(lib().gwsem_engine_fp64_peak(self.h, C.byref(v)))
+        return float(v.value)
 
     def decode_2bit(self, packed, n_samples, plink1=False, row_filter=None):
         """packed: uint8 [n_snps, pitch] host array -> (geno[n_snps, dest_rows], maf[n_snps])"""

@@ -225,8 +225,8 @@ def run_plan(model, device=0, batch_snps=0):
                 device=device, batch_snps=batch_snps)
 
 
-def GWAS(model, snpData, out="out.log", *dots, SNP=None, startFrom=1, rowFilter=None, device=0, batch_snps=0):
-    """R/model.R:305-315."""
+def GWAS(model, snpData, out="out.log", *dots, SNP=None, startFrom=1, rowFilter=None, device=0, batch_snps=0, _timing=None):
+    """R/model.R:305-315.  (_timing: optional dict that receives the seconds spent inside gwsem_gwas_run.)"""
     if dots:
         raise ValueError("Rejected are any values passed in the '...' argument")
     if not isinstance(snpData, str):
@@ -272,7 +272,11 @@ def GWAS(model, snpData, out="out.log", *dots, SNP=None, startFrom=1, rowFilter=
                            c_pairs.ctypes.data_as(C.POINTER(C.c_int32)) if len(pairs) else None, len(pairs),
                            int(batch_snps), model.name.encode(), c_manifest)
             written = C.c_int64()
+            import time
+            t0 = time.perf_counter()
             check(lib().gwsem_gwas_run(gm.h, src.h, C.byref(job), C.byref(written)))
+            if _timing is not None:
+                _timing["gwas_run_s"] = time.perf_counter() - t0
             last = None
             if written.value:
                 last_idx = int(snp_arr[-1]) - 1 if snp_arr is not None and len(snp_arr) else src.num_variants - 1

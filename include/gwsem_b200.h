@@ -54,10 +54,15 @@ int gwsem_engine_synchronize(gwsem_engine* e);
 /* kernels launched by this engine since creation (bench.py's gpu_launches) */
 int64_t gwsem_engine_launch_count(const gwsem_engine* e);
 /* Per-launch timing with CUDA events on the launch stream.  gwsem_engine_profile_read fills
- * launches[4] / total_ms[4] for the kernel families {class sums, count+missing, fit, decode}
+ * launches[8] / total_ms[8] for the kernel families {class sums, count+missing, fit, decode,
+ * marginals statistics (fast path), marginals statistics (exact path), reserved, reserved}
  * seen since the previous read, and clears them (synchronises the stream). */
+#define GWSEM_PROFILE_FAMILIES 8
 int gwsem_engine_profile(gwsem_engine* e, int enable);
 int gwsem_engine_profile_read(gwsem_engine* e, int64_t* launches, double* total_ms);
+/* Measured FP64 FMA throughput of this GPU right now (TFLOP/s, DFMA micro-benchmark without memory
+ * traffic): the roofline denominator of the FP64-bound statistics kernels (bench.py). */
+int gwsem_engine_fp64_peak(gwsem_engine* e, double* tflops);
 
 /* ----------------------------------------------------------- genotype sources (providers) */
 /* method: "pgen" (also PLINK 1 .bed, as R/model.R:36) or "bgen".  src_rows: number of people
