@@ -177,6 +177,95 @@ def _gwas_multigroup(model, snpData, out, SNP, startFrom, rowFilter, device, bat
     return GWASResult(model, out, n, None, sum(r.loadCounter for r in results))
 
 
+def call_arguments(model, snpData, out="out.log", SNP=None, startFrom=1, rowFilter=None, device=0, batch_snps=0):
+    """The six arguments of .Call("gwsem_run", spec, data, path, method, rowFilter, job) (src/gwsem_call.c) as the
+    reference-side glue R/flatten.R assembles them from an MxModel -- flattenModel(), manifestColumns(), jobList().
+    Returned as plain Python values; dump_call() writes them to a text file that the C harness of `make -C src check`
+    turns back into SEXPs, so the .Call layer is exercised end to end without R."""
+    psd = processSnpData(snpData)
+    method, ext, stem = psd["method"][0], psd["snpFileExt"][0], psd["stem"][0]
+    flat = flatten(model)
+    data, n_categories = model_columns(model)
+    nm = flat["nm"]
+    n_rows = len(model.data)
+    kinds, cols = [], []
+    for name in flat["manifest"]:
+        if name == "snp":
+            kinds.append(1); cols.append(None)
+        elif name.startswith("snp_") and name[4:] in flat["gxe"]:
+            kinds.append(2); cols.append(data[name[4:]])
+        else:
+            kinds.append(0); cols.append(data[name])
+    exo, exo_kind = [], []
+    for name in flat["exo_pred"]:
+        if name == "snp" and "snp" not in data:
+            exo.append(None); exo_kind.append(1)
+        elif name.startswith("snp_") and name[4:] in flat["gxe"] and name not in data:
+            exo.append(data[name[4:]]); exo_kind.append(2)
+        else:
+            exo.append(data[name]); exo_kind.append(0)
+    exo_free = (flat["exo_free"].astype(np.uint8) if flat["exo_free"] is not None else np.zeros((nm, 0), np.uint8))
+    fit = {("WLS", "cumulants"): 0, ("WLS", "marginals"): 1}.get((flat["fitfun"], flat["continuous_type"]), 2)
+    spec = dict(n_vars=flat["nv"], n_manifest=nm, n_params=len(flat["par_names"]), n_cells=len(flat["cells"]),
+                cells=np.asarray(flat["cells"], float).reshape(-1), par_start=np.asarray(flat["par_start"], float),
+                par_lbound=np.asarray(flat["par_lbound"], float), fit=fit, min_variance=float(flat["min_variance"]),
+                n_rows=n_rows, manifest_kind=np.asarray(kinds, np.int32),
+                n_categories=np.asarray([n_categories.get(m, 0) for m in flat["manifest"]], np.int32),
+                exo=exo, exo_latent=np.asarray([nm + flat["latent"].index(c) for c in flat["exo_pred"]], np.int32),
+                exo_kind=np.asarray(exo_kind, np.int32), exo_free=exo_free.reshape(-1),
+                n_thresholds=len(flat["thresholds"]), thresholds=np.asarray(flat["thresholds"], float).reshape(-1))
+    names = flat["par_names"]
+    off = _offdiag(model, names)
+    pairs = [(names.index(a), names.index(b)) for i, a in enumerate(off) for b in off[i + 1:]]
+    job = dict(device=int(device), snp=None if SNP is None else np.asarray(SNP, np.int32).reshape(-1),
+               start_from=int(startFrom), out=out, par_names=list(names),
+               context_path={"pgen": stem + ".pvar", "bed": stem + ".bim"}.get(ext),
+               vcov_pairs=np.asarray(pairs, np.int32).reshape(-1) if pairs else None, batch_snps=int(batch_snps),
+               model_name=model.name, manifest_names=list(flat["manifest"]))
+    rf = None if rowFilter is None else np.asarray(rowFilter).astype(bool)
+    return dict(spec=spec, data=cols, path=snpData, method=method, rowFilter=rf, job=job)
+
+
+def dump_call(args, path):
+    """One value per line: `<list> <name> <type> <n> v...`; doubles as C99 hex floats (exact), strings %-quoted."""
+    from urllib.parse import quote
+
+    def line(lst, name, v):
+        if v is None:
+            return f"{lst} {name} null 0"
+        if isinstance(v, str):
+            return f"{lst} {name} str 1 {quote(v, safe='/')}"
+        if isinstance(v, (list, tuple)) and all(isinstance(x, str) for x in v):
+            return f"{lst} {name} str {len(v)} " + " ".join(quote(x, safe='/') for x in v)
+        if isinstance(v, (bool, np.bool_)):
+            return f"{lst} {name} lgl 1 {int(v)}"
+        if isinstance(v, (int, np.integer)):
+            return f"{lst} {name} int 1 {int(v)}"
+        if isinstance(v, float):
+            return f"{lst} {name} real 1 {float(v).hex()}"
+        a = np.asarray(v)
+        if a.dtype == bool:
+            return f"{lst} {name} lgl {a.size} " + " ".join(str(int(x)) for x in a.reshape(-1))
+        if a.dtype == np.uint8:
+            return f"{lst} {name} raw {a.size} " + " ".join(str(int(x)) for x in a.reshape(-1))
+        if a.dtype.kind in "iu":
+            return f"{lst} {name} int {a.size} " + " ".join(str(int(x)) for x in a.reshape(-1))
+        return f"{lst} {name} real {a.size} " + " ".join("nan" if x != x else float(x).hex() for x in a.reshape(-1))
+
+    out = []
+    for k, v in args["spec"].items():
+        if k == "exo":
+            out.append(f"spec n_exo int 1 {len(v)}")
+            out += [line("exo", str(j), c) for j, c in enumerate(v)]
+        else:
+            out.append(line("spec", k, v))
+    out += [line("data", str(j), c) for j, c in enumerate(args["data"])]
+    out += [line("top", "path", args["path"]), line("top", "method", args["method"]), line("top", "rowFilter", args["rowFilter"])]
+    out += [line("job", k, v) for k, v in args["job"].items()]
+    with open(path, "w") as f:
+        f.write("\n".join(out) + "\n")
+
+
 class GWASResult:
     """What the reference's GWAS() returns invisibly: the model with the last SNP loaded."""
 

@@ -58,10 +58,16 @@ def test_one_fac_with_exogenous_covariates(pheno):
 
 
 def test_endogenous_covariates(pheno):
-    m = buildOneFac(pheno, [f"i{k}" for k in range(3, 8)], covariates=["covar1"], exogenous=False)
+    cont = pheno.drop(columns=["i1", "i2"])
+    m = buildOneFac(cont, [f"i{k}" for k in range(3, 8)], covariates=["covar1"], exogenous=False)
     assert "covar1" in m.manifestVars and "covar1_to_F" in m.parameters()[0]
     # all continuous + no exogenous covariates -> cumulants: the mean structure is dropped (R/model.R:497-503)
     assert "covar1_var" in m.parameters()[0] and "covar1_mean" not in m.parameters()[0]
+    # a factor column anywhere in the observed data has typeof() == 'integer' in R: the reference warns and stays
+    # on marginals (R/model.R:486-496), even when the model does not use that column
+    with pytest.warns(UserWarning, match="Cumulants method prevented by integer observed columns"):
+        m = buildOneFac(pheno, [f"i{k}" for k in range(3, 8)], covariates=["covar1"], exogenous=False)
+    assert m.continuousType == "marginals" and "covar1_mean" in m.parameters()[0]
     m = buildOneFac(pheno, [f"i{k}" for k in range(1, 8)], covariates=["covar1"], exogenous=False)
     assert m.continuousType == "marginals" and "covar1_mean" in m.parameters()[0]
 
