@@ -100,7 +100,7 @@ def test_one_factor_pins(engine, tmp_path, model_pheno):
     assert list(pgen["SNP"]) == [f"RSID_{k}" for k in (4, 5, 6)] and list(pgen2["SNP"]) == 2 * list(pgen["SNP"])
     assert np.array_equal(np.round(pgen["snp_to_F"], 3), [0.242, 0.072, -0.087])   # see test_reference_pins.py
     assert all_equal(pgen["snp_to_F"], [0.242, 0.072, -0.087], 2.5e-3)
-    assert all_equal(log[["lambda_" + i for i in ITEMS]].mean(0) / loadings, np.ones(7), 0.2)
+    assert all_equal(log[["lambda_" + i for i in ITEMS]].mean(axis=0) / loadings, np.ones(7), 0.2)
     check_against_oracle(log, *run(m, geno("example_pgen"), [3, 4, 5], "marginals"))
 
 
@@ -117,7 +117,7 @@ def test_one_factor_residuals_pins(engine, tmp_path, model_pheno):
     q13 = np.repeat(rp.quantile7(orig["i1"], [1 / 3]), 3)
     assert np.mean(np.abs(log["i1_Thr_1"] - q13)) / np.mean(np.abs(log["i1_Thr_1"])) <= 0.21   # see test_reference_pins.py
     assert np.mean(np.abs(log["i2_Thr_1"])) <= 0.15
-    assert all_equal(log[["lambda_" + i for i in ITEMS]].mean(0) / loadings, np.ones(7), 0.2)
+    assert all_equal(log[["lambda_" + i for i in ITEMS]].mean(axis=0) / loadings, np.ones(7), 0.2)
     r = signif(loadResults(out, "snp_to_i2"), "snp_to_i2")
     assert all_equal(r["P"], [0.455, 0.885, 0.395], 1e-2)
     check_against_oracle(log, *run(m2, geno("example_pgen"), [3, 4, 5], "marginals"))
@@ -130,7 +130,7 @@ def test_two_factor_pins(engine, tmp_path, model_pheno):
     m = buildTwoFac(pheno, ITEMS[:4], ITEMS[3:])
     out, log, _ = gwas(m, "example.pgen", tmp_path, SNP=[3, 4, 5])
     names = [f"F1_lambda_i{k}" for k in (1, 2, 3)] + [f"F2_lambda_i{k}" for k in (5, 6, 7)]
-    assert all_equal(log[names].mean(0) / np.delete(loadings, 3), np.ones(6), 0.15)
+    assert all_equal(log[names].mean(axis=0) / np.delete(loadings, 3), np.ones(6), 0.15)
     assert all_equal(log["facCov"], np.repeat(1.17, 3), 0.02)
     check_against_oracle(log, *run(m, geno("example_pgen"), [3, 4, 5], "marginals"))
 
