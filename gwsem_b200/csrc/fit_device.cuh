@@ -39,17 +39,26 @@ __host__ __device__ inline WarpScratch scratch_layout(int p, int q, int nv, int 
   return w;
 }
 
-// A group of LANES threads (1 or 32) works on one SNP.
+// A group of LANES threads works on one SNP: one thread, one warp, or (LANES > 32) the whole CTA.
 template <int LANES>
 __device__ __forceinline__ void gsync() {
-  if (LANES > 1) __syncwarp();
+  if (LANES > 32) __syncthreads();
+  else if (LANES > 1) __syncwarp();
 }
 template <int LANES>
-__device__ __forceinline__ double gbcast(double v) {
+__device__ __forceinline__ double gbcast(double v) {   // the value of the group's first thread
+  if (LANES > 32) {
+    __shared__ double slot;
+    __syncthreads();
+    if (threadIdx.x == 0) slot = v;
+    __syncthreads();
+    return slot;
+  }
   return LANES > 1 ? __shfl_sync(0xffffffffu, v, 0) : v;
 }
 template <int LANES>
 __device__ __forceinline__ bool gany(bool p) {
+  if (LANES > 32) return __syncthreads_or(p) != 0;
   return LANES > 1 ? __any_sync(0xffffffffu, p) != 0 : p;
 }
 

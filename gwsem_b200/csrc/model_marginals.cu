@@ -605,11 +605,41 @@ void gwsem_model::run_marginals(const uint8_t* d_packed, int64_t pitch, const do
     launch_class_sums_tc5(engine, d_packed, pitch, n, plink1, layout, d_csq, d_cs_inv_scale, mp.cs_nf, d_cs_sums.p, nullptr);
     mpl.cs_sums = d_cs_sums.p;
   }
+  // SNPs with a missing call: the people retained differ from the model's, so every statistic is recomputed over them
+  // (marg_exact_kernel; the others leave at once).  It goes first, on a side stream: its few long-running CTAs keep
+  // their SMs while marg_stats_kernel streams the whole batch through the rest.
+  if (!side_stream) {
+    GW_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+    GW_CUDA(cudaEventCreateWithFlags(&ev_side_go, cudaEventDisableTiming));
+    GW_CUDA(cudaEventCreateWithFlags(&ev_side_done, cudaEventDisableTiming));
+  }
+  {
+    cudaStream_t main_stream = engine->stream;
+    GW_CUDA(cudaEventRecord(ev_side_go, main_stream));
+    GW_CUDA(cudaStreamWaitEvent(side_stream, ev_side_go, 0));
+    engine->stream = side_stream;
+    try {
+      launch_marg_exact(engine, ex, d_packed, pitch, n, n_src, layout.d_inc8, d_geno ? nullptr : d_counts.p, plink1, d_geno,
+                        n_pad, d_full.p);
+    } catch (...) {
+      engine->stream = main_stream;
+      throw;
+    }
+    engine->stream = main_stream;
+    GW_CUDA(cudaEventRecord(ev_side_done, side_stream));
+  }
   launch_marg_stats(engine, mpl, d_packed, pitch, n, n_src, layout.d_inc8, d_geno ? nullptr : d_counts.p, plink1, d_geno,
                     n_pad, d_summary.p);
-  // SNPs with a missing call: the people retained differ from the model's, so every statistic is recomputed over them
-  launch_marg_exact(engine, ex, d_packed, pitch, n, n_src, layout.d_inc8, d_geno ? nullptr : d_counts.p, plink1, d_geno, n_pad,
-                    d_full.p);
+  GW_CUDA(cudaStreamWaitEvent(engine->stream, ev_side_done, 0));
   exact_diag(n);
+  static const bool dbg = getenv("GWSEM_DEBUG_SYNC") != nullptr;   // development aid: attribute a device fault to its kernel
+  if (dbg) {
+    GW_CUDA(cudaStreamSynchronize(engine->stream));
+    fprintf(stderr, "gwsem debug: statistics kernels of %d SNPs done\n", n);
+  }
   launch_marg_fit(engine, fp, mpl, n, d_summary.p, maf, r);
+  if (dbg) {
+    GW_CUDA(cudaStreamSynchronize(engine->stream));
+    fprintf(stderr, "gwsem debug: marg_fit of %d SNPs done\n", n);
+  }
 }
