@@ -56,6 +56,14 @@ WORKLOADS = {
         kernel="class_sums_imma_kernel<2,2,4,512>", family="class_sums", bound="hbm"),
 }
 N_CAUSAL = 4
+# the other two configurations of BASELINE.json ride along, device-resident input only
+RIDERS = {
+    "res_c4": dict(n_people=50_000, snps=32_768,
+                   workload="C4: buildOneFacRes, 5 continuous items, WLS cumulants, PLINK 1 .bed coding, 50k people x 32,768 SNPs per step"),
+    "twofac_c5": dict(n_people=200_000, snps=2_048,
+                      workload="C5: buildTwoFac ML, 8 continuous items + gxe moderator, dosages (doubles, as decoded from bgen), "
+                               "200k people x 2,048 SNPs per step"),
+}
 
 
 def measured_peaks():
@@ -402,6 +410,84 @@ def measure(rk, eng, stream, which, n_snps, steps, warmup, missing_rate=0.0, hos
     return out
 
 
+def measure_rider(rk, eng, stream, name, steps, warmup):
+    """C4 / C5: value and kernel shares with the genotypes resident in HBM."""
+    import numpy as np
+    import pandas as pd
+    import torch
+    from gwsem_b200 import _lib, synth
+    from gwsem_b200.engine import Model
+    from gwsem_b200.gwas import model_columns
+    from gwsem_b200.model import buildOneFacRes, buildTwoFac, flatten
+    w = RIDERS[name]
+    n, m, dev = w["n_people"], w["snps"], rk.dev
+    rng = np.random.default_rng(2003)
+    if name == "res_c4":
+        F = rng.normal(size=n)
+        ph = pd.DataFrame({f"i{k + 1}": lam * F + rng.normal(size=n) for k, lam in enumerate([.8, .7, .6, .5, .4])})
+        sem = buildOneFacRes(ph, list(ph.columns))
+    else:
+        F1 = rng.normal(size=n)
+        F2 = 0.3 * F1 + rng.normal(size=n)
+        ph = pd.DataFrame({"E": rng.integers(0, 2, n).astype(float)})
+        for k in range(8):
+            ph[f"i{k + 1}"] = (0.5 + 0.05 * k) * (F1 if k < 4 else F2) + rng.normal(size=n)
+        sem = buildTwoFac(ph, [f"i{k}" for k in range(1, 5)], [f"i{k}" for k in range(5, 9)], gxe="E", fitfun="ML")
+    flat = flatten(sem)
+    cols, ncat = model_columns(sem)
+    model = Model(eng, flat, cols, ncat)
+    model.set_row_filter(None, n)
+    P = model.P
+    dres = {"est": torch.empty((m, P), dtype=torch.float64, device=dev), "vcov": torch.empty((m, P, P), dtype=torch.float64, device=dev),
+            "fit": torch.empty(m, dtype=torch.float64, device=dev), "maf": torch.empty(m, dtype=torch.float64, device=dev)}
+    for k in ("n_used", "status", "catch_code", "catch_var", "iterations"):
+        dres[k] = torch.empty(m, dtype=torch.int32, device=dev)
+    ds = _lib.Result(*[dres[f].data_ptr() for f, _ in _lib.Result._fields_])
+    packed = synth.device_hardcalls(n, m, seed=1003 + rk.rank, device=dev, maf_range=(0.1, 0.5))
+    if name == "res_c4":
+        lut = torch.tensor([3, 2, 0, 1], dtype=torch.uint8, device=dev)      # PLINK 2 -> PLINK 1 two-bit codes
+        bed = torch.zeros_like(packed)
+        for sh in (0, 2, 4, 6):
+            bed |= lut[((packed >> sh) & 3).long()] << sh
+        row_bytes = (n + 3) // 4
+        bed[:, row_bytes:] = 0
+        step = lambda: model.fit_2bit_device(bed.data_ptr(), bed.shape[1], m, ds, plink1=True)
+    else:
+        n_pad = (n + 31) // 32 * 32
+        geno = torch.full((m, n_pad), float("nan"), dtype=torch.float64, device=dev)
+        g = torch.Generator(device=dev)
+        g.manual_seed(5 + rk.rank)
+        for s0 in range(0, m, 256):        # dosage = hardcall +- a little uncertainty, clipped to [0, 2]
+            blk = packed[s0:s0 + 256]
+            codes = torch.stack([(blk >> sh) & 3 for sh in (0, 2, 4, 6)], dim=2).reshape(blk.shape[0], -1)[:, :n].double()
+            geno[s0:s0 + 256, :n] = (codes + 0.1 * torch.rand(codes.shape, device=dev, generator=g, dtype=torch.float64) *
+                                     (1.0 - codes)).clamp_(0.0, 2.0)
+        maf = geno[:, :n].mean(1) / 2
+        dres["maf"].copy_(torch.minimum(maf, 1 - maf))
+        step = lambda: model.fit_rows_device(geno.data_ptr(), m, ds)
+    for _ in range(warmup):
+        step()
+    rk.barrier()
+    eng.profile(True)
+    eng.profile_read()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    stream.synchronize()
+    rk.barrier()
+    ms = e0.elapsed_time(e1)
+    prof = eng.profile_read()
+    eng.profile(False)
+    ok = float((dres["status"] == 0).float().mean().item())
+    model.close()
+    (ms,) = rk.max_over_ranks([ms])
+    return {"value": m * rk.world * steps / (ms / 1e3), "unit": UNIT, "steps": steps, "ms_per_step": ms / steps,
+            "workload": w["workload"], "status_ok_fraction": ok,
+            "kernel_ms_share": {k: v[1] / ms for k, v in prof.items() if v[0]}}
+
+
 def roofline(which, m, n_snps, steps, fp64_peak):
     """Dominant kernel of the workload against the roofline that bounds it; launch times from CUDA events on the launch
     stream over the timed region (gwsem_engine_profile*)."""
@@ -536,6 +622,8 @@ def run_gpu(args):
             "e2e": {"value": tot_o / (ms_oe / 1e3), "unit": UNIT, "h2d_bytes_per_step": mo_["h2d"], "d2h_bytes_per_step": mo_["d2h"]},
             "gpu_launches": int(mo_["launches"]), "roofline": roofline(other, mo_, wo["snps"], st, fp64_peak)}
         del mo_
+    if not args.no_secondary:
+        line["riders"] = {name: measure_rider(rk, eng, stream, name, max(1, min(args.steps, 3)), 2) for name in RIDERS}
     if variants:
         line["variants"] = variants
     if rk.rank != 0:

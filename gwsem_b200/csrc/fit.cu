@@ -246,6 +246,8 @@ __global__ void __launch_bounds__(128)
     }
     gsync<LANES>();
     for (int idx = lane; idx < P * P; idx += LANES) vcov[idx] = Hc[idx];
+  } else if (status == GWSEM_STATUS_OK) {
+    status = GWSEM_STATUS_NOT_CONVEX;   // the information matrix is not positive definite at the solution
   }
   for (int k = lane; k < P; k += LANES) est[k] = theta[k];
   if (lane == 0) {

@@ -260,7 +260,7 @@ struct Stager {
         std::vector<uint8_t> none;
         try { bgen_inflate(*s, nullptr, 0, none); } catch (const std::exception&) {}
       }
-      const int threads = (int)std::min<unsigned>(std::min(16u, std::max(1u, std::thread::hardware_concurrency())), (unsigned)n);
+      const int threads = (int)std::min<unsigned>(std::min(64u, std::max(1u, std::thread::hardware_concurrency())), (unsigned)n);   // every host core: inflate bounds bgen end to end
       std::vector<std::exception_ptr> err(std::max(threads, 1));
       auto work = [&](int t) {
         try {

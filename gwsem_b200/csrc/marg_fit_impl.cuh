@@ -507,6 +507,8 @@ __global__ void __launch_bounds__(GW_MF_LANES > 64 ? GW_MF_LANES : 64)
   if (warp_cholesky<LANES>(H, P, lane)) {
     chol_inverse(H, P, Hc, lane);
     for (int idx = lane; idx < P * P; idx += LANES) vcov[idx] = Hc[idx];
+  } else if (status == GWSEM_STATUS_OK) {
+    status = GWSEM_STATUS_NOT_CONVEX;   // the information matrix is not positive definite at the solution
   }
   for (int k = lane; k < P; k += LANES) est[k] = theta[k];
   if (lane == 0) {

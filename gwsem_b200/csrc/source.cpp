@@ -98,7 +98,12 @@ void open_pgen(gwsem_source* s, int src_rows) {
   if (s->mode != 0x10)
     fail("%s: third byte does not correspond to a storage mode supported by this reader", s->path.c_str());
   if (ctrl & 8) fail("%s: fused vrtype/record-length headers (single-sample files) are not supported", s->path.c_str());
-  if ((ctrl >> 4) & 3) fail("%s: multiallelic .pgen files are not supported", s->path.c_str());
+  // A header with stored ALT-allele counts is a multiallelic file.  The reference provider opens it with
+  // allele_idx_offsets == NULL (src/loader.cpp:323-327), which pgenlib rejects (src/pgenlib_read.cc:1172-1178); the
+  // aux1 tracks of such records (SkipAux1, src/pgenlib_read.cc:6605-6620) are therefore never reached from gwsem.
+  if ((ctrl >> 4) & 3)
+    fail("%s: PgfiInitPhase2: pgfip->allele_idx_offsets must be allocated before PgfiInitPhase2() is called "
+         "(multiallelic .pgen: not readable through gwsem's provider)", s->path.c_str());
   const bool nonref_stored = (ctrl >> 6) == 3;
   const bool wide = (ctrl & 4) != 0;
   const uint32_t len_bytes = 1 + (ctrl & 3);

@@ -183,6 +183,11 @@ class Model:
         check(lib().gwsem_fit_2bit_device(self.h, C.c_void_p(d_packed_ptr), pitch, n_snps, int(plink1),
                                           C.byref(d_result_struct)))
 
+    def fit_rows_device(self, d_geno_ptr, n_snps, d_result_struct):
+        """Generic path on decoded doubles resident in HBM (dosages): d_geno[n_snps][n_pad] in file order, NaN =
+        missing, n_pad = people rounded up to 32; the result's maf array must hold the MAFs on entry."""
+        check(lib().gwsem_fit_rows_device(self.h, C.c_void_p(d_geno_ptr), n_snps, C.byref(d_result_struct)))
+
     def close(self):
         if self.h:
             lib().gwsem_model_destroy(self.h)

@@ -129,7 +129,8 @@ void gwsem_model_destroy(gwsem_model* m);
 int gwsem_model_set_row_filter(gwsem_model* m, const int32_t* row_filter, int src_rows);
 
 /* status codes in gwsem_result.status (text as OpenMx prints statusCode) */
-enum { GWSEM_STATUS_OK = 0, GWSEM_STATUS_ITERATION_LIMIT = 4, GWSEM_STATUS_NONZERO_GRADIENT = 6, GWSEM_STATUS_NA = -1 };
+enum { GWSEM_STATUS_OK = 0, GWSEM_STATUS_ITERATION_LIMIT = 4, GWSEM_STATUS_NOT_CONVEX = 5, GWSEM_STATUS_NONZERO_GRADIENT = 6,
+       GWSEM_STATUS_NA = -1 };
 /* reasons the per-SNP TryCatch fired (column catch1) */
 enum { GWSEM_CATCH_NONE = 0, GWSEM_CATCH_MIN_VARIANCE = 1, GWSEM_CATCH_ACOV_NOT_PD = 2 };
 

@@ -212,9 +212,12 @@ def fit_snp_cumulants(flat, pheno_cols, snp):
     theta, F, it, status = wls_fit(s, W, lambda t: sigma_cumulants(ram, t), lambda t: jac_cumulants(ram, t),
                                    flat["par_start"], flat["par_lbound"])
     J = jac_cumulants(ram, theta)
-    try:
+    try:    # an information matrix that is not positive definite at the solution: OpenMx statusCode 5, no covariance
+        cholesky_checked(J.T @ W @ J)
         vcov = np.linalg.inv(J.T @ W @ J)
     except np.linalg.LinAlgError:
         vcov = np.full((ram.P, ram.P), np.nan)
+        if status == "OK":
+            status = "not convex/red"
     out.update(est=theta, vcov=vcov, status=status, fit=F, iterations=it)
     return out

@@ -25,7 +25,7 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import 
 import numpy as np
 from scipy.special import ndtr
 
-from fit_oracle import FlatRAM, wls_fit
+from fit_oracle import FlatRAM, cholesky_checked, wls_fit
 
 SQRT2PI = np.sqrt(2 * np.pi)
 ZMAX = 12.0  # stands in for +-infinity thresholds
@@ -447,9 +447,12 @@ def fit_snp_marginals(flat, pheno_cols, snp, n_cats):
 
     theta, F, it, status = wls_fit(st["s"], W, sig, jac, flat["par_start"], flat["par_lbound"])
     J = jac(theta)
-    try:
+    try:    # an information matrix that is not positive definite at the solution: OpenMx statusCode 5, no covariance
+        cholesky_checked(J.T @ W @ J)
         vcov = np.linalg.inv(J.T @ W @ J)
     except np.linalg.LinAlgError:
         vcov = np.full((P, P), np.nan)
+        if status == "OK":
+            status = "not convex/red"
     out.update(est=theta, vcov=vcov, status=status, fit=F, iterations=it, stats=st)
     return out

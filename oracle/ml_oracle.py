@@ -173,13 +173,17 @@ def fit_snp_ml(flat, pheno_cols, snp):
             break
     f, g = fun(theta)
     H = hessian(theta)
-    try:
+    gmax = np.max(np.abs(g[theta > lb + 1e-12])) if np.any(theta > lb + 1e-12) else 0.0
+    status = "OK" if gmax < 1e-4 * n_all else "nonzero gradient/red"
+    try:    # a Hessian that is not positive definite at the solution: OpenMx statusCode 5, no covariance
+        from fit_oracle import cholesky_checked
+        cholesky_checked(H)
         vcov = 2 * np.linalg.inv(H)
     except np.linalg.LinAlgError:
         vcov = np.full((P, P), np.nan)
-    gmax = np.max(np.abs(g[theta > lb + 1e-12])) if np.any(theta > lb + 1e-12) else 0.0
-    out.update(est=theta, vcov=vcov, status="OK" if gmax < 1e-4 * n_all else "nonzero gradient/red", fit=f,
-               iterations=int(res.nit))
+        if status == "OK":
+            status = "not convex/red"
+    out.update(est=theta, vcov=vcov, status=status, fit=f, iterations=int(res.nit))
     return out
 
 

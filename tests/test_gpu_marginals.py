@@ -120,6 +120,31 @@ def test_marginals_with_missing_calls(engine, rate, n):
     gm.close()
 
 
+def test_large_batches_are_repeatable_bit_for_bit(engine):
+    """compute-sanitizer is closed on this pool, so data races have to show up as run-to-run differences: a batch
+    large enough to keep every SM full (the multi-warp fit kernel once raced in its pivot search and only showed
+    it beyond ~8,000 SNPs per launch), three times, must give identical bits -- and the same bits as small batches."""
+    from gwsem_b200.engine import Model
+    n, m = 1500, 12_000
+    ph = cohort(n, 17, 3, 2, [True, False, True])
+    model = buildOneFac(ph, ["i1", "i2", "i3"], covariates=["pc1", "pc2"])
+    flat = flatten(model)
+    data, ncat = model_columns(model)
+    codes = synth.simulate_hardcalls(n, m, seed=23, maf_range=(0.05, 0.5))
+    codes[::97, ::11] = 3                      # some SNPs through the exact re-estimation kernel
+    packed = synth.pack_2bit(codes)
+    gm = Model(engine, flat, data, ncat)
+    runs = [gm.fit_2bit(packed) for _ in range(3)]
+    for r in runs[1:]:
+        for f in ("est", "vcov", "fit"):
+            assert np.array_equal(getattr(r, f).view(np.uint64), getattr(runs[0], f).view(np.uint64)), f
+        assert np.array_equal(r.status, runs[0].status) and np.array_equal(r.catch_code, runs[0].catch_code)
+    small = gm.fit_2bit(packed[5000:5300])
+    assert np.array_equal(small.est.view(np.uint64), runs[0].est[5000:5300].view(np.uint64))
+    assert (runs[0].status[runs[0].catch_code == 0] == 0).mean() > 0.99
+    gm.close()
+
+
 def test_items_with_exogenous_snp_match_oracle(engine):
     """buildItem with several depVars, one of them ordinal (tests/testthat/test-model.R:86): exogenous defaults
     to TRUE, snp is a definition variable of every item and of their residual correlation."""
