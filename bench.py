@@ -410,6 +410,26 @@ def measure(rk, eng, stream, which, n_snps, steps, warmup, missing_rate=0.0, hos
     return out
 
 
+def host_link_ceiling(rk):
+    """Pinned host -> device copy bandwidth with every rank copying at the same time: the ceiling of any `e2e` number
+    (bytes per SNP / this).  Returns GB/s of this rank (slowest rank reported by the caller) -- torch is the copier."""
+    import torch
+    n = 1 << 30
+    host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    devb = torch.empty(n, dtype=torch.uint8, device=rk.dev)
+    devb.copy_(host, non_blocking=True)
+    rk.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        devb.copy_(host, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize(rk.dev)
+    gbs = 3 * n / (e0.elapsed_time(e1) / 1e3) / 1e9
+    del host, devb
+    return gbs
+
+
 def measure_rider(rk, eng, stream, name, steps, warmup):
     """C4 / C5: value and kernel shares with the genotypes resident in HBM."""
     import numpy as np
@@ -588,6 +608,13 @@ def run_gpu(args):
         "run": {"status_ok_fraction": m["ok_frac"], "caught_fraction": m["caught_frac"],
                 "e2e_results_identical_to_device_path": m["e2e_identical"], "fp64_peak_tflops": fp64_peak},
     }
+    (neg_link,) = rk.max_over_ranks([-host_link_ceiling(rk)])
+    link = -neg_link
+    bytes_per_snp = (w["n_people"] + 3) // 4
+    line["e2e"]["host_to_device_gbs_per_gpu_all_ranks_copying"] = link
+    line["e2e"]["ceiling_snps_per_s"] = rk.world * link * 1e9 / bytes_per_snp
+    line["e2e"]["ceiling_note"] = ("pinned host -> device copy bandwidth of the slowest rank while all ranks copy, measured in this run; "
+                                   f"ceiling = ranks x that / {bytes_per_snp} B of packed genotypes per SNP")
     variants = {}
     if not args.no_variants:
         if which == "c3":
@@ -603,7 +630,7 @@ def run_gpu(args):
                 "what": "same model and cohort, 0.5 % of the calls missing: naAction='omit' drops those people from every "
                         "statistic of the SNP, marg_exact_kernel re-estimates all of them (device-resident input)"}
             del mm
-        n_g = min(args.snps, 16_384)
+        n_g = min(args.snps, 32_768)
         g = gwas_file_to_log(rk, which, m["packed"], m["model"], n_g)
         (g_min,) = rk.max_over_ranks([-g["value"]])
         g["value_slowest_rank"] = -g_min
@@ -619,7 +646,8 @@ def run_gpu(args):
         line["item_c2" if other == "c2" else "onefac_c3"] = {
             "metric": wo["metric"], "value": tot_o / (ms_o / 1e3), "unit": UNIT, "steps": st, "ms_per_step": ms_o / st,
             "config": config_of(other, wo["snps"]),
-            "e2e": {"value": tot_o / (ms_oe / 1e3), "unit": UNIT, "h2d_bytes_per_step": mo_["h2d"], "d2h_bytes_per_step": mo_["d2h"]},
+            "e2e": {"value": tot_o / (ms_oe / 1e3), "unit": UNIT, "h2d_bytes_per_step": mo_["h2d"], "d2h_bytes_per_step": mo_["d2h"],
+                    "ceiling_snps_per_s": rk.world * link * 1e9 / ((wo["n_people"] + 3) // 4)},
             "gpu_launches": int(mo_["launches"]), "roofline": roofline(other, mo_, wo["snps"], st, fp64_peak)}
         del mo_
     if not args.no_secondary:
