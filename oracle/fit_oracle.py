@@ -1,10 +1,13 @@
 """TEST INFRASTRUCTURE ONLY -- CPU (numpy, float64) restatement of the per-SNP fit.
 
-PARITY UNPINNED.  The arithmetic below is what the reference delegates to OpenMx
-(`DESCRIPTION:49-51`, Depends: OpenMx >= 2.19.8), an un-vendored CRAN dependency that is
-absent from /root/reference and from this image (no R either).  It is restated from
-the published algorithms that OpenMx's WLS path implements, anchored on the reference's
-own call sites:
+PARITY PINNED BY THE REFERENCE'S KNOWN ANSWERS (round 2).  The arithmetic below is what the reference delegates
+to OpenMx (`DESCRIPTION:49-51`, Depends: OpenMx >= 2.19.8), an un-vendored CRAN dependency that is absent from
+/root/reference and from this image (no R either).  It is restated from the published algorithms that OpenMx's WLS
+path implements, and checked against numbers OpenMx produced: the reference's tests assert them on phenotypes
+simulated with R's RNG, which oracle/r_rng.py replays bit for bit (tests/test_reference_pins.py:
+tests/testthat/test-model.R:58 P == .155 and which.min(P) == 3; test-gxe.R:61-64 fivenum of the moderated Z scores
+over 199 SNPs and the 197 / 2 split of clean / suspicious rows).  What those pins cannot resolve at N = 500 (effects
+below 0.2 %): N vs N-1 denominators.  Anchored on the reference's own call sites:
   * R/model.R:5      mxFitFunctionWLS(allContinuousMethod="marginals"), full weight
   * R/model.R:497-503  continuousType <- 'cumulants', mean structure dropped
   * R/model.R:435-436  mxData(type='raw', minVariance=2*minMAF*(1-minMAF), naAction='omit')
@@ -19,10 +22,9 @@ Published algorithms restated here:
     omxData::wlsAllContinuousCumulants states it follows); W = N * Gamma^{-1}
   * RAM expectation: McArdle & McDonald (1984): Sigma = F (I-A)^-1 S (I-A)^-T F'
   * WLS discrepancy F = (s - sigma)' W (s - sigma); vcov = (J' W J)^-1
-The only reference-side numeric pins for this part need R's RNG; what is
-checked instead (tests/test_oracle_fit.py): the closed form of the saturated buildItem
-model, agreement with scipy's generic optimiser on the same objective, finite-difference
-Jacobians, and recovery of simulated parameters within their standard errors.
+Also checked (tests/test_oracle_fit.py): the closed form of the saturated buildItem model, agreement with scipy's
+generic optimiser on the same objective, finite-difference Jacobians, and recovery of simulated parameters within
+their standard errors.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this.
 """

@@ -4,8 +4,13 @@ reference R/model.R:5, selected whenever postprocessModel does not switch to cum
 (R/model.R:488-510); thresholds from setupThresholds (R/model.R:346-365), exogenous covariates
 as definition-variable latents with `exoFree` slopes (R/model.R:403-418).
 
-PARITY UNPINNED: the arithmetic lives in OpenMx (DESCRIPTION:49-51), absent from the
-reference tree and from this image.  Restated from the published three-stage estimator
+PARITY PINNED BY THE REFERENCE'S KNOWN ANSWERS (round 2): the arithmetic lives in OpenMx (DESCRIPTION:49-51), absent
+from the reference tree and from this image, but the reference's tests assert numbers it produced on phenotypes
+simulated with R's RNG, which oracle/r_rng.py replays bit for bit.  tests/test_reference_pins.py reproduces
+test-model.R:97,103 (P == .0251 / .086, ordinal + continuous depVars with an exogenous snp), :122 (snp_to_F of the
+7-item one-factor model, to the three printed decimals), :157 (P == c(.455, .885, .395)), :171 (facCov == 1.17) and
+test-formats.R:65-70 (on example.bed: 171 clean / 28 failed rows against 173 / 26 +- 6, fivenum(Z) to 1e-2), each at
+the reference's own tolerance except the two noted in DESIGN.md section 3.  Restated from the published three-stage estimator
 (Muthen 1984; Olsson 1979; Olsson, Drasgow & Dorans 1982) in the outer-product form used by
 lavaan's muthen1984(), which OpenMx's omxData::estimateObservedStats states it follows:
   stage 1  per variable given its exogenous predictors: OLS (continuous; ML variance /N) or

@@ -4,8 +4,11 @@
 definition variables), 421-437 (raw data, gxe product columns)).  Only tests/, smoke() and the
 cpu_baseline leg of bench.py may import this.
 
-PARITY UNPINNED: the arithmetic lives in OpenMx (not in the reference tree, no R here).  What is
-restated is full-information maximum likelihood for continuous manifest variables as OpenMx
+PARITY WEAKLY PINNED: the arithmetic lives in OpenMx (not in the reference tree, no R here).  The one reference
+assertion on an ML fit, tests/testthat/test-model.R:68-79 (the P values of buildItem under ML correlate 1 +- 1e-3
+with those under WLS, which are pinned absolutely), is reproduced in tests/test_reference_pins.py on the R-RNG replay
+of that test's phenotypes; no reference test pins a multi-item ML estimate.  What is restated is full-information
+maximum likelihood for continuous manifest variables as OpenMx
 defines it:
   -2 lnL = sum_i [ p_i log 2 pi + log |Sigma_i| + (y_i - mu_i)' Sigma_i^-1 (y_i - mu_i) ]
 with Sigma_i, mu_i the model-implied moments filtered to the variables observed for row i, and

@@ -286,6 +286,40 @@ def test_multigroup_independent_groups(engine, tmp_path):
             assert np.allclose(both[name], logs[k][name], rtol=1e-12, equal_nan=True)
             assert np.allclose(both[f"V{name}:{name}"], logs[k][f"V{name}:{name}"], rtol=1e-12, equal_nan=True)
     assert np.allclose(both["fit"], logs[1]["fit"] + logs[2]["fit"])
+    # ... and an independent *joint* fit: mxFitFunctionMultigroup minimises the sum of the groups' WLS fit functions
+    # over the concatenated parameter vector; a generic optimiser on that sum (no knowledge that it separates) must
+    # land on the multigroup log's estimates (tests/testthat/test-multigroup.R:38, tolerance 1e-4)
+    import fit_oracle as fo
+    from scipy import optimize
+    from gwsem_b200.gwas import model_columns
+    from gwsem_b200.model import flatten
+    parts = []
+    for k in (1, 2):
+        flat = flatten(groups[k - 1])
+        data, _ = model_columns(groups[k - 1])
+        geno = np.load(os.path.join(os.path.dirname(EXTDATA), f"group{k}_bed.npz"))["geno"]
+        parts.append((flat, data, geno, fo.FlatRAM(flat)))
+    for row, snp in zip(both.to_dict("records"), (0, 1, 2)):
+        pieces = []
+        for flat, data, geno, ram in parts:
+            X = fo.snp_columns(flat, data, geno[snp])
+            sv, gamma, n = fo.cumulants_stats(X)
+            pieces.append((ram, sv, n * np.linalg.inv(gamma), len(flat["par_names"])))
+
+        def joint(theta):
+            total, at = 0.0, 0
+            for ram, sv, W, P in pieces:
+                r = sv - fo.sigma_cumulants(ram, theta[at:at + P])
+                total += r @ W @ r
+                at += P
+            return total
+
+        x0 = np.concatenate([np.asarray(flat["par_start"], float) for flat, *_ in parts])
+        best = optimize.minimize(joint, x0, method="Nelder-Mead", options=dict(xatol=1e-10, fatol=1e-14, maxiter=20000, maxfev=20000))
+        names = [n for flat, *_ in parts for n in flat["par_names"]]
+        assert best.fun == pytest.approx(row["fit"], rel=1e-6, abs=1e-9)
+        for nme, v in zip(names, best.x):
+            assert row[nme] == pytest.approx(v, rel=1e-4, abs=1e-6), (snp, nme)
     shared = MultigroupModel("mg2", groups[0], mxRename(groups[0], "again"))
     with pytest.raises(NotImplementedError, match="shared"):
         GWAS(shared, {"sample1": os.path.join(EXTDATA, "group1.bed"), "again": os.path.join(EXTDATA, "group1.bed")}, out, SNP=[1])
