@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(kT, 2)
   __shared__ double sums_sh[J][3];
   __shared__ int done_sh;
   const int snp = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (!DOSAGE && mp.se_done && mp.se_done[snp]) return;   // the series path (marg_series.cu) has written this record
   double* out = summary + (int64_t)snp * mp.sum_stride;
   int n;
   double dn, mu, var;

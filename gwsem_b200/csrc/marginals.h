@@ -74,6 +74,24 @@ struct MargProgram {
   int cs_nf = 0;
   const double* cs_sums = nullptr;
   const double* cs_tot = nullptr;
+  // Series path (marg_series.cu): for hardcalls without a missing call every SNP-dependent statistic is a power series
+  // in rho_j whose coefficients are polynomials in the standardised genotype (Mehler expansion), i.e. a combination of
+  // genotype-class sums of SNP-independent per-person features.  se_sums[snp][2][se_nf] (het, hom ALT; per launch),
+  // se_tot[se_nf] the sums over all included people; feature offsets below (pair tables in marg_series.h).
+  // se_done[snp] = 1: the record of this SNP is complete, marg_stats_kernel leaves at once.
+  int se_nf = 0;
+  const double* se_sums = nullptr;
+  const double* se_tot = nullptr;
+  const double* se_err = nullptr;            // [J][10]: second moments of the first neglected coefficients (acceptance bound)
+  uint8_t* se_done = nullptr;
+  int se_o_psi[kMargMaxItems] = {0};         // [w = 0 (weight 1), 1 + b (SC0 column b)][8 pairs]
+  int se_o_hi[kMargMaxItems] = {0};          // psi, weight 1, orders 4 and 5: 7 pairs
+  int se_o_f3[kMargMaxItems] = {0};          // 5 pairs
+  int se_o_thr[kMargMaxItems] = {0};         // [threshold][8 pairs]
+  int se_o_slope[kMargMaxItems] = {0};       // [covariate][8 pairs]
+  int se_o_diag[kMargMaxItems] = {0};        // psi_j^2: 10 terms
+  int se_o_cross = 0;                        // [pair (a > b), column-major lower triangle][27 terms]
+  int se_o_sc0 = 0;                          // plain SC0 columns: q0
   // summary record per SNP (doubles)
   int sum_stride = 0, o_rho = 0, o_a22 = 0, o_a21snp = 0, o_a21item = 0, o_bdd = 0, o_bd0 = 0;
   int o_msum = 0, o_mmat = 0;  // missing-call people: sum of their item-side score rows, and of the outer products

@@ -61,7 +61,10 @@ struct gwsem_model {
   gwsem::MarginalsHost mh;
   gwsem::MargProgram mp;
   gwsem::ExactProgram ex;   // marg_exact_kernel: SNPs with a missing call (marg_mode 0), every SNP (marg_mode 3)
-  gwsem::DeviceBuffer<double> d_summary, d_cs_sums, d_full;
+  gwsem::DeviceBuffer<double> d_summary, d_cs_sums, d_full, d_se_sums;
+  gwsem::DeviceBuffer<uint8_t> d_se_done;
+  const int8_t* d_seq = nullptr;          // marginals: digits of the series-path features (tcgen05 layout)
+  const double* d_se_inv_scale = nullptr;
   cudaStream_t side_stream = nullptr;   // marg_exact_kernel next to marg_stats_kernel
   cudaEvent_t ev_side_go = nullptr, ev_side_done = nullptr;
   const int8_t* d_csq = nullptr;          // marginals: digits of the series products (tcgen05 layout)

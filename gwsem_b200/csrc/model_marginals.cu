@@ -14,6 +14,11 @@
 using namespace gwsem;
 
 namespace gwsem {
+void build_series_features(MargProgram& mp, int n_src, int n_pad, const std::vector<uint8_t>& inc,
+                           const std::vector<double>& zz, const std::vector<uint8_t>& cat, const std::vector<double>& X,
+                           const std::vector<double>& sc0, std::vector<int8_t>& packed, std::vector<double>& inv_scale,
+                           std::vector<double>& tot, std::vector<double>& err);
+void launch_marg_series(gwsem_engine* e, const MargProgram& mp, const int32_t* d_counts, int n_snps, double* d_summary);
 size_t marg_exact_smem_bytes(const ExactProgram& ex);
 void launch_marg_exact(gwsem_engine* e, const ExactProgram& ex, const uint8_t* d_rows, int64_t pitch, int n_snps, int n_src,
                        const uint8_t* d_inc8, const int32_t* d_counts, int plink1, const double* d_geno, int n_pad,
@@ -421,6 +426,29 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
       mp.cs_nf = nF;
     }
   }
+  // Series path (marg_series.cu): every SNP-dependent statistic of a call-complete hardcall SNP from genotype-class sums
+  // of per-person series coefficients (all items ordinal; GWSEM_NO_SERIES=1 switches it off, an A/B aid)
+  mp.se_nf = 0;
+  d_seq = nullptr;
+  {
+    bool all_ordinal = J > 0;
+    for (int j = 0; j < J; ++j) all_ordinal = all_ordinal && mh.items[j].n_cat > 0;
+    static const bool off = getenv("GWSEM_NO_SERIES") != nullptr;
+    if (all_ordinal && !off && mh.q0 <= 64) {
+      std::vector<uint8_t> inc(n_pad, 0);
+      for (int s2 = 0; s2 < n_src; ++s2) {
+        const int r = dest_of[s2];
+        inc[s2] = r >= 0 && row_ok[r];
+      }
+      std::vector<int8_t> packed;
+      std::vector<double> inv, tot, err;
+      build_series_features(mp, n_src, n_pad, inc, zz, cat, X, sc0, packed, inv, tot, err);
+      d_seq = up(pool, packed, st);
+      d_se_inv_scale = up(pool, inv, st);
+      mp.se_tot = up(pool, tot, st);
+      mp.se_err = up(pool, err, st);
+    }
+  }
   mp.cat = up(pool, cat, st);
   mp.X = up(pool, X, st);
   mp.B00 = up(pool, mh.B00, st);
@@ -627,6 +655,16 @@ void gwsem_model::run_marginals(const uint8_t* d_packed, int64_t pitch, const do
     }
     engine->stream = main_stream;
     GW_CUDA(cudaEventRecord(ev_side_done, side_stream));
+  }
+  mpl.se_done = nullptr;
+  if (!d_geno && mp.se_nf > 0) {
+    // call-complete SNPs with a small correlation: the whole record from class sums, no pass over people
+    d_se_sums.ensure((size_t)n * 2 * mp.se_nf);
+    d_se_done.ensure(n);
+    launch_class_sums_tc5(engine, d_packed, pitch, n, plink1, layout, d_seq, d_se_inv_scale, mp.se_nf, d_se_sums.p, nullptr);
+    mpl.se_sums = d_se_sums.p;
+    mpl.se_done = d_se_done.p;
+    launch_marg_series(engine, mpl, d_counts.p, n, d_summary.p);
   }
   launch_marg_stats(engine, mpl, d_packed, pitch, n, n_src, layout.d_inc8, d_geno ? nullptr : d_counts.p, plink1, d_geno,
                     n_pad, d_summary.p);

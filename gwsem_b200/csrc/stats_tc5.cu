@@ -370,6 +370,22 @@ void tc5_pack_features(const std::vector<std::vector<int64_t>>& q, int n_pad, co
   }
 }
 
+// One 64-column chunk of the same layout from q[feature in chunk][n_pad] (marg_series.cu packs its chunks in parallel)
+void tc5_pack_chunk(const int64_t* q, int n_in_chunk, int n_pad, int8_t* chunk_base) {
+  const int ncol = 64;
+  for (int fi = 0; fi < n_in_chunk; ++fi)
+    for (int i = 0; i < n_pad; ++i) {
+      int64_t v = q[(size_t)fi * n_pad + i];
+      if (v == 0) continue;
+      for (int d = 0; d < 4; ++d) {
+        const int64_t digit = ((v + 128) & 255) - 128;
+        chunk_base[tc5_offset(ncol, i / 32, fi * 4 + d, i % 32)] = (int8_t)digit;
+        v = (v - digit) >> 8;
+      }
+      if (v != 0) fail("series feature does not fit four balanced base-256 digits");
+    }
+}
+
 void launch_class_sums_tc5(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
                            const PeopleLayout& pl, const int8_t* d_featq, const double* d_inv_scale, int n_feat,
                            double* d_sums, int32_t* d_counts, int32_t* d_miss_list, int32_t* d_miss_n) {
