@@ -7,6 +7,8 @@
 //   model-implied vector: RAM moments conditional on the exogenous covariates, ordinal rows
 //   standardised by the implied sd; damped Gauss-Newton with the analytic Jacobian.
 // Mirrors oracle/marginals_oracle.py (fit_snp_marginals).
+#include <algorithm>
+
 #include "common.h"
 #include "fit_device.cuh"
 #include "kernels.h"
@@ -98,14 +100,49 @@ void launch_marg_fit(gwsem_engine* e, const FitProgram& fp, const MargProgram& m
   // each of them keep its issue slots busier than one warp per SNP did
   if (per > 227 * 1024) fail("marginals model too large for the per-SNP fit kernel (%zu bytes of scratch)", per);
   const size_t smem = per;
+  // Records assembled from the SNP-independent item side go through the structured one-warp kernel (GWSEM_FIT_GENERIC=1
+  // keeps everything on the generic one, an A/B aid); full records (marg_exact) stay on the generic kernel.
+  static const bool generic_only = getenv("GWSEM_FIT_GENERIC") != nullptr;
+  MargProgram mpl = mp;
+  mpl.fast_fit = 0;
+  if (!generic_only && !mp.full_all && d_summary && mp.n_a > 0 && mp.Wcc) {
+    const int D = 2 + mp.J;
+    const size_t fper = ((size_t)marg_ws(fp.p, fp.nv).total + mf32::fast_layout(mp.nt, D, mp.q0, mp.n_stat, fp.P, mp.n_a, mp.n_b, mp.n_beta).total) * sizeof(double);
+    const size_t tables = (size_t)mf32::fast_table_bytes(fp, mp);
+    static const int warps_env = getenv("GWSEM_FIT_WARPS") ? atoi(getenv("GWSEM_FIT_WARPS")) : 0;   // tuning aid
+    int warps = warps_env > 0 ? warps_env : 8;
+    while (warps > 1 && warps * fper + tables > 225 * 1024) --warps;
+    if (warps * fper + tables <= 225 * 1024) {
+      const size_t fsmem = warps * fper + tables;
+      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (225 * 1024) / (fsmem + 2048)));
+      const int grid = std::min((n_snps + warps - 1) / warps, e->sm_count * per_sm);
+      mpl.fast_fit = 1;
+      static const bool diag = getenv("GWSEM_FIT_DIAG") != nullptr;
+      mpl.diag = diag;
+      e->prof_begin(kFamFit);
+      GW_CUDA(cudaFuncSetAttribute(mf32::marg_fit_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+      mf32::marg_fit_fast_kernel<<<grid, 32 * warps, fsmem, e->stream>>>(fp, mpl, n_snps, d_summary, d_maf, d_res);
+      GW_CUDA(cudaGetLastError());
+      e->prof_end(kFamFit);
+      e->launches++;
+      if (diag) {
+        unsigned long long h[8], z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        GW_CUDA(cudaStreamSynchronize(e->stream));
+        GW_CUDA(cudaMemcpyFromSymbol(h, mf32::g_fast_clk, sizeof(h)));
+        GW_CUDA(cudaMemcpyToSymbol(mf32::g_fast_clk, z, sizeof(z)));
+        fprintf(stderr, "marg_fit_fast: %d SNPs, mean kcycles acov rows %.1f, gamma %.1f, iterations %.1f (%.2f), eliminated %.1f, vcov %.1f; %zu B of scratch\n",
+                n_snps, h[0] / 1e3 / n_snps, h[1] / 1e3 / n_snps, h[2] / 1e3 / n_snps, (double)h[6] / n_snps, h[3] / 1e3 / n_snps, h[4] / 1e3 / n_snps, fper);
+      }
+    }
+  }
   static const bool one_warp = getenv("GWSEM_FIT_ONE_WARP") != nullptr;   // A/B aid: the one-warp-per-SNP kernel
   e->prof_begin(kFamFit);
   if (one_warp) {
     GW_CUDA(cudaFuncSetAttribute(mf32::marg_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mf32::marg_fit_kernel<<<n_snps, 32, smem, e->stream>>>(fp, mp, n_snps, d_summary, d_maf, d_res);
+    mf32::marg_fit_kernel<<<n_snps, 32, smem, e->stream>>>(fp, mpl, n_snps, d_summary, d_maf, d_res);
   } else {
     GW_CUDA(cudaFuncSetAttribute(mf128::marg_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mf128::marg_fit_kernel<<<n_snps, 128, smem, e->stream>>>(fp, mp, n_snps, d_summary, d_maf, d_res);
+    mf128::marg_fit_kernel<<<n_snps, 128, smem, e->stream>>>(fp, mpl, n_snps, d_summary, d_maf, d_res);
   }
   GW_CUDA(cudaGetLastError());
   e->prof_end(kFamFit);

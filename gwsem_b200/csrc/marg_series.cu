@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(kWarps * 32)
   }
   __syncwarp();
   // ---- the correlation of every item: root of the score polynomial sum_m rho^m a_m
-  bool good = true;
+  bool good = true, start_ok = true;
   if (lane < J) {
     const int j = lane;
     double a[kM + 1];
@@ -346,6 +346,7 @@ __global__ void __launch_bounds__(kWarps * 32)
       if (fabs(step) < 1e-15) { conv = true; break; }
     }
     good = conv;
+    double rel4 = 0.0;
     if (good) {
       // first neglected term of psi against psi at rho = 0, in mean square over people
       const double* E = mp.se_err + 10 * j;
@@ -357,13 +358,20 @@ __global__ void __launch_bounds__(kWarps * 32)
       }
       const double r2 = rho * rho, r8 = r2 * r2 * r2 * r2;
       good = r8 * e2 <= tol2 * E[6];
+      rel4 = sqrt(r8 * e2 / E[6]);
     }
+    // The root itself comes from the order-5 series: its first neglected term is about 1.5 rho^2 times the order-4 one
+    // (measured on the C3 items, scripts/series_proto.py).  When that is small the root is a Newton starting point
+    // within marg_stats_kernel's own stopping distance, and that kernel goes straight to its Gamma pass.
+    start_ok = conv && 1.5 * rho * rho * rel4 <= 1e-5;
     double pw = 1.0;
     for (int m = 0; m <= kM; ++m) { w.rp[j][m] = pw; pw *= rho; }
   }
   good = __all_sync(0xffffffffu, good);
   if (!good) {
-    if (lane == 0) mp.se_done[snp] = 0;
+    start_ok = __all_sync(0xffffffffu, start_ok);
+    if (start_ok && lane < J) summary[(int64_t)snp * mp.sum_stride + mp.o_rho + lane] = w.rp[lane][1];
+    if (lane == 0) mp.se_done[snp] = start_ok ? 2 : 0;
     return;
   }
   __syncwarp();
@@ -468,7 +476,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 void launch_marg_series(gwsem_engine* e, const MargProgram& mp, const int32_t* d_counts, int n_snps, double* d_summary) {
   if (n_snps <= 0) return;
   static const double tol = getenv("GWSEM_SERIES_TOL") ? atof(getenv("GWSEM_SERIES_TOL")) : 3e-6;      // tuning aids
-  static const double rho_max = getenv("GWSEM_SERIES_RHOMAX") ? atof(getenv("GWSEM_SERIES_RHOMAX")) : 0.04;
+  static const double rho_max = getenv("GWSEM_SERIES_RHOMAX") ? atof(getenv("GWSEM_SERIES_RHOMAX")) : 0.15;
   e->prof_begin(kFamMargSeries);
   marg_series_kernel<<<(n_snps + kWarps - 1) / kWarps, kWarps * 32, 0, e->stream>>>(mp, d_counts, n_snps, d_summary, tol * tol, rho_max);
   GW_CUDA(cudaGetLastError());

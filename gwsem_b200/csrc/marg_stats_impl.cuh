@@ -168,8 +168,14 @@ __global__ void __launch_bounds__(kT, 2)
   __shared__ double sums_sh[J][3];
   __shared__ int done_sh;
   const int snp = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (!DOSAGE && mp.se_done && mp.se_done[snp]) return;   // the series path (marg_series.cu) has written this record
+  const int se = (!DOSAGE && mp.se_done) ? mp.se_done[snp] : 0;
+  if (se == 1) return;   // the series path (marg_series.cu) has written this record
   double* out = summary + (int64_t)snp * mp.sum_stride;
+  // se == 2: the series path left the roots of its order-5 score polynomials in the record: correlations within this
+  // kernel's own Newton stopping distance of the estimates (read before the record is cleared)
+  double rho_given = 0.0;
+  if (se == 2 && tid < J) rho_given = out[mp.o_rho + tid];
+  __syncthreads();
   int n;
   double dn, mu, var;
   const double* grow = DOSAGE ? geno + (int64_t)snp * n_pad : nullptr;
@@ -228,7 +234,7 @@ __global__ void __launch_bounds__(kT, 2)
 
   // ---- stage 2: Newton on the score of every rho_j (exact second derivative; the outer-product
   // information stands in when the curvature estimate is not negative)
-  if (tid < J) rho_sh[tid] = 0.0;
+  if (tid < J) rho_sh[tid] = se == 2 ? rho_given : 0.0;
   if (tid == 0) done_sh = 0;
   __syncthreads();
   // Iteration 0 is at rho = 0, where the tetrachoric series gives the score and its first two
@@ -243,7 +249,7 @@ __global__ void __launch_bounds__(kT, 2)
   // The series root is O(rho^3) from the estimate: accepted below 0.012 (2e-6), so that the scores of the Gamma pass,
   // taken at the accepted point, stand within 1e-5 of an SE of those at the estimate.
   constexpr double kNewtonStop = 3e-5, kFinalClamp = 3e-4, kSeriesMax = 0.012;
-  for (int iter = 0; iter < 30; ++iter) {
+  for (int iter = 0; iter < 30 && se != 2; ++iter) {
     double s1[J], s2[J], s3[J], rh[J];
 #pragma unroll
     for (int j = 0; j < J; ++j) { s1[j] = s2[j] = s3[j] = 0.0; rh[j] = rho_sh[j]; }

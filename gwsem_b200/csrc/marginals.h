@@ -51,6 +51,10 @@ struct MargProgram {
   const double* X = nullptr;                 // [n_pad][Kp]
   const double* B00 = nullptr;               // [q0][q0]
   const double* A21ii = nullptr;             // [npii][n1]
+  const double* Wcc = nullptr;               // [q0][q0]: inverse of the item-side block of Muthen's A (marg_fit_fast_kernel)
+  int diag = 0;                              // GWSEM_FIT_DIAG: per-phase cycle counters
+  int fast_fit = 0;                          // set per launch: marg_fit_fast_kernel takes the SNPs without a full record
+  const double* acov_cc = nullptr;           // [q0][q0]: Wcc B00 Wcc', the SNP-independent block of acov(theta)
   const double* theta1 = nullptr;            // n1 stage-1 estimates of the items, in column order
   const double* rho_ii = nullptr;            // npii
   const double* H11 = nullptr;               // exact stage-1 information of the items, blocks of n_par^2 back to back

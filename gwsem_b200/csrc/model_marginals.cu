@@ -456,6 +456,59 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
   mp.theta1 = up(pool, theta1, st);
   mp.rho_ii = up(pool, mh.rho, st);
   {
+    // item-side block of Muthen's A (block-diagonal stage-1 information, polychoric rows A21 | diagonal) -> W = A_cc^-1
+    // and acov_cc = W B00 W', the SNP-independent part of acov(theta) (marg_fit_fast_kernel)
+    const int q = mh.q0, n1 = mh.n1;
+    std::vector<double> Acc((size_t)q * q, 0.0), W((size_t)q * q, 0.0), T((size_t)q * q, 0.0), AC((size_t)q * q, 0.0);
+    auto item_of = [&](int c) { int j = 0; while (j + 1 < J && c >= mh.col_of[j + 1]) ++j; return j; };
+    for (int x = 0; x < q; ++x)
+      for (int y = 0; y < q; ++y) {
+        double a = 0.0;
+        if (x < n1 && y < n1) { if (item_of(x) == item_of(y)) a = mh.B00[(size_t)x * q + y]; }
+        else if (x >= n1) {
+          if (y < n1) a = mh.A21[(size_t)(x - n1) * n1 + y];
+          else if (y == x) a = mh.B00[(size_t)x * q + x];
+        }
+        Acc[(size_t)x * q + y] = a;
+        W[(size_t)x * q + y] = x == y ? 1.0 : 0.0;
+      }
+    bool ok = true;
+    for (int c = 0; c < q && ok; ++c) {   // Gauss-Jordan with partial pivoting
+      int piv = c;
+      for (int r = c + 1; r < q; ++r)
+        if (std::fabs(Acc[(size_t)r * q + c]) > std::fabs(Acc[(size_t)piv * q + c])) piv = r;
+      if (!(std::fabs(Acc[(size_t)piv * q + c]) > 0.0)) { ok = false; break; }
+      if (piv != c)
+        for (int k = 0; k < q; ++k) { std::swap(Acc[(size_t)c * q + k], Acc[(size_t)piv * q + k]); std::swap(W[(size_t)c * q + k], W[(size_t)piv * q + k]); }
+      const double inv = 1.0 / Acc[(size_t)c * q + c];
+      for (int k = 0; k < q; ++k) { Acc[(size_t)c * q + k] *= inv; W[(size_t)c * q + k] *= inv; }
+      for (int r = 0; r < q; ++r) {
+        if (r == c) continue;
+        const double f = Acc[(size_t)r * q + c];
+        if (f == 0.0) continue;
+        for (int k = 0; k < q; ++k) { Acc[(size_t)r * q + k] -= f * Acc[(size_t)c * q + k]; W[(size_t)r * q + k] -= f * W[(size_t)c * q + k]; }
+      }
+    }
+    mp.Wcc = nullptr;
+    mp.acov_cc = nullptr;
+    if (ok) {
+      for (int x = 0; x < q; ++x)
+        for (int y = 0; y < q; ++y) {
+          double v = 0.0;
+          for (int k = 0; k < q; ++k) v += W[(size_t)x * q + k] * mh.B00[(size_t)k * q + y];
+          T[(size_t)x * q + y] = v;
+        }
+      for (int x = 0; x < q; ++x)
+        for (int y = 0; y <= x; ++y) {
+          double v = 0.0;
+          for (int k = 0; k < q; ++k) v += T[(size_t)x * q + k] * W[(size_t)y * q + k];
+          AC[(size_t)x * q + y] = AC[(size_t)y * q + x] = v;
+        }
+      mp.Wcc = up(pool, W, st);
+      mp.acov_cc = up(pool, AC, st);
+    }
+  }
+  {
     std::vector<double> h11;
     for (int j = 0; j < J; ++j) {
       mp.h11_of[j] = (int)h11.size();
