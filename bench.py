@@ -4,19 +4,22 @@
 
 Headline workload (default, `--workload c3`): BASELINE.json configs[2], the configuration the
 north-star target is quoted on -- buildOneFac WLS, 3 ordinal items (3/4/5 levels) + 5 PC covariates,
-50,000 people, packed hardcalls; 32,768 SNPs per step per GPU (the 1M-SNP file streams through in
-such batches; ranks own disjoint SNP shards: weak scaling, no collective on the data path).
-1 % of the SNPs are causal (noisy copies of four variants that drive the factor), so the exact
-Newton passes of the statistics kernel are timed, not only its null-SNP branch.
+50,000 people, packed hardcalls; 37,888 SNPs per step per GPU (= 148 SMs x 2 waves of 128-SNP CTAs;
+the 1M-SNP file streams through in such batches; ranks own disjoint SNP shards: weak scaling, no
+collective on the data path).
+1 % of the SNPs are causal (noisy copies of four variants that drive the factor): those leave the
+series path and take the per-person statistics kernel, so both are timed.
 One step = one pass of the hot path over the rank's batch: class counts, tcgen05 class sums of the
-series products, marg_stats (per-SNP polyserials + Muthen score products), marg_fit (asymptotic
-covariance, WLS fit, SEs).
+per-person series coefficients (33 launches of 128 digit columns), marg_series (per-SNP assembly of the
+polyserials + Muthen score products), marg_stats (causal SNPs), marg_fit (asymptotic covariance, WLS
+fit, SEs).
 
   value         SNPs/s with the packed genotypes already resident in HBM (device-pointer C ABI)
   e2e           SNPs/s through the host-buffer C ABI call (gwsem_fit_2bit): pinned host packed rows
                 -> H2D -> kernels -> D2H of every result array, all inside the timed region
-  roofline      dominant kernel (marg_stats) against the FP64 FMA peak measured in the same run
-                (gwsem_engine_fp64_peak); algorithmic flops = SURVEY.md section 8d: 1,624 N per SNP
+  roofline      dominant kernel (class_sums_tc5_kernel<128,512>: exact int8 contraction on tcgen05) against the
+                tensor peak: int8 ops of the launch / CUDA-event launch time; the FP64 figure SURVEY.md section
+                8d counts for the per-person algorithm (1,624 N flop per SNP) rides along as fp64_equivalent
   cpu_baseline  the same path on the host cores: numpy restatement of the OpenMx WLS marginals fit
                 (oracle/marginals_oracle.py, which recomputes every statistic per SNP as OpenMx does;
                 vectorised over people -- the interpreter is < 2 % of its time)
@@ -43,12 +46,12 @@ UNIT = "SNPs/s"
 FLOP_PER_PERSON_SNP = 1624
 WORKLOADS = {
     "c3": dict(
-        n_people=50_000, snps=32_768, causal_fraction=0.01,
+        n_people=50_000, snps=37_888, causal_fraction=0.01,
         metric="SNPs/sec per model (oneFac WLS, 3 ordinal items + 5 PCs, 50k people)",
         workload=("C3: buildOneFac, 3 ordinal items (3/4/5 levels) + 5 PC covariates, WLS marginals, synthetic 50k people x "
-                  "32,768 SNPs of packed hardcalls per step per GPU (the 1M-SNP file streams through in such batches); "
+                  "37,888 SNPs of packed hardcalls per step per GPU (the 1M-SNP file streams through in such batches); "
                   "1 % causal SNPs"),
-        kernel="marg_stats_kernel<3,false,1>", family="marg_stats", bound="fp64"),
+        kernel="class_sums_tc5_kernel<128,512,false>", family="series_sums", bound="tensor"),
     "c2": dict(
         n_people=100_000, snps=100_000, causal_fraction=0.0,
         metric="SNPs/sec per model (buildItem WLS, 100k people)",
@@ -72,6 +75,16 @@ def measured_peaks():
         with open(path) as f:
             return json.load(f)["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_tensor_peak():
+    """Dense int8 tensor peak in TOP/s: twice the driver-measured cuBLAS bf16 burst figure (the nominal int8 : bf16 ratio
+    of the part; MEASURED_PEAKS.json holds no int8 number), else twice the recipe's fallback."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return 2.0 * json.load(f)["bf16_tflops"], "2 x measured bf16 burst (MEASURED_PEAKS.json); int8 : bf16 = 2 nominal, no int8 figure is measured"
+    return 2.0 * 1590.0, "2 x fallback bf16 (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -514,6 +527,31 @@ def roofline(which, m, n_snps, steps, fp64_peak):
     w = WORKLOADS[which]
     n_k, ms_k = m["prof"][w["family"]]
     share = {k: v[1] / m["ms"] for k, v in m["prof"].items() if v[0]}
+    if w["bound"] == "tensor":
+        # one launch = 128 digit columns (32 features x 4 base-256 digits) x 2 genotype classes x people x SNPs, 2 ops each
+        n_pad = (w["n_people"] + 31) // 32 * 32
+        per_launch = 2.0 * 2 * 128 * n_pad * n_snps
+        achieved = per_launch / (ms_k / max(n_k, 1) / 1e3) / 1e12 if n_k else None
+        peak, src = measured_tensor_peak()
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r02_series_sums_traffic.json")
+        if os.path.exists(tpath) and n_k:
+            with open(tpath) as f:
+                t = json.load(f)
+            traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["snps_in_launch"] * n_snps
+        step_ms = m["ms"] / steps
+        fp64_eq = FLOP_PER_PERSON_SNP * w["n_people"] * n_snps / (step_ms / 1e3) / 1e12
+        return {"bound": "tensor", "kernel": w["kernel"], "achieved": achieved, "peak": peak, "unit": "TOP/s",
+                "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": src,
+                "launches_timed": n_k, "launches_per_step": n_k / steps, "kernel_ms_share": share,
+                "algorithmic_ops_per_launch": per_launch,
+                "fp64_equivalent": {"tflops": fp64_eq, "fp64_peak_tflops": fp64_peak, "ratio": fp64_eq / fp64_peak if fp64_peak else None,
+                                    "note": "SURVEY.md section 8(d)'s 1,624 N FP64 flop per SNP (the per-person algorithm the reference "
+                                            "runs) x SNPs / whole-step time, against the DFMA peak measured in this run: above 1 because "
+                                            "the series path replaces the pass over people by class sums"},
+                "note": "achieved = int8 multiply-adds of one launch of the exact class-sum contraction (one-hot genotype classes x "
+                        "base-256 digits of the per-person series coefficients) / CUDA-event launch time, averaged over the timed "
+                        "launches; packed genotypes are re-read by every launch (12,500 B per SNP), the digit planes are L2-resident"}
     if w["bound"] == "fp64":
         per_launch = FLOP_PER_PERSON_SNP * w["n_people"] * n_snps * steps / max(n_k, 1)
         achieved = per_launch / (ms_k / max(n_k, 1) / 1e3) / 1e12 if n_k else None

@@ -248,7 +248,9 @@ void gwsem_model_destroy(gwsem_model* m) {
   cudaStreamSynchronize(m->engine->stream);
   if (m->side_stream) { cudaStreamSynchronize(m->side_stream); cudaStreamDestroy(m->side_stream); }
   if (m->copy_stream) { cudaStreamSynchronize(m->copy_stream); cudaStreamDestroy(m->copy_stream); }
-  for (cudaEvent_t ev : {m->ev_side_go, m->ev_side_done, m->ev_copied[0], m->ev_copied[1], m->ev_done[0], m->ev_done[1]})
+  if (m->out_stream) { cudaStreamSynchronize(m->out_stream); cudaStreamDestroy(m->out_stream); }
+  for (cudaEvent_t ev : {m->ev_side_go, m->ev_side_done, m->ev_copied[0], m->ev_copied[1], m->ev_done[0], m->ev_done[1],
+                         m->ev_fitted[0], m->ev_fitted[1], m->ev_out[0], m->ev_out[1]})
     if (ev) cudaEventDestroy(ev);
   delete m;
 }

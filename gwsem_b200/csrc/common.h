@@ -73,7 +73,7 @@ struct DeviceBuffer {
 }  // namespace gwsem
 
 namespace gwsem {
-enum KernelFamily { kFamClassSums = 0, kFamCountMissing = 1, kFamFit = 2, kFamDecode = 3, kFamMargStats = 4, kFamMargExact = 5, kFamMargSeries = 6, kFamCount = 8 };
+enum KernelFamily { kFamClassSums = 0, kFamCountMissing = 1, kFamFit = 2, kFamDecode = 3, kFamMargStats = 4, kFamMargExact = 5, kFamMargSeries = 6, kFamSeriesSums = 7, kFamCount = 8 };
 }
 
 struct gwsem_engine {

@@ -136,7 +136,6 @@ void parallel_for(int n, Body body) {
 
 }  // namespace
 
-void tc5_pack_chunk(const int64_t* q, int n_in_chunk, int n_pad, int8_t* chunk_base);   // stats_tc5.cu
 
 // Builds the per-person features in genotype-file order and packs them as int8 digits for the tcgen05 class-sum kernel.
 // zz [n_pad][J][5], cat [n_pad][J], X [n_pad][Kp], sc0 [.][q0p] as laid out for marg_stats_kernel; inc[s] = person enters
@@ -170,8 +169,9 @@ void build_series_features(MargProgram& mp, int n_src, int n_pad, const std::vec
       for (int p = 0; p < kCross; ++p) feats.push_back({6, a, b, p});
   mp.se_o_sc0 = (int)feats.size();
   for (int b = 0; b < q0; ++b) feats.push_back({7, 0, b, 0});
-  while (feats.size() % 16) feats.push_back({-1, 0, 0, 0});   // whole 64-column chunks (no indicator slot)
-  const int nf = (int)feats.size(), chunks = nf / 16;
+  constexpr int kCF = kTcWideFeatures;
+  while (feats.size() % kCF) feats.push_back({-1, 0, 0, 0});   // whole 128-column chunks
+  const int nf = (int)feats.size(), chunks = nf / kCF;
   mp.se_nf = nf;
 
   // per person and item: the series
@@ -200,16 +200,16 @@ void build_series_features(MargProgram& mp, int n_src, int n_pad, const std::vec
     }
   }
 
-  const size_t chunk_bytes = imma_feature_bytes(nf, n_pad) / chunks;
+  const size_t chunk_bytes = tc5_wide_chunk_bytes(n_pad);
   packed.assign(chunk_bytes * chunks, 0);
   inv_scale.assign(nf, 0.0);
   tot.assign(nf, 0.0);
   const int q0p = mp.q0p, Kp = mp.Kp;
   parallel_for(chunks, [&](int c) {
-    std::vector<double> h((size_t)16 * n_pad, 0.0);
-    std::vector<int64_t> q((size_t)16 * n_pad, 0);
-    for (int fi = 0; fi < 16; ++fi) {
-      const Feature f = feats[c * 16 + fi];
+    std::vector<double> h((size_t)kCF * n_pad, 0.0);
+    std::vector<int64_t> q((size_t)kCF * n_pad, 0);
+    for (int fi = 0; fi < kCF; ++fi) {
+      const Feature f = feats[c * kCF + fi];
       if (f.type < 0) continue;
       double* hv = &h[(size_t)fi * n_pad];
       CrossTerm ct = {0, 0, 0};
@@ -254,16 +254,16 @@ void build_series_features(MargProgram& mp, int n_src, int n_pad, const std::vec
       int ex = 0;
       if (mx > 0) std::frexp(mx, &ex);
       const double sc = std::ldexp(1.0, 30 - ex);
-      inv_scale[c * 16 + fi] = std::ldexp(1.0, ex - 30);
+      inv_scale[c * kCF + fi] = std::ldexp(1.0, ex - 30);
       long double acc = 0;
       int64_t* qv = &q[(size_t)fi * n_pad];
       for (int s = 0; s < n_src; ++s) {
         qv[s] = std::llrint(hv[s] * sc);
         acc += (long double)qv[s];
       }
-      tot[c * 16 + fi] = (double)acc * inv_scale[c * 16 + fi];
+      tot[c * kCF + fi] = (double)acc * inv_scale[c * kCF + fi];
     }
-    tc5_pack_chunk(q.data(), 16, n_pad, packed.data() + (size_t)c * chunk_bytes);
+    tc5_pack_chunk(q.data(), kCF, n_pad, packed.data() + (size_t)c * chunk_bytes);
   });
 }
 

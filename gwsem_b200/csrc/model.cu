@@ -497,8 +497,8 @@ gwsem_result gwsem_model::device_result() {
   return r;
 }
 
-void gwsem_model::download_result(const gwsem_result& h, const gwsem_result& d, int n, int offset) {
-  cudaStream_t st = engine->stream;
+void gwsem_model::download_result(const gwsem_result& h, const gwsem_result& d, int n, int offset, cudaStream_t on) {
+  cudaStream_t st = on ? on : engine->stream;
   auto dl = [&](void* dst, const void* src, size_t bytes) {
     if (dst) GW_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
   };
@@ -515,7 +515,9 @@ void gwsem_model::download_result(const gwsem_result& h, const gwsem_result& d, 
 
 // Host buffers in, host results out.  The packed rows are cut into chunks that alternate between
 // two HBM staging buffers: the H2D copy of chunk c+1 (copy stream) overlaps the kernels of chunk c
-// (engine stream); results come back once per chunk on the engine stream.
+// (engine stream), and the results of chunk c come back on a third stream while chunk c+1 computes.  A chunk is a
+// whole number of waves of the 128-SNP class-sum CTAs over the SMs (18,944 SNPs on 148 SMs) when the rows are short
+// enough for two such staging buffers.
 void gwsem_model::fit_2bit_host(const uint8_t* packed, int64_t pitch, int n_snps, int plink1, const gwsem_result& h) {
   if (!prepared) prepare(nullptr, n_rows);
   GW_CUDA(cudaSetDevice(engine->device));
@@ -525,13 +527,20 @@ void gwsem_model::fit_2bit_host(const uint8_t* packed, int64_t pitch, int n_snps
   const int64_t dpitch = (std::max<int64_t>(row_bytes, n_pad / 4) + 15) / 16 * 16;
   if (!copy_stream) {
     GW_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    GW_CUDA(cudaStreamCreateWithFlags(&out_stream, cudaStreamNonBlocking));
     for (int b = 0; b < 2; ++b) {
       GW_CUDA(cudaEventCreateWithFlags(&ev_copied[b], cudaEventDisableTiming));
       GW_CUDA(cudaEventCreateWithFlags(&ev_done[b], cudaEventDisableTiming));
+      GW_CUDA(cudaEventCreateWithFlags(&ev_fitted[b], cudaEventDisableTiming));
+      GW_CUDA(cudaEventCreateWithFlags(&ev_out[b], cudaEventDisableTiming));
     }
   }
-  // ~128 MiB of packed rows per chunk
-  const int chunk = (int)std::max<int64_t>(256, std::min<int64_t>(1 << 16, (128ll << 20) / dpitch));
+  // ~128 MiB of packed rows per chunk, rounded to whole waves of 128-SNP CTAs (up to 1 GiB per staging buffer)
+  int chunk = (int)std::max<int64_t>(256, std::min<int64_t>(1 << 16, (128ll << 20) / dpitch));
+  {
+    const int64_t wave = 128ll * engine->sm_count;
+    if (wave * dpitch <= (1ll << 30)) chunk = (int)(std::max<int64_t>(1, (chunk + wave / 2) / wave) * wave);
+  }
   ensure_result_buffers(std::min(chunk, n_snps) * 2);
   for (int b = 0; b < 2; ++b) {
     d_stage2[b].ensure((size_t)std::min(chunk, n_snps) * dpitch + 16);
@@ -539,6 +548,8 @@ void gwsem_model::fit_2bit_host(const uint8_t* packed, int64_t pitch, int n_snps
   }
   GW_CUDA(cudaEventRecord(ev_done[0], st));
   GW_CUDA(cudaEventRecord(ev_done[1], st));
+  GW_CUDA(cudaEventRecord(ev_out[0], st));
+  GW_CUDA(cudaEventRecord(ev_out[1], st));
   int c = 0;
   for (int s0 = 0; s0 < n_snps; s0 += chunk, ++c) {
     const int b = c & 1;
@@ -555,9 +566,14 @@ void gwsem_model::fit_2bit_host(const uint8_t* packed, int64_t pitch, int n_snps
     const size_t o = (size_t)b * std::min(chunk, n_snps);
     r.est += o * P; r.vcov += o * P * P; r.fit += o; r.maf += o; r.n_used += o;
     r.status += o; r.catch_code += o; r.catch_var += o; r.iterations += o;
+    GW_CUDA(cudaStreamWaitEvent(st, ev_out[b], 0));   // the results that lived in this half two chunks ago are on the host
     fit_2bit_device(d_stage2[b].p, dpitch, n, plink1, r);
-    download_result(h, r, n, s0);
     GW_CUDA(cudaEventRecord(ev_done[b], st));
+    GW_CUDA(cudaEventRecord(ev_fitted[b], st));
+    GW_CUDA(cudaStreamWaitEvent(out_stream, ev_fitted[b], 0));
+    download_result(h, r, n, s0, out_stream);
+    GW_CUDA(cudaEventRecord(ev_out[b], out_stream));
   }
   GW_CUDA(cudaStreamSynchronize(st));
+  GW_CUDA(cudaStreamSynchronize(out_stream));
 }

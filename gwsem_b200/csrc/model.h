@@ -40,8 +40,8 @@ struct gwsem_model {
   gwsem::DeviceBuffer<double> d_sums, d_miss, d_R, d_mafs;
   gwsem::DeviceBuffer<int32_t> d_nrows;
   gwsem::DeviceBuffer<uint8_t> d_stage2[2];
-  cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr, out_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_fitted[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   gwsem::DeviceBuffer<double> r_est, r_vcov, r_fit, r_maf;
   gwsem::DeviceBuffer<int32_t> r_n, r_status, r_catch, r_cvar, r_iter;
 
@@ -82,5 +82,5 @@ struct gwsem_model {
   void fit_2bit_host(const uint8_t* packed, int64_t pitch, int n_snps, int plink1, const gwsem_result& h);
   void ensure_result_buffers(int n);
   gwsem_result device_result();
-  void download_result(const gwsem_result& h, const gwsem_result& d, int n, int offset);
+  void download_result(const gwsem_result& h, const gwsem_result& d, int n, int offset, cudaStream_t on = nullptr);
 };

@@ -103,9 +103,10 @@ __global__ void __launch_bounds__(kTcThreads + 32)
   constexpr int kBStage = kBlocks * kBBlock;
   constexpr int kGStage = kSnps * kGRow;
   constexpr int kStage = kGStage + kBStage;
-  constexpr int kCols = 2 * N + 3 * 32 <= 128 ? 128 : 256;   // TMEM allocation (power of two)
-  constexpr int kBufs = (kCols - 2 * N) / 32;                // A buffers in tensor memory: 3 (N = 16) or 4 (N = 64)
+  constexpr int kCols = 2 * N + 3 * 32 <= 128 ? 128 : (2 * N + 3 * 32 <= 256 ? 256 : 512);   // TMEM allocation (power of two)
+  constexpr int kBufs = (kCols - 2 * N) / 32 < 4 ? (kCols - 2 * N) / 32 : 4;   // A buffers in tensor memory: 3 (N = 16) or 4
   static_assert(kBufs == 3 || kBufs == 4, "A ring");
+  static_assert(2 * N + kBufs * 32 <= 512, "tensor memory");
   constexpr unsigned kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((128u >> 4) << 24);
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[kBufs], empty_bar[kBufs];
@@ -324,6 +325,26 @@ void launch_tc5(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_s
 // kernel by IMMA issue + ALU: equal at 16 digit columns (0.70 ms per 65,536 SNPs x 100k people), and the tcgen05
 // kernel wins 1.6x at 64 columns, where mma.sync needs four times the IMMAs for the same expansion.
 // GWSEM_CS_KERNEL=imma|tc5 forces one of them (development aid).
+// Wide chunks (N = 128 digit columns = 32 features per launch) for the series path of the WLS marginals statistics:
+// the one-hot expansion, which bounds the kernel, is shared by twice as many features as in a 64-column launch.
+// d_featq: chunks of tc5_wide_chunk_bytes packed by tc5_pack_chunk; n_feat a multiple of kTcWideFeatures.
+void launch_class_sums_tc5_wide(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
+                                const PeopleLayout& pl, const int8_t* d_featq, const double* d_inv_scale, int n_feat,
+                                double* d_sums) {
+  if (n_snps <= 0 || n_feat <= 0) return;
+  if (n_feat % kTcWideFeatures != 0) fail("wide class sums: %d features (a multiple of %d expected)", n_feat, kTcWideFeatures);
+  if (pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(d_packed) & 15))
+    fail("packed genotype rows must be 16-byte aligned with a pitch that is a multiple of 16 (pitch=%lld)", (long long)pitch);
+  const size_t chunk_bytes = tc5_wide_chunk_bytes(pl.n_pad);
+  const int n_live = (pl.n_pad / 32 + 1) / 2 * 2;
+  for (int f0 = 0, c = 0; f0 < n_feat; f0 += kTcWideFeatures, ++c) {
+    e->prof_begin(kFamSeriesSums);   // one event pair per launch: bench.py's roofline divides by the launch count
+    launch_tc5<kTcWideFeatures * 4, 512>(e, d_packed, pitch, n_snps, plink1, n_live, d_featq + (size_t)c * chunk_bytes, d_inv_scale, f0,
+                                         n_feat, d_sums, nullptr, 0, nullptr, nullptr);
+    e->prof_end(kFamSeriesSums);
+  }
+}
+
 bool cs_use_tc5(int n_feat) {
   const char* v = getenv("GWSEM_CS_KERNEL");   // read when a model is prepared (the digit layout follows the kernel)
   if (v && std::string(v) == "imma") return false;
@@ -370,9 +391,11 @@ void tc5_pack_features(const std::vector<std::vector<int64_t>>& q, int n_pad, co
   }
 }
 
-// One 64-column chunk of the same layout from q[feature in chunk][n_pad] (marg_series.cu packs its chunks in parallel)
+// One chunk of the same layout from q[feature in chunk][n_pad] (marg_series.cu packs its chunks in parallel);
+// kTcWideFeatures features = 128 digit columns per chunk
+size_t tc5_wide_chunk_bytes(int n_pad) { return (size_t)((n_pad / 32 + 31) / 32 * 32) * (kTcWideFeatures * 4) * 32; }
 void tc5_pack_chunk(const int64_t* q, int n_in_chunk, int n_pad, int8_t* chunk_base) {
-  const int ncol = 64;
+  const int ncol = kTcWideFeatures * 4;
   for (int fi = 0; fi < n_in_chunk; ++fi)
     for (int i = 0; i < n_pad; ++i) {
       int64_t v = q[(size_t)fi * n_pad + i];

@@ -35,7 +35,7 @@ class Engine:
     def launches(self):
         return int(lib().gwsem_engine_launch_count(self.h))
 
-    KERNEL_FAMILIES = ("class_sums", "count_missing", "fit", "decode", "marg_stats", "marg_exact", "marg_series", "reserved7")
+    KERNEL_FAMILIES = ("class_sums", "count_missing", "fit", "decode", "marg_stats", "marg_exact", "marg_series", "series_sums")
 
     def profile(self, enable=True):
         check(lib().gwsem_engine_profile(self.h, int(enable)))
