@@ -102,7 +102,7 @@ void launch_marg_fit(gwsem_engine* e, const FitProgram& fp, const MargProgram& m
   const size_t smem = per;
   // Records assembled from the SNP-independent item side go through the structured one-warp kernel (GWSEM_FIT_GENERIC=1
   // keeps everything on the generic one, an A/B aid); full records (marg_exact) stay on the generic kernel.
-  static const bool generic_only = getenv("GWSEM_FIT_GENERIC") != nullptr;
+  const bool generic_only = getenv("GWSEM_FIT_GENERIC") != nullptr;   // read per launch (tests compare both in one process)
   MargProgram mpl = mp;
   mpl.fast_fit = 0;
   if (!generic_only && !mp.full_all && d_summary && mp.n_a > 0 && mp.Wcc) {

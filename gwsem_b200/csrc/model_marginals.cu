@@ -433,7 +433,7 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
   {
     bool all_ordinal = J > 0;
     for (int j = 0; j < J; ++j) all_ordinal = all_ordinal && mh.items[j].n_cat > 0;
-    static const bool off = getenv("GWSEM_NO_SERIES") != nullptr;
+    const bool off = getenv("GWSEM_NO_SERIES") != nullptr;   // read per model: the tests build both variants in one process
     if (all_ordinal && !off && mh.q0 <= 64) {
       std::vector<uint8_t> inc(n_pad, 0);
       for (int s2 = 0; s2 < n_src; ++s2) {

@@ -104,8 +104,8 @@ __global__ void __launch_bounds__(kTcThreads + 32)
   constexpr int kGStage = kSnps * kGRow;
   constexpr int kStage = kGStage + kBStage;
   constexpr int kCols = 2 * N + 3 * 32 <= 128 ? 128 : (2 * N + 3 * 32 <= 256 ? 256 : 512);   // TMEM allocation (power of two)
-  constexpr int kBufs = (kCols - 2 * N) / 32 < 4 ? (kCols - 2 * N) / 32 : 4;   // A buffers in tensor memory: 3 (N = 16) or 4
-  static_assert(kBufs == 3 || kBufs == 4, "A ring");
+  constexpr int kBufs = (kCols - 2 * N) / 32 < 4 ? (kCols - 2 * N) / 32 : 4;   // A buffers in tensor memory: 3 (N = 16) or 4 (a ring of 6 at N = 128 measured slower: 18.5 vs 16.0 ms per 33 launches)
+  static_assert(kBufs == 3 || kBufs == 4 || kBufs == 6, "A ring");
   static_assert(2 * N + kBufs * 32 <= 512, "tensor memory");
   constexpr unsigned kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((128u >> 4) << 24);
   extern __shared__ __align__(128) uint8_t smem[];
@@ -252,6 +252,10 @@ __global__ void __launch_bounds__(kTcThreads + 32)
       if (a < total) do_stage(std::integral_constant<int, 2>{});
       if constexpr (kBufs > 3) {
         if (a < total) do_stage(std::integral_constant<int, 3>{});
+      }
+      if constexpr (kBufs > 4) {
+        if (a < total) do_stage(std::integral_constant<int, 4>{});
+        if (a < total) do_stage(std::integral_constant<int, 5>{});
       }
       phase ^= 1u;
     }

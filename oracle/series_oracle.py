@@ -1,6 +1,13 @@
-"""Development aid: numpy prototype of the rho-series of the polyserial score terms (Mehler expansion), checked against
-the direct formulas of marg_stats_kernel's pair_terms.  Calibrates the truncation order / acceptance bound of the
-class-sum ("series") statistics path."""
+"""TEST INFRASTRUCTURE ONLY (tests/ and development scripts; the product never imports it).
+
+numpy restatement of the rho-series behind gwsem_b200/csrc/marg_series.cu: by Mehler's expansion the rectangle
+probability of an ordinal item given the standardised genotype u is pi(rho, u) = pi(0) sum_k rho^k He_k(u) C_k / k!, so
+the polyserial score psi = d log pi / d rho and its products with d log pi / du, d log pi / dz1, d log pi / dz0 are
+power series in rho whose coefficients are polynomials in u with per-person coefficients.  `direct` holds the closed
+forms (the per-person terms of lavaan's muthen1984 polyserial score, which oracle/marginals_oracle.py restates for the
+reference's WLS marginals statistics, R/model.R:413-436 through OpenMx); tests/test_series_math.py checks one against
+the other, which is what the truncation orders and the acceptance bound of the CUDA path rest on.
+Run as a script it prints the truncation error by order, |rho| and u."""
 import math
 import numpy as np
 from scipy.stats import norm

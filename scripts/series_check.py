@@ -39,6 +39,8 @@ if sys.argv[1] == "run":
     with torch.cuda.stream(st):
         model.fit_2bit_device(packed.data_ptr(), packed.shape[1], n, ds)
     print("per-kernel ms:", {k: round(v[1], 3) for k, v in eng.profile_read().items() if v[0]})
+    if tag == "p":   # profiling run: nothing to keep
+        sys.exit(0)
     vc = dres["vcov"].cpu().numpy()
     np.savez(os.path.join(ROOT, "gpurun_out", f"series_{tag}.npz"), est=dres["est"].cpu().numpy(),
              se=np.sqrt(np.diagonal(vc, axis1=1, axis2=2)), status=dres["status"].cpu().numpy(), fit=dres["fit"].cpu().numpy(),

@@ -412,3 +412,59 @@ def test_build_item_ordinal_with_gxe_matches_oracle(engine):
     res = gm.fit_2bit(synth.pack_2bit(codes))
     compare(res, want, flat["par_names"])
     gm.close()
+
+
+def _c3_like(n, seed):
+    rng = np.random.default_rng(seed)
+    K = 5
+    X = rng.normal(size=(n, K))
+    causal = synth.simulate_hardcalls(n, 2, seed=seed + 1, maf_range=(0.2, 0.4))
+    gz = (causal - causal.mean(1, keepdims=True)) / causal.std(1, keepdims=True)
+    F = rng.normal(size=n) + X @ np.full(K, 0.1) + 0.15 * gz.sum(0)
+    ph = pd.DataFrame({f"pc{k + 1}": X[:, k] for k in range(K)})
+    cuts = [[-.43, .43], [-.67, 0, .67], [-.84, -.25, .25, .84]]
+    for j, lam in enumerate([.8, .7, .6]):
+        ystar = lam * F + X @ (rng.normal(size=K) * 0.1) + rng.normal(size=n)
+        ph[f"i{j + 1}"] = pd.Categorical(np.searchsorted(cuts[j], ystar), ordered=True)
+    return ph, causal
+
+
+def test_series_path_and_structured_fit_match_the_per_person_kernels(engine, monkeypatch):
+    """The class-sum (series) statistics + the structured one-warp fit against the per-person statistics kernel + the
+    generic fit on the same batch: null SNPs (series path), causal SNPs (per-person kernel started from the series root),
+    rare alleles, a monomorphic row.  Tolerances far inside the oracle tolerances; any sub-batch gives the same bits."""
+    from gwsem_b200.engine import Model
+    n, m = 20000, 300
+    ph, causal = _c3_like(n, 77)
+    model = buildOneFac(ph, ["i1", "i2", "i3"], covariates=[f"pc{k + 1}" for k in range(5)])
+    flat = flatten(model)
+    data, ncat = model_columns(model)
+    codes = synth.simulate_hardcalls(n, m, seed=78, maf_range=(0.05, 0.5))
+    codes[10:40] = synth.simulate_hardcalls(n, 30, seed=79, maf_range=(0.008, 0.04))   # rare alleles: large |u| in the hom class
+    codes[50] = causal[0]
+    codes[51] = causal[1]
+    codes[60] = 0
+    packed = synth.pack_2bit(codes)
+    gm = Model(engine, flat, data, ncat)
+    res = gm.fit_2bit(packed)
+    sub = gm.fit_2bit(synth.pack_2bit(codes[[51, 7, 299, 20]]))
+    assert np.array_equal(sub.est.view(np.uint64), res.est[[51, 7, 299, 20]].view(np.uint64))
+    assert np.array_equal(sub.vcov.view(np.uint64), res.vcov[[51, 7, 299, 20]].view(np.uint64))
+    gm.close()
+    monkeypatch.setenv("GWSEM_NO_SERIES", "1")
+    monkeypatch.setenv("GWSEM_FIT_GENERIC", "1")
+    gm2 = Model(engine, flat, data, ncat)
+    ref = gm2.fit_2bit(packed)
+    gm2.close()
+    assert np.array_equal(res.status, ref.status) and np.array_equal(res.catch_code, ref.catch_code)
+    assert res.catch_code[60] != 0 and (res.catch_code[40:60] == 0).all() and (res.catch_code[61:] == 0).all()
+    assert (res.catch_code[10:40] == 0).sum() >= 20   # (the rarest fall under minVariance, in both paths)
+    ok = res.catch_code == 0
+    se = np.sqrt(np.diagonal(ref.vcov[ok], axis1=1, axis2=2))
+    se2 = np.sqrt(np.diagonal(res.vcov[ok], axis1=1, axis2=2))
+    d = np.abs(res.est[ok] - ref.est[ok]) / np.maximum(np.abs(ref.est[ok]), se)
+    assert d.max() < 2e-5, d.max()
+    assert np.max(np.abs(se2 / se - 1)) < 1e-5
+    k = flat["par_names"].index("snp_to_F")
+    z = res.est[:, k] / np.sqrt(res.vcov[:, k, k])
+    assert abs(z[50]) > 8 and abs(z[51]) > 8                      # the causal SNPs are found
