@@ -802,7 +802,21 @@ __device__ void fast_fit_one(const FitProgram& fp, const MargProgram& mp, const 
   };
   for (int k = lane; k < P; k += 32) theta[k] = fp.par_warm ? fp.par_warm[k] : fp.par_start[k];
   __syncwarp();
+  if (mp.n_init > 0) {
+    // parameters that are a mean / variance outright start at the observed value (the snp's mean and variance differ
+    // from the warm start's by far more than anything else does)
+    implied_stats(fp, mp, ev, ws, sm, theta, sig, lane);
+    if (lane < mp.n_init) {
+      const int k = mp.init_par[lane], e = mp.init_row[lane];
+      double v = theta[k] + (s[e] - sig[e]);
+      const double lb = fp.par_lbound[k];
+      if (lb == lb && v < lb) v = lb;
+      theta[k] = v;
+    }
+    __syncwarp();
+  }
   double F = objective(theta, r);
+  double dF_prev = 0.0;
   bool at_theta = true;   // the RAM scratch (Z, C, mu, sig) was last evaluated at theta: the Jacobian can reuse it
   double lam = 1e-4;
   int status = GWSEM_STATUS_ITERATION_LIMIT;
@@ -881,7 +895,18 @@ __device__ void fast_fit_one(const FitProgram& fp, const MargProgram& mp, const 
     F = Fc;
     at_theta = true;   // theta = cand, where the objective was just evaluated
     lam = fmax(lam / 10, 1e-12);
-    if (step < 1e-10 || dF <= 1e-14 * (1 + F)) { status = GWSEM_STATUS_OK; break; }
+    // F is on the chi-square scale (the weight is the inverse covariance of the statistics), so a decrease dF moved the
+    // estimate by about sqrt(2 dF) standard errors.  With the contraction kappa = sqrt(dF / previous dF) seen so far,
+    // what is left after this step is sqrt(2 dF) kappa / (1 - kappa) standard errors: stop below 2e-6 (C3 cohort: kappa
+    // around 0.01, three to four iterations; slowly contracting models run on to the oracle's own rule, which
+    // marg_fit_kernel always uses).
+    bool close_enough = false;
+    if (it >= 2 && dF_prev > 0.0 && dF >= 0.0) {
+      const double kappa = sqrt(dF / dF_prev);
+      close_enough = kappa < 0.5 && sqrt(2.0 * dF) * kappa / (1.0 - kappa) <= 2e-6;
+    }
+    dF_prev = dF;
+    if (step < 1e-10 || dF <= 1e-14 * (1 + F) || close_enough) { status = GWSEM_STATUS_OK; break; }
   }
   if (nbeta == 0) { status = GWSEM_STATUS_OK; it = 0; }
   if (it > max_iter) it = max_iter;

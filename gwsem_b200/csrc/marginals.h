@@ -72,6 +72,10 @@ struct MargProgram {
   const int32_t* elim_a_row = nullptr;
   const int32_t* elim_b_par = nullptr;
   const int32_t* elim_b_row = nullptr;
+  // iterated parameters that are the mean / variance of a continuous variable outright (unit derivative of that
+  // statistic, e.g. the snp mean and variance): the structured fit moves them onto the observed value before iterating
+  int n_init = 0;
+  int init_par[4] = {0, 0, 0, 0}, init_row[4] = {0, 0, 0, 0};
   // series pass at rho = 0 from genotype-class sums (hardcalls without missing calls, all items ordinal): per item the
   // six products {c1, c2, c1^2, c3, c1^3, c1 c2} of the tetrachoric coefficients, class-summed exactly by the tcgen05
   // kernel; cs_sums[snp][2][6 J] (het, hom ALT) is set per launch, cs_tot[6 J] are the sums over all included people

@@ -576,6 +576,19 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
     }
     for (int e = 0; e < ns; ++e) if (!row_taken[e]) b_row.push_back(e);
     for (int k = 0; k < P; ++k) if (!par_gone[k]) b_par.push_back(k);
+    mp.n_init = 0;
+    for (int e : b_row) {
+      if (kind_[e] != 0 && kind_[e] != 3) continue;
+      for (int k : b_par) {
+        if (par_lbound[k] == par_lbound[k] && kind_[e] == 0) continue;
+        if (jj[(size_t)e * P + k] == 1.0 && jj[(size_t)(ns + e) * P + k] == 1.0 && mp.n_init < 4) {
+          mp.init_par[mp.n_init] = k;
+          mp.init_row[mp.n_init] = e;
+          ++mp.n_init;
+          break;
+        }
+      }
+    }
     if (!a_par.empty()) {
       mp.n_a = (int)a_par.size(); mp.n_b = (int)b_row.size(); mp.n_beta = (int)b_par.size();
       mp.elim_a_par = up(pool, a_par, st); mp.elim_a_row = up(pool, a_row, st);
