@@ -372,6 +372,7 @@ def measure(rk, eng, stream, which, n_snps, steps, warmup, missing_rate=0.0, hos
     if sampler is not None:
         sampler.start()
     launches0 = eng.launches
+    cols0 = eng.series_columns
     eng.profile(True)
     eng.profile_read()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -385,7 +386,7 @@ def measure(rk, eng, stream, which, n_snps, steps, warmup, missing_rate=0.0, hos
     ms = e0.elapsed_time(e1)
     prof = eng.profile_read()
     eng.profile(False)
-    out = {"ms": ms, "prof": prof, "launches": eng.launches - launches0, "P": P, "pitch": pitch,
+    out = {"ms": ms, "prof": prof, "launches": eng.launches - launches0, "series_columns": eng.series_columns - cols0, "P": P, "pitch": pitch,
            "ok_frac": float((dres["status"] == 0).float().mean().item()),
            "caught_frac": float((dres["catch_code"] != 0).float().mean().item())}
     if host_leg:
@@ -528,9 +529,10 @@ def roofline(which, m, n_snps, steps, fp64_peak):
     n_k, ms_k = m["prof"][w["family"]]
     share = {k: v[1] / m["ms"] for k, v in m["prof"].items() if v[0]}
     if w["bound"] == "tensor":
-        # one launch = 128 digit columns (32 features x 4 base-256 digits) x 2 genotype classes x people x SNPs, 2 ops each
+        # one launch = 128 or 144 digit columns (32 features x 4 base-256 digits, or 48 x 3) x 2 genotype classes x people x
+        # SNPs, 2 ops each; the engine counts the columns it launched
         n_pad = (w["n_people"] + 31) // 32 * 32
-        per_launch = 2.0 * 2 * 128 * n_pad * n_snps
+        per_launch = 2.0 * 2 * (m["series_columns"] / max(n_k, 1)) * n_pad * n_snps
         achieved = per_launch / (ms_k / max(n_k, 1) / 1e3) / 1e12 if n_k else None
         peak, src = measured_tensor_peak()
         traffic = None

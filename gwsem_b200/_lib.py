@@ -49,6 +49,7 @@ SYMBOLS = {
     "gwsem_engine_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gwsem_engine_synchronize": (C.c_int, [C.c_void_p]),
     "gwsem_engine_launch_count": (C.c_int64, [C.c_void_p]),
+    "gwsem_engine_series_columns": (C.c_int64, [C.c_void_p]),
     "gwsem_engine_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "gwsem_engine_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "gwsem_engine_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),

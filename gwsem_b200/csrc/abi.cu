@@ -191,6 +191,7 @@ int gwsem_engine_synchronize(gwsem_engine* e) {
 }
 
 int64_t gwsem_engine_launch_count(const gwsem_engine* e) { return e->launches; }
+int64_t gwsem_engine_series_columns(const gwsem_engine* e) { return e->series_columns; }
 
 int gwsem_decode_2bit_device(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int n_samples,
                              int plink1, const int32_t* d_dest_of, int dest_rows, double* d_out, double* d_maf) {

@@ -88,6 +88,7 @@ struct gwsem_engine {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
+  int64_t series_columns = 0;   // digit columns of the series-path class-sum launches, summed over launches
   // scratch reused by the host-pointer entry points
   gwsem::DeviceBuffer<uint8_t> d_packed;
   gwsem::DeviceBuffer<double> d_rows, d_maf;

@@ -381,18 +381,19 @@ void append_double(std::string& out, double v) {  // as printf("%.15g"), NA for 
 struct RowBatch {
   int n = 0;
   std::vector<uint32_t> variant;
-  std::vector<double> est, vcov, fit, maf;
-  std::vector<int32_t> n_used, status, catch_code, catch_var, iterations;
+  // pinned: the device -> host copies of a batch run at link speed and asynchronously, behind the next batch's kernels
+  PinnedBuffer<double> est, vcov, fit, maf;
+  PinnedBuffer<int32_t> n_used, status, catch_code, catch_var, iterations;
   void resize(int rows, int P) {
     n = rows;
     variant.resize(rows);
-    est.resize((size_t)rows * P); vcov.resize((size_t)rows * P * P); fit.resize(rows); maf.resize(rows);
-    n_used.resize(rows); status.resize(rows); catch_code.resize(rows); catch_var.resize(rows); iterations.resize(rows);
+    est.ensure((size_t)rows * P); vcov.ensure((size_t)rows * P * P); fit.ensure(rows); maf.ensure(rows);
+    n_used.ensure(rows); status.ensure(rows); catch_code.ensure(rows); catch_var.ensure(rows); iterations.ensure(rows);
   }
   gwsem_result view() {
     gwsem_result h;
-    h.est = est.data(); h.vcov = vcov.data(); h.fit = fit.data(); h.maf = maf.data(); h.n_used = n_used.data();
-    h.status = status.data(); h.catch_code = catch_code.data(); h.catch_var = catch_var.data(); h.iterations = iterations.data();
+    h.est = est.p; h.vcov = vcov.p; h.fit = fit.p; h.maf = maf.p; h.n_used = n_used.p;
+    h.status = status.p; h.catch_code = catch_code.p; h.catch_var = catch_var.p; h.iterations = iterations.p;
     return h;
   }
 };
@@ -544,30 +545,36 @@ int gwsem_gwas_run(gwsem_model* m, gwsem_source* s, const gwsem_job* job, int64_
     Stager sg(e, s);
     const bool hard_file = s->kind == gwsem_source::kPgen && !s->any_dosage;
     int batch = job->batch_snps > 0 ? job->batch_snps
-                                    : (int)(hard_file ? std::min<int64_t>(1 << 15, std::max<int64_t>(64, (sg.fixed_width() ? 96ll << 20 : 256ll << 20) / sg.pitch))
+                                    : (int)(hard_file ? std::min<int64_t>(1 << 16, std::max<int64_t>(64, (384ll << 20) / sg.pitch))
                                                       : std::min<int64_t>(4096, std::max<int64_t>(16, (512ll << 20) / (8ll * sg.n_pad))));
+    if (job->batch_snps <= 0 && hard_file) {
+      // whole waves of the 128-SNP class-sum CTAs over the SMs (18,944 SNPs on 148 SMs), else whole CTAs
+      const int wave = 128 * e->sm_count;
+      if (batch >= wave) batch = batch / wave * wave;
+      else if (batch >= 128) batch = batch / 128 * 128;
+    }
     RowBatch rb[2];
     std::future<void> pending;  // formatting + writing of the previous batch
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     // rows [k0, k1) of batch b as text
     auto format_rows = [&](const RowBatch& b, int k0, int k1, const char* tbuf, std::string& line) {
       for (int k = k0; k < k1; ++k) {
-        const bool caught = b.catch_code[k] != GWSEM_CATCH_NONE;
-        line += std::to_string(b.iterations[k] + 1);  // objective evaluations are not tracked separately
+        const bool caught = b.catch_code.p[k] != GWSEM_CATCH_NONE;
+        line += std::to_string(b.iterations.p[k] + 1);  // objective evaluations are not tracked separately
         line += '\t';
-        line += std::to_string(b.iterations[k]);
+        line += std::to_string(b.iterations.p[k]);
         line += '\t';
         line += tbuf;
         line += '\t';
         line += std::to_string(b.variant[k] + 1);
-        for (int a = 0; a < P; ++a) { line += '\t'; append_double(line, b.est[(size_t)k * P + a]); }
+        for (int a = 0; a < P; ++a) { line += '\t'; append_double(line, b.est.p[(size_t)k * P + a]); }
         line += '\t';
-        append_double(line, b.fit[k]);
+        append_double(line, b.fit.p[k]);
         line += m->fit_kind == 2 ? "\t-2lnL\t" : "\tr'Wr\t";
-        line += std::to_string(b.n_used[k]);
+        line += std::to_string(b.n_used.p[k]);
         line += '\t';
-        line += caught ? "NA" : status_text(b.status[k]);
-        for (auto& pr : vc) { line += '\t'; append_double(line, b.vcov[(size_t)k * P * P + (size_t)pr.first * P + pr.second]); }
+        line += caught ? "NA" : status_text(b.status.p[k]);
+        for (auto& pr : vc) { line += '\t'; append_double(line, b.vcov.p[(size_t)k * P * P + (size_t)pr.first * P + pr.second]); }
         if (s->kind == gwsem_source::kPgen) {
           if (!ctx.lines.empty()) { line += '\t'; line += ctx.fields(b.variant[k]); }
         } else {
@@ -576,15 +583,15 @@ int gwsem_gwas_run(gwsem_model* m, gwsem_source* s, const gwsem_job* job, int64_
           line += std::to_string(bv.pos); line += '\t'; line += bv.a2; line += '\t'; line += bv.a1;
         }
         char mbuf[32];
-        snprintf(mbuf, sizeof(mbuf), "\t%.8f\t", b.maf[k]);  // loader.cpp:404
+        snprintf(mbuf, sizeof(mbuf), "\t%.8f\t", b.maf.p[k]);  // loader.cpp:404
         line += mbuf;
-        if (b.catch_code[k] == GWSEM_CATCH_MIN_VARIANCE) {
+        if (b.catch_code.p[k] == GWSEM_CATCH_MIN_VARIANCE) {
           char cbuf[256];
-          const char* var = b.catch_var[k] == -2 ? "snp" : (job->manifest_names && b.catch_var[k] >= 0) ? job->manifest_names[b.catch_var[k]] : "?";
+          const char* var = b.catch_var.p[k] == -2 ? "snp" : (job->manifest_names && b.catch_var.p[k] >= 0) ? job->manifest_names[b.catch_var.p[k]] : "?";
           snprintf(cbuf, sizeof(cbuf), "%s.data: '%s' has observed variance less than %g", job->model_name ? job->model_name : "model",
                    var, m->min_variance);
           line += cbuf;
-        } else if (b.catch_code[k] == GWSEM_CATCH_ACOV_NOT_PD) {
+        } else if (b.catch_code.p[k] == GWSEM_CATCH_ACOV_NOT_PD) {
           line += job->model_name ? job->model_name : "model";
           line += ".data: asymptotic covariance matrix is not positive definite";
         }
@@ -643,16 +650,49 @@ int gwsem_gwas_run(gwsem_model* m, gwsem_source* s, const gwsem_job* job, int64_
     static const bool timing = getenv("GWSEM_TIMING") != nullptr;   // development aid: phase times on stderr
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_stage = 0, t_fit = 0, t_wait = 0, t_dl = 0;
+    const size_t cap = std::min<size_t>(batch, todo.size());
+    m->ensure_result_buffers((int)(2 * cap));
+    cudaStream_t out_stream = nullptr;
+    cudaEvent_t ev_fitted[2] = {nullptr, nullptr}, ev_down[2] = {nullptr, nullptr}, ev_up[2] = {nullptr, nullptr};
+    GW_CUDA(cudaStreamCreateWithFlags(&out_stream, cudaStreamNonBlocking));
+    for (int b2 = 0; b2 < 2; ++b2) {
+      GW_CUDA(cudaEventCreateWithFlags(&ev_fitted[b2], cudaEventDisableTiming));
+      GW_CUDA(cudaEventCreateWithFlags(&ev_down[b2], cudaEventDisableTiming));
+      GW_CUDA(cudaEventCreateWithFlags(&ev_up[b2], cudaEventDisableTiming));
+    }
+    bool up_used[2] = {false, false};
+    auto release_streams = [&] {
+      if (out_stream) { cudaStreamSynchronize(out_stream); cudaStreamDestroy(out_stream); out_stream = nullptr; }
+      for (int b2 = 0; b2 < 2; ++b2) {
+        if (ev_fitted[b2]) cudaEventDestroy(ev_fitted[b2]);
+        if (ev_down[b2]) cudaEventDestroy(ev_down[b2]);
+        if (ev_up[b2]) cudaEventDestroy(ev_up[b2]);
+        ev_fitted[b2] = ev_down[b2] = ev_up[b2] = nullptr;
+      }
+    };
+    bool have_prev = false;
+    int last_slot = 0;
     try {
     for (size_t t0 = 0; t0 < todo.size(); t0 += batch) {
       const int n = (int)std::min<size_t>(batch, todo.size() - t0);
       const uint32_t* v = &todo[t0];
       const double c0 = now();
-      m->ensure_result_buffers(n);
+      const int slot = (int)((t0 / batch) & 1);
+      // results of consecutive batches alternate between the two halves of the device buffers: batch k computes while
+      // batch k - 1 is copied out (the copy of batch k - 2, which used this half, was awaited one iteration ago)
       gwsem_result dres = m->device_result();
+      {
+        const size_t o = (size_t)slot * cap;
+        dres.est += o * P; dres.vcov += o * P * P; dres.fit += o; dres.maf += o; dres.n_used += o;
+        dres.status += o; dres.catch_code += o; dres.catch_var += o; dres.iterations += o;
+      }
       if (ahead) {
         reading.get();
-        sg.upload_fixed(n, (int)((t0 / batch) & 1));
+        sg.upload_fixed(n, slot);
+        GW_CUDA(cudaEventRecord(ev_up[slot], st));
+        up_used[slot] = true;
+        // the reader refills the other pinned slot: the upload that read it (previous batch) must be over
+        if (up_used[slot ^ 1]) GW_CUDA(cudaEventSynchronize(ev_up[slot ^ 1]));
         start_read(t0 + batch);
         m->fit_2bit_device(sg.d_rows.p, sg.pitch, n, sg.plink1, dres);
       } else if (s->kind == gwsem_source::kPgen) {
@@ -668,7 +708,10 @@ int gwsem_gwas_run(gwsem_model* m, gwsem_source* s, const gwsem_job* job, int64_
         }
       } else {
         reading.get();
-        sg.upload_bgen(n, (int)((t0 / batch) & 1));
+        sg.upload_bgen(n, slot);
+        GW_CUDA(cudaEventRecord(ev_up[slot], st));
+        up_used[slot] = true;
+        if (up_used[slot ^ 1]) GW_CUDA(cudaEventSynchronize(ev_up[slot ^ 1]));
         start_read_bgen(t0 + batch);
         if (timing) { GW_CUDA(cudaStreamSynchronize(st)); t_stage += now() - c0; }
         d_geno.ensure((size_t)n * sg.n_pad);
@@ -683,24 +726,45 @@ int gwsem_gwas_run(gwsem_model* m, gwsem_source* s, const gwsem_job* job, int64_
       }
       double c1 = 0;
       if (timing) { GW_CUDA(cudaStreamSynchronize(st)); c1 = now(); t_fit += c1 - c0; }
-      if (pending.valid()) pending.get();  // at most one batch in flight behind the device
-      if (timing) { t_wait += now() - c1; c1 = now(); }
-      RowBatch& cur = rb[(t0 / batch) & 1];
+      GW_CUDA(cudaEventRecord(ev_fitted[slot], st));
+      // the previous batch: its results are on the host once its download is done; hand it to the writer
+      // (one batch being written, one being downloaded, one on the device)
+      if (have_prev) {
+        GW_CUDA(cudaEventSynchronize(ev_down[slot ^ 1]));
+        if (timing) { t_dl += now() - c1; c1 = now(); }
+        if (pending.valid()) pending.get();
+        if (timing) { t_wait += now() - c1; c1 = now(); }
+        RowBatch& prev = rb[slot ^ 1];
+        pending = std::async(std::launch::async, [&write_batch, &prev] { write_batch(prev); });
+      } else if (pending.valid()) {
+        pending.get();
+      }
+      RowBatch& cur = rb[slot];   // (its previous contents were written two batches ago: that writer was joined above)
       cur.resize(n, P);
       std::copy(v, v + n, cur.variant.begin());
-      m->download_result(cur.view(), dres, n, 0);
-      GW_CUDA(cudaStreamSynchronize(st));
-      if (timing) t_dl += now() - c1;
-      pending = std::async(std::launch::async, [&write_batch, &cur] { write_batch(cur); });
+      GW_CUDA(cudaStreamWaitEvent(out_stream, ev_fitted[slot], 0));
+      m->download_result(cur.view(), dres, n, 0, out_stream);
+      GW_CUDA(cudaEventRecord(ev_down[slot], out_stream));
+      have_prev = true;
+      last_slot = slot;
       written += n;
+    }
+    if (have_prev) {
+      GW_CUDA(cudaEventSynchronize(ev_down[last_slot]));
+      if (pending.valid()) pending.get();
+      RowBatch& prev = rb[last_slot];
+      pending = std::async(std::launch::async, [&write_batch, &prev] { write_batch(prev); });
     }
     if (pending.valid()) pending.get();
     } catch (...) {
       // the helper threads use this frame's objects: let them finish before it unwinds
       if (pending.valid()) pending.wait();
       if (reading.valid()) reading.wait();
+      cudaStreamSynchronize(st);
+      release_streams();
       throw;
     }
+    release_streams();
     if (timing)
       fprintf(stderr, "gwsem timing: batch %d, stage(bgen only) %.3f s, stage+fit %.3f s, wait-for-writer %.3f s, download %.3f s\n",
               batch, t_stage, t_fit, t_wait, t_dl);

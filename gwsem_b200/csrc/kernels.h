@@ -55,12 +55,14 @@ void launch_class_sums_tc5(gwsem_engine* e, const uint8_t* d_packed, int64_t pit
                            double* d_sums, int32_t* d_counts, int32_t* d_miss_list = nullptr,
                            int32_t* d_miss_n = nullptr);
 
-constexpr int kTcWideFeatures = 32;   // features per wide chunk (128 digit columns)
+constexpr int kTcWideFeatures = 32;     // features per wide chunk (4 digits each: 128 digit columns)
+constexpr int kTcNarrowFeatures = 48;   // features per narrow chunk (3 digits each: 144 digit columns)
 size_t tc5_wide_chunk_bytes(int n_pad);
-void tc5_pack_chunk(const int64_t* q, int n_in_chunk, int n_pad, int8_t* chunk_base);
+size_t tc5_narrow_chunk_bytes(int n_pad);
+void tc5_pack_chunk(const int64_t* q, int n_in_chunk, int n_pad, int8_t* chunk_base, bool narrow);
 void launch_class_sums_tc5_wide(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
-                                const PeopleLayout& pl, const int8_t* d_featq, const double* d_inv_scale, int n_feat,
-                                double* d_sums);
+                                const PeopleLayout& pl, const int8_t* d_featq, const double* d_inv_scale, int n_wide,
+                                int n_narrow, double* d_sums);
 
 // counts[snp][8] = {n_class1, n_class2, n_missing over included people; the same three over the
 // people kept by rowFilter (for MAF); 0; 0} and, for the missing class, sums of `n_featm`

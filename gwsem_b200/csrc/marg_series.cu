@@ -145,13 +145,23 @@ void build_series_features(MargProgram& mp, int n_src, int n_pad, const std::vec
                            const std::vector<double>& sc0, std::vector<int8_t>& packed, std::vector<double>& inv_scale,
                            std::vector<double>& tot, std::vector<double>& err) {
   const int J = mp.J, K = mp.K, q0 = mp.q0;
+  // The score polynomial (psi with weight 1, all fifteen terms: its root is the estimate) keeps four base-256 digits of a
+  // 2^-30 grid and goes into wide chunks; every other feature feeds the SNP-dependent rows of Muthen's A and B, which
+  // need about 1e-6 of their scale: three digits of a 2^-22 grid (rounding error of a class sum over 50k people:
+  // < 1e-5 of the sum's own sampling scale even for heavy-tailed features), narrow chunks.
   std::vector<Feature> feats;
   for (int j = 0; j < J; ++j) {
-    mp.se_o_psi[j] = (int)feats.size();
-    for (int w = 0; w <= q0; ++w)
-      for (int p = 0; p < kPsiB; ++p) feats.push_back({0, j, w, p});
+    mp.se_o_psi0[j] = (int)feats.size();
+    for (int p = 0; p < kPsiB; ++p) feats.push_back({0, j, 0, p});
     mp.se_o_hi[j] = (int)feats.size();
     for (int p = kPsiB; p < kPsiAll; ++p) feats.push_back({1, j, 0, p});
+  }
+  while (feats.size() % kTcWideFeatures) feats.push_back({-1, 0, 0, 0});
+  const int n_wide = (int)feats.size();
+  for (int j = 0; j < J; ++j) {
+    mp.se_o_psi[j] = (int)feats.size();
+    for (int w = 1; w <= q0; ++w)
+      for (int p = 0; p < kPsiB; ++p) feats.push_back({0, j, w, p});
     mp.se_o_f3[j] = (int)feats.size();
     for (int p = 0; p < kF3; ++p) feats.push_back({2, j, 0, p});
     mp.se_o_thr[j] = (int)feats.size();
@@ -169,10 +179,10 @@ void build_series_features(MargProgram& mp, int n_src, int n_pad, const std::vec
       for (int p = 0; p < kCross; ++p) feats.push_back({6, a, b, p});
   mp.se_o_sc0 = (int)feats.size();
   for (int b = 0; b < q0; ++b) feats.push_back({7, 0, b, 0});
-  constexpr int kCF = kTcWideFeatures;
-  while (feats.size() % kCF) feats.push_back({-1, 0, 0, 0});   // whole 128-column chunks
-  const int nf = (int)feats.size(), chunks = nf / kCF;
-  mp.se_nf = nf;
+  while ((feats.size() - n_wide) % kTcNarrowFeatures) feats.push_back({-1, 0, 0, 0});
+  const int nf = (int)feats.size(), n_narrow = nf - n_wide;
+  const int wide_chunks = n_wide / kTcWideFeatures, chunks = wide_chunks + n_narrow / kTcNarrowFeatures;
+  mp.se_nf = nf; mp.se_n_wide = n_wide; mp.se_n_narrow = n_narrow;
 
   // per person and item: the series
   std::vector<double> ps((size_t)n_pad * J * kPer, 0.0);
@@ -200,16 +210,21 @@ void build_series_features(MargProgram& mp, int n_src, int n_pad, const std::vec
     }
   }
 
-  const size_t chunk_bytes = tc5_wide_chunk_bytes(n_pad);
-  packed.assign(chunk_bytes * chunks, 0);
+  const size_t wide_bytes = tc5_wide_chunk_bytes(n_pad), narrow_bytes = tc5_narrow_chunk_bytes(n_pad);
+  packed.assign(wide_bytes * wide_chunks + narrow_bytes * (chunks - wide_chunks), 0);
   inv_scale.assign(nf, 0.0);
   tot.assign(nf, 0.0);
   const int q0p = mp.q0p, Kp = mp.Kp;
   parallel_for(chunks, [&](int c) {
-    std::vector<double> h((size_t)kCF * n_pad, 0.0);
-    std::vector<int64_t> q((size_t)kCF * n_pad, 0);
-    for (int fi = 0; fi < kCF; ++fi) {
-      const Feature f = feats[c * kCF + fi];
+    const bool narrow = c >= wide_chunks;
+    const int cf = narrow ? kTcNarrowFeatures : kTcWideFeatures;
+    const int first = narrow ? n_wide + (c - wide_chunks) * kTcNarrowFeatures : c * kTcWideFeatures;
+    const int grid_bits = narrow ? 22 : 30;
+    int8_t* dst = packed.data() + (narrow ? wide_bytes * wide_chunks + narrow_bytes * (size_t)(c - wide_chunks) : wide_bytes * (size_t)c);
+    std::vector<double> h((size_t)cf * n_pad, 0.0);
+    std::vector<int64_t> q((size_t)cf * n_pad, 0);
+    for (int fi = 0; fi < cf; ++fi) {
+      const Feature f = feats[first + fi];
       if (f.type < 0) continue;
       double* hv = &h[(size_t)fi * n_pad];
       CrossTerm ct = {0, 0, 0};
@@ -253,17 +268,17 @@ void build_series_features(MargProgram& mp, int n_src, int n_pad, const std::vec
       for (int s = 0; s < n_src; ++s) mx = std::max(mx, std::fabs(hv[s]));
       int ex = 0;
       if (mx > 0) std::frexp(mx, &ex);
-      const double sc = std::ldexp(1.0, 30 - ex);
-      inv_scale[c * kCF + fi] = std::ldexp(1.0, ex - 30);
+      const double sc = std::ldexp(1.0, grid_bits - ex);
+      inv_scale[first + fi] = std::ldexp(1.0, ex - grid_bits);
       long double acc = 0;
       int64_t* qv = &q[(size_t)fi * n_pad];
       for (int s = 0; s < n_src; ++s) {
         qv[s] = std::llrint(hv[s] * sc);
         acc += (long double)qv[s];
       }
-      tot[c * kCF + fi] = (double)acc * inv_scale[c * kCF + fi];
+      tot[first + fi] = (double)acc * inv_scale[first + fi];
     }
-    tc5_pack_chunk(q.data(), kCF, n_pad, packed.data() + (size_t)c * chunk_bytes);
+    tc5_pack_chunk(q.data(), cf, n_pad, dst, narrow);
   });
 }
 
@@ -331,7 +346,7 @@ __global__ void __launch_bounds__(kWarps * 32)
     double a[kM + 1];
     for (int m = 0; m <= kM; ++m) a[m] = 0.0;
     for (int p = 0; p < kPsiAll; ++p) {
-      const int f = p < kPsiB ? mp.se_o_psi[j] + p : mp.se_o_hi[j] + (p - kPsiB), l = psi_l(p);
+      const int f = p < kPsiB ? mp.se_o_psi0[j] + p : mp.se_o_hi[j] + (p - kPsiB), l = psi_l(p);
       a[psi_m(p)] += w.u0[l] * T[f] + w.ud1[l] * S1[f] + w.ud2[l] * S2[f];
     }
     double rho = 0.0;
@@ -383,7 +398,7 @@ __global__ void __launch_bounds__(kWarps * 32)
     const int j = e / 3, cls = e % 3;
     double ps = 0.0, fs = 0.0;
     for (int p = 0; p < kPsiAll; ++p) {
-      const int f = p < kPsiB ? mp.se_o_psi[j] + p : mp.se_o_hi[j] + (p - kPsiB);
+      const int f = p < kPsiB ? mp.se_o_psi0[j] + p : mp.se_o_hi[j] + (p - kPsiB);
       const double s = cls == 0 ? T[f] - S1[f] - S2[f] : (cls == 1 ? S1[f] : S2[f]);
       double up = 1.0;
       for (int l = 0; l < psi_l(p); ++l) up *= uc[cls];
@@ -451,7 +466,7 @@ __global__ void __launch_bounds__(kWarps * 32)
       for (int cls = 0; cls < 3; ++cls) v += (a == 0 ? uc[cls] * isd : (uc[cls] * uc[cls] - 1.0) * i2v) * s[cls];
     } else {
       const int j = a - 2;
-      v = eval_terms(w, w.rp[j], T, S1, S2, mp.se_o_psi[j] + (1 + b2) * kPsiB, kPsiB, [](int p) { return psi_m(p); }, [](int p) { return psi_l(p); });
+      v = eval_terms(w, w.rp[j], T, S1, S2, mp.se_o_psi[j] + b2 * kPsiB, kPsiB, [](int p) { return psi_m(p); }, [](int p) { return psi_l(p); });
     }
     out[mp.o_bd0 + a * q0 + b2] = v;
   }

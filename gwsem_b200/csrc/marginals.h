@@ -87,13 +87,14 @@ struct MargProgram {
   // genotype-class sums of SNP-independent per-person features.  se_sums[snp][2][se_nf] (het, hom ALT; per launch),
   // se_tot[se_nf] the sums over all included people; feature offsets below (pair tables in marg_series.h).
   // se_done[snp] = 1: the record of this SNP is complete, marg_stats_kernel leaves at once.
-  int se_nf = 0;
+  int se_nf = 0, se_n_wide = 0, se_n_narrow = 0;   // features in all; in four-digit (wide) and three-digit (narrow) chunks
   const double* se_sums = nullptr;
   const double* se_tot = nullptr;
   const double* se_err = nullptr;            // [J][10]: second moments of the first neglected coefficients (acceptance bound)
   uint8_t* se_done = nullptr;
-  int se_o_psi[kMargMaxItems] = {0};         // [w = 0 (weight 1), 1 + b (SC0 column b)][8 pairs]
-  int se_o_hi[kMargMaxItems] = {0};          // psi, weight 1, orders 4 and 5: 7 pairs
+  int se_o_psi0[kMargMaxItems] = {0};        // psi, weight 1, orders 0..3: 8 pairs   } the score polynomial: four digits
+  int se_o_hi[kMargMaxItems] = {0};          // psi, weight 1, orders 4 and 5: 7 pairs } (everything below: three)
+  int se_o_psi[kMargMaxItems] = {0};         // psi times SC0 column b: [b][8 pairs]
   int se_o_f3[kMargMaxItems] = {0};          // 5 pairs
   int se_o_thr[kMargMaxItems] = {0};         // [threshold][8 pairs]
   int se_o_slope[kMargMaxItems] = {0};       // [covariate][8 pairs]

@@ -727,7 +727,8 @@ void gwsem_model::run_marginals(const uint8_t* d_packed, int64_t pitch, const do
     // call-complete SNPs with a small correlation: the whole record from class sums, no pass over people
     d_se_sums.ensure((size_t)n * 2 * mp.se_nf);
     d_se_done.ensure(n);
-    launch_class_sums_tc5_wide(engine, d_packed, pitch, n, plink1, layout, d_seq, d_se_inv_scale, mp.se_nf, d_se_sums.p);
+    launch_class_sums_tc5_wide(engine, d_packed, pitch, n, plink1, layout, d_seq, d_se_inv_scale, mp.se_n_wide, mp.se_n_narrow,
+                               d_se_sums.p);
     mpl.se_sums = d_se_sums.p;
     mpl.se_done = d_se_done.p;
     launch_marg_series(engine, mpl, d_counts.p, n, d_summary.p);

@@ -54,6 +54,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
       : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine (UBLKCP in SASS); bytes a multiple of 16, both addresses 16-byte
+// aligned; completion is counted on the mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(unsigned dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
 // 16 consecutive 32-bit columns of this thread's lane
 __device__ __forceinline__ void tmem_st16(unsigned taddr, const unsigned (&r)[16]) {
   asm volatile(
@@ -89,13 +100,28 @@ __device__ __forceinline__ void mma_i8_ts(unsigned d_tmem, unsigned a_tmem, uint
 }
 
 // N = digit columns of the chunk (16 or 64), TILE = people per cp.async stage
+// Expanding groups: with a ring of four A buffers two groups of four warps take alternate A stages (group g: stages
+// g, g + 2, ...; buffers g and g + 2).  One stage is a serial chain for a warp -- expand, wait for the buffer, store,
+// tcgen05.wait::st, fence, arrive: about 600 cycles whatever the MMA size -- so one group alone left the tensor pipe
+// 46 % busy at 128 columns; two chains in flight feed it twice as fast.
+#ifndef GW_TC5_GROUPS
+#define GW_TC5_GROUPS 2
+#endif
+template <int N>
+struct TcShape {
+  static constexpr int kCols = 2 * N + 3 * 32 <= 128 ? 128 : (2 * N + 3 * 32 <= 256 ? 256 : 512);
+  static constexpr int kBufs = (kCols - 2 * N) / 32 < 4 ? (kCols - 2 * N) / 32 : 4;
+  static constexpr int kGroups = kBufs == 4 ? GW_TC5_GROUPS : 1;
+  static constexpr int kThreads = kTcThreads * kGroups + 32;
+};
+
 template <int N, int TILE, bool PLINK1>
-__global__ void __launch_bounds__(kTcThreads + 32)
+__global__ void __launch_bounds__(TcShape<N>::kThreads)
     class_sums_tc5_kernel(const uint8_t* __restrict__ rows, int64_t pitch, int n_snps, int n_blocks,
                           const int8_t* __restrict__ Bq, const double* __restrict__ inv_scale, int f0, int n_feat,
                           double* __restrict__ sums, unsigned tab1, unsigned tab2, int32_t* __restrict__ counts,
                           int count_slot, int32_t* __restrict__ miss_list, int32_t* __restrict__ miss_n,
-                          unsigned m30, unsigned m16, unsigned m14) {
+                          unsigned m30, unsigned m16, unsigned m14, int dbg) {
   constexpr int kSnps = kTcThreads;
   constexpr int kGRow = TILE / 4 + kTcGPad;
   constexpr int kBlocks = TILE / 32;
@@ -103,14 +129,17 @@ __global__ void __launch_bounds__(kTcThreads + 32)
   constexpr int kBStage = kBlocks * kBBlock;
   constexpr int kGStage = kSnps * kGRow;
   constexpr int kStage = kGStage + kBStage;
-  constexpr int kCols = 2 * N + 3 * 32 <= 128 ? 128 : (2 * N + 3 * 32 <= 256 ? 256 : 512);   // TMEM allocation (power of two)
-  constexpr int kBufs = (kCols - 2 * N) / 32 < 4 ? (kCols - 2 * N) / 32 : 4;   // A buffers in tensor memory: 3 (N = 16) or 4 (a ring of 6 at N = 128 measured slower: 18.5 vs 16.0 ms per 33 launches)
-  static_assert(kBufs == 3 || kBufs == 4 || kBufs == 6, "A ring");
+  constexpr int kCols = TcShape<N>::kCols;     // TMEM allocation (power of two)
+  constexpr int kBufs = TcShape<N>::kBufs;     // A buffers in tensor memory: 3 (N = 16) or 4 (a ring of 6 at N = 128 measured slower: 18.5 vs 16.0 ms per 33 launches)
+  constexpr int kGroups = TcShape<N>::kGroups; // expanding groups of four warps
+  constexpr int kExp = kTcThreads * kGroups;   // expanding threads
+  static_assert(kBufs == 3 || kBufs == 4, "A ring");
   static_assert(2 * N + kBufs * 32 <= 512, "tensor memory");
   constexpr unsigned kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((128u >> 4) << 24);
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t full_bar[kBufs], empty_bar[kBufs];
+  __shared__ __align__(8) uint64_t full_bar[kBufs], empty_bar[kBufs], tile_bar[2];
   __shared__ unsigned tmem_base_sh;
+  __shared__ unsigned mdet_sh[TcShape<N>::kGroups][kTcThreads];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int snp0 = blockIdx.x * kSnps;
   const int n_tiles = (n_blocks + kBlocks - 1) / kBlocks;
@@ -128,6 +157,8 @@ __global__ void __launch_bounds__(kTcThreads + 32)
       mbar_init(&full_bar[b], kTcThreads);   // every expanding thread arrives once its lane of the A buffer is stored
       mbar_init(&empty_bar[b], 1);           // tcgen05.commit: the MMAs that read the buffer are done
     }
+    mbar_init(&tile_bar[0], 1);              // staging of the feature digits: thread 0 announces the bytes of its bulk copy
+    mbar_init(&tile_bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -137,13 +168,14 @@ __global__ void __launch_bounds__(kTcThreads + 32)
   const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem);
   constexpr unsigned kDHet = 0u, kDHom = (unsigned)N, kA0 = 2u * N;   // A[buf][cls] at kA0 + (2 buf + cls) * 16
 
-  if (warp == 4) {
+  if (warp == 4 * kGroups) {
     // ---- MMA warp (one lane): per A stage two blocks x two classes, then a commit that frees the buffer
     if (lane == 0) {
       const int total = n_tiles * kPairs;
       int buf = 0;
       unsigned phase = 0;
       for (int a = 0, tile = 0, kp = 0; a < total; ++a) {
+        if (kp == 0) mbar_wait(&tile_bar[tile & 1], (unsigned)((tile >> 1) & 1));   // the feature digits of this tile have landed
         mbar_wait(&full_bar[buf], phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const unsigned b_tile = smem0 + (tile & 1) * kStage + kGStage;
@@ -151,6 +183,7 @@ __global__ void __launch_bounds__(kTcThreads + 32)
         for (int h = 0; h < 2; ++h) {
           const uint64_t bd = smem_desc(b_tile + (2 * kp + h) * kBBlock, N * 16, 128);
           const unsigned acc = (a > 0 || h > 0) ? 1u : 0u;
+          if (dbg & 1) continue;   // development aid (GWSEM_TC5_DBG): no MMAs
           mma_i8_ts(tmem_base + kDHet, tmem_base + kA0 + (2 * buf + 0) * 16 + h * 8, bd, kIdesc, acc);
           mma_i8_ts(tmem_base + kDHom, tmem_base + kA0 + (2 * buf + 1) * 16 + h * 8, bd, kIdesc, acc);
         }
@@ -163,18 +196,19 @@ __global__ void __launch_bounds__(kTcThreads + 32)
     }
     __syncwarp();
   } else {
-    // ---- expanding warps: thread = SNP = TMEM lane
-    const unsigned lane_base = tmem_base + ((unsigned)(warp * 32) << 16);
-    // staging (cp.async, one pointer bump per copy; see stats_imma.cu)
+    // ---- expanding warps: thread t of group g = SNP t = TMEM lane t (a warp reaches the lane quarter warp % 4)
+    const int grp = tid / kTcThreads, t = tid % kTcThreads;
+    const unsigned lane_base = tmem_base + ((unsigned)((warp & 3) * 32) << 16);
+    // Staging.  The tile's feature digits are one contiguous kBStage-byte piece of the chunk: thread 0 hands it to the
+    // TMA engine (cp.async.bulk, UBLKCP in SASS; the MMA warp waits for it on tile_bar).  The packed rows stay on
+    // cp.async with eight threads per 128-byte row piece: one bulk copy per row and thread (128 small copies per tile)
+    // was measured 35 % slower for the whole kernel.
     constexpr int kPieces = TILE / 64;
-    constexpr int kRowsPerPass = kTcThreads / kPieces;
+    constexpr int kRowsPerPass = kExp / kPieces;
     constexpr int kPasses = kSnps / kRowsPerPass;
-    constexpr int kBCopies = kBStage / 16 / kTcThreads;
-    static_assert(kBStage % (16 * kTcThreads) == 0, "staging layout");
+    static_assert(kBStage % 16 == 0 && kSnps % kRowsPerPass == 0, "staging layout");
     const int gc = tid % kPieces, gr = tid / kPieces;
     const unsigned gdst = smem0 + gr * kGRow + gc * 16;
-    const unsigned bdst = smem0 + kGStage + tid * 16;
-    const int8_t* bsrc = Bq + tid * 16;
     const int last_piece = (int)pitch - 16;
     const uint8_t* gp[kPasses];   // rows past the batch are clamped to its last row (not stored), pieces past the pitch to the last piece
 #pragma unroll
@@ -185,31 +219,41 @@ __global__ void __launch_bounds__(kTcThreads + 32)
 #pragma unroll
       for (int k = 0; k < kPasses; ++k)
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + k * kRowsPerPass * kGRow), "l"(gp[k] + off) : "memory");
-      const int8_t* q = bsrc + (int64_t)tile * kBStage;
-      const unsigned db = bdst + s * kStage;
-#pragma unroll
-      for (int k = 0; k < kBCopies; ++k)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(db + k * kTcThreads * 16), "l"(q + k * kTcThreads * 16) : "memory");
       asm volatile("cp.async.commit_group;" ::: "memory");
+      if (tid == 0) {
+        // the MMAs that read this stage's digits are done (the empty-barrier wait before this call covers the previous tile)
+        mbar_arrive_expect_tx(&tile_bar[s], (unsigned)kBStage);
+        tma_bulk_g2s(smem0 + s * kStage + kGStage, Bq + (int64_t)tile * kBStage, (unsigned)kBStage, &tile_bar[s]);
+      }
     };
-    auto expanders_sync = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
+    auto expanders_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kExp) : "memory"); };
 
     unsigned mdet = 0u;      // missing-call detector (see stats_imma.cu)
-    constexpr int kIssue = kBufs < kPairs ? kBufs : kPairs - 1;   // stage of a tile at which the next tile's copies start
-    static_assert(kIssue >= kBufs, "tiles shorter than the A ring are not handled");
+    // stage of a tile at which the next tile's copies start: the first one of this group at or after kBufs (its
+    // empty-barrier wait then covers every MMA of the previous tile)
+    constexpr int kIssue0 = kBufs < kPairs ? kBufs : kPairs - 1;
+    static_assert(kIssue0 >= kBufs && kIssue0 + kGroups - 1 < kPairs, "tiles shorter than the A ring are not handled");
+    static_assert(kPairs % kGroups == 0 && kIssue0 % kGroups == 0, "every group meets every tile at the same stages");
+    const int kIssue = kIssue0 + grp;
     const int total = n_tiles * kPairs;   // A stages; stage a uses buffer a % kBufs, phase = parity of a / kBufs
-    int a = 0, kp = 0, tile = 0;
+    int a = grp, kp = grp, tile = 0;      // this group's stages: grp, grp + kGroups, ...
     unsigned phase = 0;
     const uint8_t* Gt = nullptr;
     load_stage(0, 0);
     // One A stage with a compile-time buffer: the TMEM addresses and barrier addresses are constants of the unrolled body.
     auto do_stage = [&](auto bufc) {
       constexpr int BUF = decltype(bufc)::value;
-      if (kp == 0) {   // tile start
+      if (kp == grp) {   // this group's first stage of the tile
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the MMAs read the feature digits through the async proxy
-        expanders_sync();   // tile landed for everyone; everyone is done with the previous tile's packed rows
-        Gt = smem + (tile & 1) * kStage + tid * kGRow;
+        expanders_sync();   // the packed rows landed for everyone; everyone is done with the previous tile's
+        Gt = smem + (tile & 1) * kStage + t * kGRow;
+        // The copies of the next tile can only start half a tile from now (the other stage is still being read), about
+        // 1 us before they are needed: less than a trip to HBM under load.  Ask L2 for those row pieces now.
+        if (!(dbg & 4) && tile + 1 < n_tiles) {
+          const int off = min((tile + 1) * (TILE / 4) + gc * 16, last_piece);
+#pragma unroll
+          for (int k = 0; k < kPasses; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(gp[k] + off));
+        }
       }
       const uint4 w4 = *reinterpret_cast<const uint4*>(Gt + kp * 16);
       unsigned ah[16], ao[16];
@@ -237,41 +281,103 @@ __global__ void __launch_bounds__(kTcThreads + 32)
       // That commit also covers every MMA of the previous tile once kp >= kBufs, and all expanding threads left
       // that tile's packed rows at the barrier above: the other shared-memory stage is free.
       if (kp == kIssue && tile + 1 < n_tiles) load_stage(tile + 1, (tile + 1) & 1);
-      tmem_st16(lane_base + kA0 + (2 * BUF + 0) * 16, ah);
-      tmem_st16(lane_base + kA0 + (2 * BUF + 1) * 16, ao);
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      if (!(dbg & 2)) {   // development aid (GWSEM_TC5_DBG): no stores to tensor memory
+        tmem_st16(lane_base + kA0 + (2 * BUF + 0) * 16, ah);
+        tmem_st16(lane_base + kA0 + (2 * BUF + 1) * 16, ao);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      } else {
+        unsigned x = 0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) x ^= ah[q] ^ ao[q];
+        mdet |= x & 1u;
+      }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&full_bar[BUF])) : "memory");
-      ++a;
-      if (++kp == kPairs) { kp = 0; ++tile; }
+      a += kGroups;
+      kp += kGroups;
+      if (kp >= kPairs) { kp -= kPairs; ++tile; }
     };
+    if constexpr (kGroups == 4) {
+      static_assert(kBufs == 4, "four groups, one buffer of the ring each");
 #pragma unroll 1
-    while (a < total) {
-      do_stage(std::integral_constant<int, 0>{});
-      if (a < total) do_stage(std::integral_constant<int, 1>{});
-      if (a < total) do_stage(std::integral_constant<int, 2>{});
-      if constexpr (kBufs > 3) {
-        if (a < total) do_stage(std::integral_constant<int, 3>{});
+      while (a < total) {
+        if (grp == 0) do_stage(std::integral_constant<int, 0>{});
+        else if (grp == 1) do_stage(std::integral_constant<int, 1>{});
+        else if (grp == 2) do_stage(std::integral_constant<int, 2>{});
+        else do_stage(std::integral_constant<int, 3>{});
+        phase ^= 1u;
       }
-      if constexpr (kBufs > 4) {
-        if (a < total) do_stage(std::integral_constant<int, 4>{});
-        if (a < total) do_stage(std::integral_constant<int, 5>{});
+    } else if constexpr (kGroups == 2) {
+      static_assert(kBufs == 4, "two groups share a ring of four");
+#pragma unroll 1
+      while (a < total) {
+        if (grp == 0) {
+          do_stage(std::integral_constant<int, 0>{});
+          if (a < total) do_stage(std::integral_constant<int, 2>{});
+        } else {
+          do_stage(std::integral_constant<int, 1>{});
+          if (a < total) do_stage(std::integral_constant<int, 3>{});
+        }
+        phase ^= 1u;
       }
-      phase ^= 1u;
+    } else {
+#pragma unroll 1
+      while (a < total) {
+        do_stage(std::integral_constant<int, 0>{});
+        if (a < total) do_stage(std::integral_constant<int, 1>{});
+        if (a < total) do_stage(std::integral_constant<int, 2>{});
+        if constexpr (kBufs > 3) {
+          if (a < total) do_stage(std::integral_constant<int, 3>{});
+        }
+        phase ^= 1u;
+      }
     }
     // all MMAs done: the last kBufs commits
 #pragma unroll
     for (int d = 1; d <= kBufs; ++d)
-      if (a >= d) mbar_wait(&empty_bar[(a - d) % kBufs], (unsigned)(((a - d) / kBufs) & 1));
+      if (total >= d) mbar_wait(&empty_bar[(total - d) % kBufs], (unsigned)(((total - d) / kBufs) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // ---- epilogue: this thread's SNP, both classes, N digit columns each (the one-hot entries are -1)
-    const int snp = snp0 + tid;
-    if (miss_list && (mdet & 0xAAAAAAAAu) != 0u && snp < n_snps) miss_list[atomicAdd(miss_n, 1)] = snp;
+    // ---- epilogue: this thread's SNP (the one-hot entries are -1); the groups share the classes and column halves
+    const int snp = snp0 + t;
+    if (kGroups > 1) {
+      mdet_sh[grp][t] = mdet;
+      expanders_sync();
+      if (grp == 0)
+        for (int g2 = 1; g2 < kGroups; ++g2) mdet |= mdet_sh[g2][t];
+    }
+    if (grp == 0 && miss_list && (mdet & 0xAAAAAAAAu) != 0u && snp < n_snps) miss_list[atomicAdd(miss_n, 1)] = snp;
+    constexpr int kColParts = kGroups == 4 ? 2 : 1;   // column ranges of an accumulator shared out between groups
+    if constexpr (N == kTcNarrowFeatures * 3) {
+      // three balanced base-256 digits per feature, digit-major: columns [d * 48, d * 48 + 48) hold digit d of the chunk's
+      // 48 features (the SNP-dependent rows of Muthen's A and B need 1e-6, not 2^-30, of the feature's range)
+      static_assert(kGroups == 2, "one class per group");
+      const int cls = grp;
+#pragma unroll
+      for (int g3 = 0; g3 < kTcNarrowFeatures / 16; ++g3) {
+        int v0[16], v1[16], v2[16];
+        const unsigned d_base = lane_base + (cls ? kDHom : kDHet) + 16 * g3;
+        tmem_ld16(d_base, v0);
+        tmem_ld16(d_base + kTcNarrowFeatures, v1);
+        tmem_ld16(d_base + 2 * kTcNarrowFeatures, v2);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (snp < n_snps) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int f = f0 + 16 * g3 + i;
+            if (f < n_feat)
+              sums[((int64_t)snp * 2 + cls) * n_feat + f] =
+                  ((double)(-v0[i]) + 256.0 * (double)(-v1[i]) + 65536.0 * (double)(-v2[i])) * inv_scale[f];
+          }
+        }
+      }
+    } else {
 #pragma unroll
     for (int cls = 0; cls < 2; ++cls) {
+      if (kGroups >= 2 && cls != (grp & 1)) continue;
 #pragma unroll
       for (int c0 = 0; c0 < N; c0 += 16) {
+        if (kColParts == 2 && (c0 >= N / 2) != (grp >= 2)) continue;
         int v[16];
         tmem_ld16(lane_base + (cls ? kDHom : kDHet) + c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -293,6 +399,7 @@ __global__ void __launch_bounds__(kTcThreads + 32)
         }
       }
     }
+    }   // four-digit chunks
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -306,17 +413,18 @@ void launch_tc5(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_s
                 const int8_t* Bq, const double* inv_scale, int f0, int n_feat, double* d_sums, int32_t* d_counts,
                 int count_slot, int32_t* d_miss_list, int32_t* d_miss_n) {
   const size_t smem = 2 * ((size_t)kTcThreads * (TILE / 4 + kTcGPad) + (size_t)(TILE / 32) * N * 32);
+  static const int dbg = getenv("GWSEM_TC5_DBG") ? atoi(getenv("GWSEM_TC5_DBG")) : 0;   // development aid: 1 no MMAs, 2 no tensor-memory stores
   const int grid = (n_snps + kTcThreads - 1) / kTcThreads;
   if (plink1) {
     auto k = class_sums_tc5_kernel<N, TILE, true>;
     GW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, kTcThreads + 32, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums,
-                                             0x00FF0000u, 0x000000FFu, d_counts, count_slot, d_miss_list, d_miss_n, 1u << 30, 1u << 16, 1u << 14);
+    k<<<grid, TcShape<N>::kThreads, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums,
+                                             0x00FF0000u, 0x000000FFu, d_counts, count_slot, d_miss_list, d_miss_n, 1u << 30, 1u << 16, 1u << 14, dbg);
   } else {
     auto k = class_sums_tc5_kernel<N, TILE, false>;
     GW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, kTcThreads + 32, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums,
-                                             0x0000FF00u, 0x00FF0000u, d_counts, count_slot, d_miss_list, d_miss_n, 1u << 30, 1u << 16, 1u << 14);
+    k<<<grid, TcShape<N>::kThreads, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums,
+                                             0x0000FF00u, 0x00FF0000u, d_counts, count_slot, d_miss_list, d_miss_n, 1u << 30, 1u << 16, 1u << 14, dbg);
   }
   GW_CUDA(cudaGetLastError());
   e->launches++;
@@ -329,26 +437,6 @@ void launch_tc5(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_s
 // kernel by IMMA issue + ALU: equal at 16 digit columns (0.70 ms per 65,536 SNPs x 100k people), and the tcgen05
 // kernel wins 1.6x at 64 columns, where mma.sync needs four times the IMMAs for the same expansion.
 // GWSEM_CS_KERNEL=imma|tc5 forces one of them (development aid).
-// Wide chunks (N = 128 digit columns = 32 features per launch) for the series path of the WLS marginals statistics:
-// the one-hot expansion, which bounds the kernel, is shared by twice as many features as in a 64-column launch.
-// d_featq: chunks of tc5_wide_chunk_bytes packed by tc5_pack_chunk; n_feat a multiple of kTcWideFeatures.
-void launch_class_sums_tc5_wide(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
-                                const PeopleLayout& pl, const int8_t* d_featq, const double* d_inv_scale, int n_feat,
-                                double* d_sums) {
-  if (n_snps <= 0 || n_feat <= 0) return;
-  if (n_feat % kTcWideFeatures != 0) fail("wide class sums: %d features (a multiple of %d expected)", n_feat, kTcWideFeatures);
-  if (pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(d_packed) & 15))
-    fail("packed genotype rows must be 16-byte aligned with a pitch that is a multiple of 16 (pitch=%lld)", (long long)pitch);
-  const size_t chunk_bytes = tc5_wide_chunk_bytes(pl.n_pad);
-  const int n_live = (pl.n_pad / 32 + 1) / 2 * 2;
-  for (int f0 = 0, c = 0; f0 < n_feat; f0 += kTcWideFeatures, ++c) {
-    e->prof_begin(kFamSeriesSums);   // one event pair per launch: bench.py's roofline divides by the launch count
-    launch_tc5<kTcWideFeatures * 4, 512>(e, d_packed, pitch, n_snps, plink1, n_live, d_featq + (size_t)c * chunk_bytes, d_inv_scale, f0,
-                                         n_feat, d_sums, nullptr, 0, nullptr, nullptr);
-    e->prof_end(kFamSeriesSums);
-  }
-}
-
 bool cs_use_tc5(int n_feat) {
   const char* v = getenv("GWSEM_CS_KERNEL");   // read when a model is prepared (the digit layout follows the kernel)
   if (v && std::string(v) == "imma") return false;
@@ -395,22 +483,54 @@ void tc5_pack_features(const std::vector<std::vector<int64_t>>& q, int n_pad, co
   }
 }
 
-// One chunk of the same layout from q[feature in chunk][n_pad] (marg_series.cu packs its chunks in parallel);
-// kTcWideFeatures features = 128 digit columns per chunk
+// Chunks of the series path (marg_series.cu packs them in parallel), same K-major layout:
+//   wide   kTcWideFeatures features x 4 digits, feature-major columns (4 f + d): 128 columns
+//   narrow kTcNarrowFeatures features x 3 digits, digit-major columns (48 d + f): 144 columns
 size_t tc5_wide_chunk_bytes(int n_pad) { return (size_t)((n_pad / 32 + 31) / 32 * 32) * (kTcWideFeatures * 4) * 32; }
-void tc5_pack_chunk(const int64_t* q, int n_in_chunk, int n_pad, int8_t* chunk_base) {
-  const int ncol = kTcWideFeatures * 4;
+size_t tc5_narrow_chunk_bytes(int n_pad) { return (size_t)((n_pad / 32 + 31) / 32 * 32) * (kTcNarrowFeatures * 3) * 32; }
+void tc5_pack_chunk(const int64_t* q, int n_in_chunk, int n_pad, int8_t* chunk_base, bool narrow) {
+  const int digits = narrow ? 3 : 4, ncol = narrow ? kTcNarrowFeatures * 3 : kTcWideFeatures * 4;
   for (int fi = 0; fi < n_in_chunk; ++fi)
     for (int i = 0; i < n_pad; ++i) {
       int64_t v = q[(size_t)fi * n_pad + i];
       if (v == 0) continue;
-      for (int d = 0; d < 4; ++d) {
+      for (int d = 0; d < digits; ++d) {
         const int64_t digit = ((v + 128) & 255) - 128;
-        chunk_base[tc5_offset(ncol, i / 32, fi * 4 + d, i % 32)] = (int8_t)digit;
+        const int col = narrow ? d * kTcNarrowFeatures + fi : fi * 4 + d;
+        chunk_base[tc5_offset(ncol, i / 32, col, i % 32)] = (int8_t)digit;
         v = (v - digit) >> 8;
       }
-      if (v != 0) fail("series feature does not fit four balanced base-256 digits");
+      if (v != 0) fail("series feature does not fit %d balanced base-256 digits", digits);
     }
+}
+
+// The series path's class sums: n_wide features (a multiple of 32) in wide chunks, then n_narrow features (a multiple
+// of 48) in narrow chunks; d_sums[snp][2][n_wide + n_narrow].  The one-hot expansion of the packed rows and the
+// re-read of the rows are shared by 128 / 144 digit columns per launch.
+void launch_class_sums_tc5_wide(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
+                                const PeopleLayout& pl, const int8_t* d_featq, const double* d_inv_scale, int n_wide,
+                                int n_narrow, double* d_sums) {
+  if (n_snps <= 0 || n_wide + n_narrow <= 0) return;
+  if (n_wide % kTcWideFeatures != 0 || n_narrow % kTcNarrowFeatures != 0)
+    fail("series class sums: %d + %d features (multiples of %d and %d expected)", n_wide, n_narrow, kTcWideFeatures, kTcNarrowFeatures);
+  if (pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(d_packed) & 15))
+    fail("packed genotype rows must be 16-byte aligned with a pitch that is a multiple of 16 (pitch=%lld)", (long long)pitch);
+  const int n_live = (pl.n_pad / 32 + 1) / 2 * 2, n_feat = n_wide + n_narrow;
+  const int8_t* q = d_featq;
+  for (int f0 = 0; f0 < n_wide; f0 += kTcWideFeatures, q += tc5_wide_chunk_bytes(pl.n_pad)) {
+    e->prof_begin(kFamSeriesSums);   // one event pair per launch: bench.py's roofline divides by the launch count
+    launch_tc5<kTcWideFeatures * 4, 512>(e, d_packed, pitch, n_snps, plink1, n_live, q, d_inv_scale, f0, n_feat, d_sums, nullptr, 0,
+                                         nullptr, nullptr);
+    e->prof_end(kFamSeriesSums);
+    e->series_columns += kTcWideFeatures * 4;
+  }
+  for (int f0 = n_wide; f0 < n_feat; f0 += kTcNarrowFeatures, q += tc5_narrow_chunk_bytes(pl.n_pad)) {
+    e->prof_begin(kFamSeriesSums);
+    launch_tc5<kTcNarrowFeatures * 3, 512>(e, d_packed, pitch, n_snps, plink1, n_live, q, d_inv_scale, f0, n_feat, d_sums, nullptr, 0,
+                                           nullptr, nullptr);
+    e->prof_end(kFamSeriesSums);
+    e->series_columns += kTcNarrowFeatures * 3;
+  }
 }
 
 void launch_class_sums_tc5(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,

@@ -35,6 +35,11 @@ class Engine:
     def launches(self):
         return int(lib().gwsem_engine_launch_count(self.h))
 
+    @property
+    def series_columns(self):
+        """int8 digit columns of the series-path class-sum launches so far, summed over launches"""
+        return int(lib().gwsem_engine_series_columns(self.h))
+
     KERNEL_FAMILIES = ("class_sums", "count_missing", "fit", "decode", "marg_stats", "marg_exact", "marg_series", "series_sums")
 
     def profile(self, enable=True):

@@ -53,9 +53,12 @@ int gwsem_engine_set_stream(gwsem_engine* e, void* cuda_stream);
 int gwsem_engine_synchronize(gwsem_engine* e);
 /* kernels launched by this engine since creation (bench.py's gpu_launches) */
 int64_t gwsem_engine_launch_count(const gwsem_engine* e);
+/* int8 digit columns contracted by the series-path class-sum launches of this engine since creation, summed over the
+ * launches (128 or 144 per launch): int8 operations = 4 x people x SNPs per launch x this (bench.py's tensor roofline) */
+int64_t gwsem_engine_series_columns(const gwsem_engine* e);
 /* Per-launch timing with CUDA events on the launch stream.  gwsem_engine_profile_read fills
  * launches[8] / total_ms[8] for the kernel families {class sums, count+missing, fit, decode,
- * marginals statistics (fast path), marginals statistics (exact path), reserved, reserved}
+ * marginals statistics (per-person path), marginals statistics (exact path), series assembly, series class sums}
  * seen since the previous read, and clears them (synchronises the stream). */
 #define GWSEM_PROFILE_FAMILIES 8
 int gwsem_engine_profile(gwsem_engine* e, int enable);
