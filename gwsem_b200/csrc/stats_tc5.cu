@@ -46,11 +46,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
-      "}\n" ::"r"(addr), "r"(parity), "r"(20000u)   // suspend-time hint (ns): fewer polls while the phase is pending
+      "}\n" ::"r"(addr), "r"(parity)
       : "memory");
 }
 
@@ -63,6 +63,25 @@ __device__ __forceinline__ void tma_bulk_g2s(unsigned dst, const void* src, unsi
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
                : "memory");
+}
+
+// the same copy delivered to the same shared-memory offset of every CTA in `mask` of this cluster, one read of L2;
+// each destination's own mbarrier (same offset) counts the bytes
+__device__ __forceinline__ void tma_bulk_g2s_multicast(unsigned dst, const void* src, unsigned bytes, uint64_t* bar, unsigned short mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)), "h"(mask)
+      : "memory");
+}
+// arrive on the mbarrier at the same offset in CTA `rank` of this cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, unsigned rank) {
+  unsigned remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // 16 consecutive 32-bit columns of this thread's lane
@@ -104,6 +123,9 @@ __device__ __forceinline__ void mma_i8_ts(unsigned d_tmem, unsigned a_tmem, uint
 // g, g + 2, ...; buffers g and g + 2).  One stage is a serial chain for a warp -- expand, wait for the buffer, store,
 // tcgen05.wait::st, fence, arrive: about 600 cycles whatever the MMA size -- so one group alone left the tensor pipe
 // 46 % busy at 128 columns; two chains in flight feed it twice as fast.
+#ifndef GW_TC5_DEBUG
+#define GW_TC5_DEBUG 0
+#endif
 #ifndef GW_TC5_GROUPS
 #define GW_TC5_GROUPS 2
 #endif
@@ -112,7 +134,7 @@ struct TcShape {
   static constexpr int kCols = 2 * N + 3 * 32 <= 128 ? 128 : (2 * N + 3 * 32 <= 256 ? 256 : 512);
   static constexpr int kBufs = (kCols - 2 * N) / 32 < 4 ? (kCols - 2 * N) / 32 : 4;
   static constexpr int kGroups = kBufs == 4 ? GW_TC5_GROUPS : 1;
-  static constexpr int kThreads = kTcThreads * kGroups + 32;
+  static constexpr int kThreads = kTcThreads * kGroups + 64;   // expanding groups + two MMA warps
 };
 
 template <int N, int TILE, bool PLINK1>
@@ -122,6 +144,9 @@ __global__ void __launch_bounds__(TcShape<N>::kThreads)
                           double* __restrict__ sums, unsigned tab1, unsigned tab2, int32_t* __restrict__ counts,
                           int count_slot, int32_t* __restrict__ miss_list, int32_t* __restrict__ miss_n,
                           unsigned m30, unsigned m16, unsigned m14, int dbg) {
+#if !GW_TC5_DEBUG
+  dbg = 0;   // the GWSEM_TC5_DBG switches (development aid) are compiled out unless built with -DGW_TC5_DEBUG=1
+#endif
   constexpr int kSnps = kTcThreads;
   constexpr int kGRow = TILE / 4 + kTcGPad;
   constexpr int kBlocks = TILE / 32;
@@ -137,11 +162,17 @@ __global__ void __launch_bounds__(TcShape<N>::kThreads)
   static_assert(2 * N + kBufs * 32 <= 512, "tensor memory");
   constexpr unsigned kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((128u >> 4) << 24);
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t full_bar[kBufs], empty_bar[kBufs], tile_bar[2];
+  __shared__ __align__(8) uint64_t full_bar[kBufs], empty_bar[kBufs], tile_bar[2], free_bar[2];
   __shared__ unsigned tmem_base_sh;
   __shared__ unsigned mdet_sh[TcShape<N>::kGroups][kTcThreads];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int snp0 = blockIdx.x * kSnps;
+  // Thread-block cluster (1 when launched without one): the CTAs of a cluster walk the same feature digits, so every
+  // tile is read from L2 once and multicast into all of them (each CTA fetches 1 / csize of it for everybody).  L2 -> SM
+  // traffic of the digits was what bounded the kernel (5.2 TB/s, ncu r02b).
+  unsigned crank, csize;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
   const int n_tiles = (n_blocks + kBlocks - 1) / kBlocks;
   constexpr int kPairs = kBlocks / 2;                    // A stages (pairs of blocks) per tile
 
@@ -154,38 +185,43 @@ __global__ void __launch_bounds__(TcShape<N>::kThreads)
   }
   if (tid == 0) {
     for (int b = 0; b < kBufs; ++b) {
-      mbar_init(&full_bar[b], kTcThreads);   // every expanding thread arrives once its lane of the A buffer is stored
-      mbar_init(&empty_bar[b], 1);           // tcgen05.commit: the MMAs that read the buffer are done
+      mbar_init(&full_bar[b], kTcThreads / 32);   // one arrival per expanding warp of the stage's group, once its lanes of the A buffer are stored
+      mbar_init(&empty_bar[b], 2);           // tcgen05.commit of each of the two MMA warps: the MMAs that read the buffer are done
     }
     mbar_init(&tile_bar[0], 1);              // staging of the feature digits: thread 0 announces the bytes of its bulk copy
     mbar_init(&tile_bar[1], 1);
+    mbar_init(&free_bar[0], csize);          // every CTA of the cluster says when this stage of its shared memory may be overwritten
+    mbar_init(&free_bar[1], csize);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (csize > 1) cluster_sync_all();   // every CTA's barriers exist before anybody signals or multicasts into them
   const unsigned tmem_base = tmem_base_sh;
   const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem);
   constexpr unsigned kDHet = 0u, kDHom = (unsigned)N, kA0 = 2u * N;   // A[buf][cls] at kA0 + (2 buf + cls) * 16
 
-  if (warp == 4 * kGroups) {
-    // ---- MMA warp (one lane): per A stage two blocks x two classes, then a commit that frees the buffer
+  if (warp >= 4 * kGroups) {
+    // ---- two MMA warps (one lane each), one per genotype class: per A stage one MMA per 32-person block into the class's
+    // own accumulator, then a commit; the buffer is free when both commits have arrived.  One thread issuing all four
+    // MMAs of a stage was the kernel's critical path: about 150 dependent instructions per stage, 500 cycles, whatever
+    // the expanding warps and the tensor pipe did (ncu r02b: IPC 0.32, tensor pipe 51 % busy at 144 columns).
+    const int cls = warp - 4 * kGroups;
     if (lane == 0) {
       const int total = n_tiles * kPairs;
+      const unsigned d_acc = tmem_base + (cls ? kDHom : kDHet);
       int buf = 0;
       unsigned phase = 0;
       for (int a = 0, tile = 0, kp = 0; a < total; ++a) {
         if (kp == 0) mbar_wait(&tile_bar[tile & 1], (unsigned)((tile >> 1) & 1));   // the feature digits of this tile have landed
         mbar_wait(&full_bar[buf], phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const unsigned b_tile = smem0 + (tile & 1) * kStage + kGStage;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const uint64_t bd = smem_desc(b_tile + (2 * kp + h) * kBBlock, N * 16, 128);
-          const unsigned acc = (a > 0 || h > 0) ? 1u : 0u;
-          if (dbg & 1) continue;   // development aid (GWSEM_TC5_DBG): no MMAs
-          mma_i8_ts(tmem_base + kDHet, tmem_base + kA0 + (2 * buf + 0) * 16 + h * 8, bd, kIdesc, acc);
-          mma_i8_ts(tmem_base + kDHom, tmem_base + kA0 + (2 * buf + 1) * 16 + h * 8, bd, kIdesc, acc);
+        const unsigned b_blk = smem0 + (tile & 1) * kStage + kGStage + (2 * kp) * kBBlock;
+        const unsigned a_buf = tmem_base + kA0 + (2 * buf + cls) * 16;
+        if (!(dbg & 1)) {   // development aid (GWSEM_TC5_DBG): no MMAs
+          mma_i8_ts(d_acc, a_buf, smem_desc(b_blk, N * 16, 128), kIdesc, a > 0 ? 1u : 0u);
+          mma_i8_ts(d_acc, a_buf + 8, smem_desc(b_blk + kBBlock, N * 16, 128), kIdesc, 1u);
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                          (unsigned)__cvta_generic_to_shared(&empty_bar[buf]))
@@ -216,14 +252,30 @@ __global__ void __launch_bounds__(TcShape<N>::kThreads)
     auto load_stage = [&](int tile, int s) {
       const int off = min(tile * (TILE / 4) + gc * 16, last_piece);
       const unsigned d = gdst + s * kStage;
+      if (!(dbg & 16)) {   // development aid (GWSEM_TC5_DBG): no packed rows
 #pragma unroll
-      for (int k = 0; k < kPasses; ++k)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + k * kRowsPerPass * kGRow), "l"(gp[k] + off) : "memory");
+        for (int k = 0; k < kPasses; ++k)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + k * kRowsPerPass * kGRow), "l"(gp[k] + off) : "memory");
+      }
       asm volatile("cp.async.commit_group;" ::: "memory");
       if (tid == 0) {
         // the MMAs that read this stage's digits are done (the empty-barrier wait before this call covers the previous tile)
+        if (dbg & 8) {   // development aid (GWSEM_TC5_DBG): no feature digits (what does their ingest cost?)
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&tile_bar[s])) : "memory");
+          return;
+        }
         mbar_arrive_expect_tx(&tile_bar[s], (unsigned)kBStage);
-        tma_bulk_g2s(smem0 + s * kStage + kGStage, Bq + (int64_t)tile * kBStage, (unsigned)kBStage, &tile_bar[s]);
+        if (csize == 1) {
+          tma_bulk_g2s(smem0 + s * kStage + kGStage, Bq + (int64_t)tile * kBStage, (unsigned)kBStage, &tile_bar[s]);
+        } else {
+          // tell every CTA of the cluster that this stage of mine is free, wait until all of theirs are, then fetch my
+          // share of the tile for everybody
+          for (unsigned r = 0; r < csize; ++r) mbar_arrive_remote(&free_bar[s], r);
+          mbar_wait(&free_bar[s], (unsigned)((tile >> 1) & 1));
+          const unsigned part = (unsigned)kBStage / csize;
+          tma_bulk_g2s_multicast(smem0 + s * kStage + kGStage + crank * part, Bq + (int64_t)tile * kBStage + crank * part, part,
+                                 &tile_bar[s], (unsigned short)((1u << csize) - 1u));
+        }
       }
     };
     auto expanders_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kExp) : "memory"); };
@@ -274,8 +326,9 @@ __global__ void __launch_bounds__(TcShape<N>::kThreads)
   }
       GW_EXPAND(0, w4.x) GW_EXPAND(1, w4.y) GW_EXPAND(2, w4.z) GW_EXPAND(3, w4.w)
 #undef GW_EXPAND
-      if (a >= kBufs) {   // the MMAs that read this buffer kBufs stages ago must be done
-        mbar_wait(&empty_bar[BUF], phase ^ 1u);
+      if (a >= kBufs) {   // the MMAs that read this buffer kBufs stages ago must be done (one lane polls for its warp)
+        if (lane == 0) mbar_wait(&empty_bar[BUF], phase ^ 1u);
+        __syncwarp();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
       // That commit also covers every MMA of the previous tile once kp >= kBufs, and all expanding threads left
@@ -292,7 +345,11 @@ __global__ void __launch_bounds__(TcShape<N>::kThreads)
         mdet |= x & 1u;
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&full_bar[BUF])) : "memory");
+      // one arrival per warp (tcgen05.wait::st is warp-wide: every lane's stores are done): 128 per-thread arrivals
+      // on one barrier word per stage were a serial cost of their own
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&full_bar[BUF])) : "memory");
       a += kGroups;
       kp += kGroups;
       if (kp >= kPairs) { kp -= kPairs; ++tile; }
@@ -351,10 +408,11 @@ __global__ void __launch_bounds__(TcShape<N>::kThreads)
     if constexpr (N == kTcNarrowFeatures * 3) {
       // three balanced base-256 digits per feature, digit-major: columns [d * 48, d * 48 + 48) hold digit d of the chunk's
       // 48 features (the SNP-dependent rows of Muthen's A and B need 1e-6, not 2^-30, of the feature's range)
-      static_assert(kGroups == 2, "one class per group");
-      const int cls = grp;
+      static_assert(kGroups == 2 || kGroups == 4, "one class per group (pair)");
+      const int cls = grp & 1;
 #pragma unroll
       for (int g3 = 0; g3 < kTcNarrowFeatures / 16; ++g3) {
+        if (kGroups == 4 && (g3 & 1) != (grp >> 1)) continue;   // the two groups of a class share its feature groups
         int v0[16], v1[16], v2[16];
         const unsigned d_base = lane_base + (cls ? kDHom : kDHet) + 16 * g3;
         tmem_ld16(d_base, v0);
@@ -403,6 +461,7 @@ __global__ void __launch_bounds__(TcShape<N>::kThreads)
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (csize > 1) cluster_sync_all();   // nobody leaves while a neighbour may still signal its barriers
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kCols) : "memory");
   }
@@ -414,17 +473,36 @@ void launch_tc5(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_s
                 int count_slot, int32_t* d_miss_list, int32_t* d_miss_n) {
   const size_t smem = 2 * ((size_t)kTcThreads * (TILE / 4 + kTcGPad) + (size_t)(TILE / 32) * N * 32);
   static const int dbg = getenv("GWSEM_TC5_DBG") ? atoi(getenv("GWSEM_TC5_DBG")) : 0;   // development aid: 1 no MMAs, 2 no tensor-memory stores
-  const int grid = (n_snps + kTcThreads - 1) / kTcThreads;
+  // clusters of CTAs share every feature tile through one multicast read of L2 (the series path's launches; the chunk's
+  // tile bytes must split into 16-byte granular shares).  GWSEM_TC5_CLUSTER sets the size; default 1 = off: measured, the
+  // lock step it forces on the CTAs costs more than the traffic it saves (24 launches: 11.0 ms alone, 14.5 in pairs, 23.0 in fours).
+  static const int cl_env = getenv("GWSEM_TC5_CLUSTER") ? atoi(getenv("GWSEM_TC5_CLUSTER")) : 1;
+  int cluster = (N >= 128 && (cl_env == 2 || cl_env == 4)) ? cl_env : 1;
+  int grid = (n_snps + kTcThreads - 1) / kTcThreads;
+  if (grid < cluster) cluster = 1;
+  grid = (grid + cluster - 1) / cluster * cluster;   // CTAs past the batch repeat its last rows and store nothing
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TcShape<N>::kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = e->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cluster > 1 ? 1 : 0;
   if (plink1) {
     auto k = class_sums_tc5_kernel<N, TILE, true>;
     GW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, TcShape<N>::kThreads, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums,
-                                             0x00FF0000u, 0x000000FFu, d_counts, count_slot, d_miss_list, d_miss_n, 1u << 30, 1u << 16, 1u << 14, dbg);
+    GW_CUDA(cudaLaunchKernelEx(&cfg, k, d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums, 0x00FF0000u, 0x000000FFu,
+                               d_counts, count_slot, d_miss_list, d_miss_n, 1u << 30, 1u << 16, 1u << 14, dbg));
   } else {
     auto k = class_sums_tc5_kernel<N, TILE, false>;
     GW_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, TcShape<N>::kThreads, smem, e->stream>>>(d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums,
-                                             0x0000FF00u, 0x00FF0000u, d_counts, count_slot, d_miss_list, d_miss_n, 1u << 30, 1u << 16, 1u << 14, dbg);
+    GW_CUDA(cudaLaunchKernelEx(&cfg, k, d_packed, pitch, n_snps, n_blocks, Bq, inv_scale, f0, n_feat, d_sums, 0x0000FF00u, 0x00FF0000u,
+                               d_counts, count_slot, d_miss_list, d_miss_n, 1u << 30, 1u << 16, 1u << 14, dbg));
   }
   GW_CUDA(cudaGetLastError());
   e->launches++;
