@@ -176,6 +176,8 @@ void gwsem_engine_destroy(gwsem_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  for (void* q : e->pinned_stage)
+    if (q) cudaFreeHost(q);
   delete e;
 }
 

@@ -88,6 +88,10 @@ struct gwsem_engine {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
+  // pinned host staging of gwsem_gwas_run (two slots of packed rows), kept between calls: pinning a few hundred MB
+  // costs more than fitting the batch it carries
+  void* pinned_stage[2] = {nullptr, nullptr};
+  size_t pinned_stage_bytes[2] = {0, 0};
   int64_t series_columns = 0;   // digit columns of the series-path class-sum launches, summed over launches
   // scratch reused by the host-pointer entry points
   gwsem::DeviceBuffer<uint8_t> d_packed;

@@ -47,7 +47,7 @@ struct Stager {
   PinnedBuffer<uint8_t> h_bytes;
   PinnedBuffer<uint8_t> h_bgen[2];   // inflated bgen blocks, read ahead like h_fixed
   std::vector<uint64_t> bgen_off[2];
-  PinnedBuffer<uint8_t> h_fixed[2];  // fixed-width records: read ahead by a host thread (see read_fixed)
+  struct Borrowed { uint8_t* p = nullptr; } h_fixed[2];  // fixed-width records: read ahead by a host thread (see read_fixed); the engine owns the memory
   DeviceBuffer<uint8_t> d_bytes, d_vt, d_rows;
   DeviceBuffer<uint64_t> d_off;
   DeviceBuffer<int32_t> d_base, d_err;
@@ -113,7 +113,17 @@ struct Stager {
   }
   void ensure_fixed(int max_rows) {  // on the calling thread: pinned allocation is a CUDA call
     const int64_t row_bytes = ((int64_t)s->n_samples + 3) / 4;
-    for (auto& b : h_fixed) b.ensure((size_t)max_rows * row_bytes + 16);
+    for (int b = 0; b < 2; ++b) {
+      const size_t need = (size_t)max_rows * row_bytes + 16;
+      if (e->pinned_stage_bytes[b] < need) {
+        if (e->pinned_stage[b]) cudaFreeHost(e->pinned_stage[b]);
+        e->pinned_stage[b] = nullptr;
+        e->pinned_stage_bytes[b] = 0;
+        GW_CUDA(cudaHostAlloc(&e->pinned_stage[b], need, cudaHostAllocDefault));
+        e->pinned_stage_bytes[b] = need;
+      }
+      h_fixed[b].p = static_cast<uint8_t*>(e->pinned_stage[b]);
+    }
   }
   void upload_fixed(int n, int slot) {
     cudaStream_t st = e->stream;
@@ -376,6 +386,17 @@ void append_double(std::string& out, double v) {  // as printf("%.15g"), NA for 
   out.append(buf, r.ptr);
 }
 
+// The log holds the variances and a few covariances of the parameters, not the P x P matrix: gather them on the device
+// (out[snp][i] = vcov[snp][pa[i]][pb[i]]) so that a batch's trip to the host is about 1 KB per SNP instead of 8 P^2 bytes.
+__global__ void gather_vcov_kernel(const double* __restrict__ vcov, int P, const int32_t* __restrict__ pa,
+                                   const int32_t* __restrict__ pb, int np, int n, double* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)n * np) return;
+  const int64_t k = e / np;
+  const int i = (int)(e % np);
+  out[e] = vcov[k * P * P + (int64_t)pa[i] * P + pb[i]];
+}
+
 // One batch of per-SNP results on the host, formatted into log rows by a pool of threads while
 // the next batch is staged and fitted.
 struct RowBatch {
@@ -384,15 +405,15 @@ struct RowBatch {
   // pinned: the device -> host copies of a batch run at link speed and asynchronously, behind the next batch's kernels
   PinnedBuffer<double> est, vcov, fit, maf;
   PinnedBuffer<int32_t> n_used, status, catch_code, catch_var, iterations;
-  void resize(int rows, int P) {
+  void resize(int rows, int P, int n_vc) {   // vcov: the n_vc gathered entries of every row
     n = rows;
     variant.resize(rows);
-    est.ensure((size_t)rows * P); vcov.ensure((size_t)rows * P * P); fit.ensure(rows); maf.ensure(rows);
+    est.ensure((size_t)rows * P); vcov.ensure((size_t)rows * n_vc); fit.ensure(rows); maf.ensure(rows);
     n_used.ensure(rows); status.ensure(rows); catch_code.ensure(rows); catch_var.ensure(rows); iterations.ensure(rows);
   }
   gwsem_result view() {
     gwsem_result h;
-    h.est = est.p; h.vcov = vcov.p; h.fit = fit.p; h.maf = maf.p; h.n_used = n_used.p;
+    h.est = est.p; h.vcov = nullptr; h.fit = fit.p; h.maf = maf.p; h.n_used = n_used.p;   // (vcov travels gathered)
     h.status = status.p; h.catch_code = catch_code.p; h.catch_var = catch_var.p; h.iterations = iterations.p;
     return h;
   }
@@ -574,7 +595,7 @@ int gwsem_gwas_run(gwsem_model* m, gwsem_source* s, const gwsem_job* job, int64_
         line += std::to_string(b.n_used.p[k]);
         line += '\t';
         line += caught ? "NA" : status_text(b.status.p[k]);
-        for (auto& pr : vc) { line += '\t'; append_double(line, b.vcov.p[(size_t)k * P * P + (size_t)pr.first * P + pr.second]); }
+        for (size_t i = 0; i < vc.size(); ++i) { line += '\t'; append_double(line, b.vcov.p[(size_t)k * vc.size() + i]); }
         if (s->kind == gwsem_source::kPgen) {
           if (!ctx.lines.empty()) { line += '\t'; line += ctx.fields(b.variant[k]); }
         } else {
@@ -652,6 +673,17 @@ int gwsem_gwas_run(gwsem_model* m, gwsem_source* s, const gwsem_job* job, int64_
     double t_stage = 0, t_fit = 0, t_wait = 0, t_dl = 0;
     const size_t cap = std::min<size_t>(batch, todo.size());
     m->ensure_result_buffers((int)(2 * cap));
+    const int n_vc = (int)vc.size();
+    DeviceBuffer<int32_t> d_vc;
+    DeviceBuffer<double> d_vcg;   // gathered entries, two halves like the result buffers
+    {
+      std::vector<int32_t> hv(2 * (size_t)n_vc);
+      for (int i = 0; i < n_vc; ++i) { hv[i] = vc[i].first; hv[n_vc + i] = vc[i].second; }
+      d_vc.ensure(hv.size() + 1);
+      GW_CUDA(cudaMemcpyAsync(d_vc.p, hv.data(), hv.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      GW_CUDA(cudaStreamSynchronize(st));
+      d_vcg.ensure(2 * cap * (size_t)n_vc + 1);
+    }
     cudaStream_t out_stream = nullptr;
     cudaEvent_t ev_fitted[2] = {nullptr, nullptr}, ev_down[2] = {nullptr, nullptr}, ev_up[2] = {nullptr, nullptr};
     GW_CUDA(cudaStreamCreateWithFlags(&out_stream, cudaStreamNonBlocking));
@@ -726,6 +758,12 @@ int gwsem_gwas_run(gwsem_model* m, gwsem_source* s, const gwsem_job* job, int64_
       }
       double c1 = 0;
       if (timing) { GW_CUDA(cudaStreamSynchronize(st)); c1 = now(); t_fit += c1 - c0; }
+      double* vcg = d_vcg.p + (size_t)slot * cap * n_vc;
+      if (n_vc > 0) {
+        const int64_t work = (int64_t)n * n_vc;
+        gather_vcov_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(dres.vcov, P, d_vc.p, d_vc.p + n_vc, n_vc, n, vcg);
+        GW_CUDA(cudaGetLastError());
+      }
       GW_CUDA(cudaEventRecord(ev_fitted[slot], st));
       // the previous batch: its results are on the host once its download is done; hand it to the writer
       // (one batch being written, one being downloaded, one on the device)
@@ -740,10 +778,12 @@ int gwsem_gwas_run(gwsem_model* m, gwsem_source* s, const gwsem_job* job, int64_
         pending.get();
       }
       RowBatch& cur = rb[slot];   // (its previous contents were written two batches ago: that writer was joined above)
-      cur.resize(n, P);
+      cur.resize(n, P, n_vc);
       std::copy(v, v + n, cur.variant.begin());
       GW_CUDA(cudaStreamWaitEvent(out_stream, ev_fitted[slot], 0));
       m->download_result(cur.view(), dres, n, 0, out_stream);
+      if (n_vc > 0)
+        GW_CUDA(cudaMemcpyAsync(cur.vcov.p, vcg, sizeof(double) * (size_t)n * n_vc, cudaMemcpyDeviceToHost, out_stream));
       GW_CUDA(cudaEventRecord(ev_down[slot], out_stream));
       have_prev = true;
       last_slot = slot;
