@@ -617,15 +617,15 @@ def gwas_file_to_log(rk, which, packed, sem, n_snps):
         # the call has a fixed cost (pinned staging for two batches of packed rows and of results, the .pvar, the first
         # read): time a quarter of the file and the whole file, report the whole-file rate, the marginal rate and the rest
         n_part = max(1, n_snps // 4)
-        t_part = run(list(range(1, n_part + 1)))
-        t_all = run(None)
+        t_all = run(None)           # (its first pass also pins the engine's staging buffers)
         log_bytes = os.path.getsize(out)
         with open(out) as f:
             n_rows = sum(1 for _ in f) - 1
         assert n_rows == n_snps, (n_rows, n_snps)
-        marginal = (n_snps - n_part) / max(t_all - t_part, 1e-9)
+        t_part = run(list(range(1, n_part + 1)))
+        marginal = (n_snps - n_part) / (t_all - t_part) if t_all > t_part else None
         return {"value": n_snps / t_all, "unit": UNIT, "snps": n_snps, "seconds": t_all,
-                "marginal_snps_per_s": marginal, "fixed_cost_s": max(0.0, t_part - n_part / marginal),
+                "marginal_snps_per_s": marginal, "fixed_cost_s": max(0.0, t_part - n_part / marginal) if marginal else None,
                 "file_bytes": os.path.getsize(stem + ".pgen"), "log_bytes": log_bytes,
                 "what": "gwsem_gwas_run: page-cached mode-0x02 .pgen + .pvar -> per-SNP fit -> tab-separated checkpoint log "
                         "(read-ahead thread, wave-sized batches, results copied out behind the next batch, threaded row "

@@ -1022,7 +1022,7 @@ __host__ __device__ inline int fast_table_bytes(const FitProgram& fp, const Marg
   return b;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(384)
     marg_fit_fast_kernel(FitProgram fp_in, MargProgram mp_in, int n_snps, const double* __restrict__ summary,
                          const double* __restrict__ maf_in, gwsem_result res) {
   extern __shared__ double smem_d[];
