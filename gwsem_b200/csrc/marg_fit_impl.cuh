@@ -5,7 +5,7 @@ namespace GW_MF_NS {
 constexpr int LANES = GW_MF_LANES;
 
 // model-implied statistic vector in the layout of mp.stat_*
-__device__ void implied_stats(const FitProgram& fp, const MargProgram& mp, ModelEval<LANES>& ev, const WarpScratch& ws,
+__device__ __noinline__ void implied_stats(const FitProgram& fp, const MargProgram& mp, ModelEval<LANES>& ev, const WarpScratch& ws,
                               double* sm, const double* theta, double* sig, int lane) {
   const int nv = fp.nv;
   ev.implied(theta, sm + ws.sig);  // fills Z, C (and the covariance vech, unused here)
@@ -47,7 +47,7 @@ __device__ void implied_stats(const FitProgram& fp, const MargProgram& mp, Model
 // Analytic Jacobian of the model-implied statistics (RAM derivatives chained through the
 // standardisation of ordinal rows) at thv: out[i * n_c + c] = d sigma_{rows[i]} / d theta_{cols[c]}
 // (rows / cols null: all of them); `pairs`: out[i] = d sigma_{rows[i]} / d theta_{cols[i]}.
-__device__ void marg_jacobian(const FitProgram& fp, const MargProgram& mp, ModelEval<LANES>& ev, const WarpScratch& ws,
+__device__ __noinline__ void marg_jacobian(const FitProgram& fp, const MargProgram& mp, ModelEval<LANES>& ev, const WarpScratch& ws,
                               double* sm, const double* thv, double* sig, double* out, const int32_t* rows, int n_r,
                               const int32_t* cols, int n_c, bool pairs, int lane, bool fresh = true) {
   const int nv = fp.nv;
@@ -1022,7 +1022,7 @@ __host__ __device__ inline int fast_table_bytes(const FitProgram& fp, const Marg
   return b;
 }
 
-__global__ void __launch_bounds__(384)
+__global__ void __launch_bounds__(384, 1)
     marg_fit_fast_kernel(FitProgram fp_in, MargProgram mp_in, int n_snps, const double* __restrict__ summary,
                          const double* __restrict__ maf_in, gwsem_result res) {
   extern __shared__ double smem_d[];
