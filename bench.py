@@ -20,9 +20,9 @@ fit, SEs).
   roofline      dominant kernel (class_sums_tc5_kernel<128,512>: exact int8 contraction on tcgen05) against the
                 tensor peak: int8 ops of the launch / CUDA-event launch time; the FP64 figure SURVEY.md section
                 8d counts for the per-person algorithm (1,624 N flop per SNP) rides along as fp64_equivalent
-  cpu_baseline  the same path on the host cores: numpy restatement of the OpenMx WLS marginals fit
-                (oracle/marginals_oracle.py, which recomputes every statistic per SNP as OpenMx does;
-                vectorised over people -- the interpreter is < 2 % of its time)
+  cpu_baseline  the same path on the host cores: compiled (gcc -O3) restatement of the OpenMx WLS marginals fit
+                (oracle/marginals_port.c == oracle/marginals_oracle.py, which recomputes every statistic per
+                SNP as OpenMx does), one process per core
   variants      the same workload with 0.5 % missing calls (every SNP then takes the exact
                 re-estimation kernel), and GWAS() file -> log through gwsem_gwas_run
   item_c2       BASELINE.json configs[1] (buildItem, 100k people x 100k SNPs) measured the same way,
@@ -246,9 +246,13 @@ def _cpu_worker(args):
     codes = np.load(path, mmap_mode="r")
     lut = np.array([0.0, 1.0, 2.0, np.nan])
     ok = 0
+    port = None
+    if which == "c3":
+        from port_lib import MarginalsPort     # oracle/marginals_port.c: the same algorithm compiled with -O3
+        port = MarginalsPort(flat, cols, ncat)
     for i in range(lo, hi):
         g = lut[codes[i]]
-        out = mo.fit_snp_marginals(flat, cols, g, ncat) if which == "c3" else fo.fit_snp_cumulants(flat, cols, g)
+        out = port.fit(g) if port is not None else fo.fit_snp_cumulants(flat, cols, g)
         ok += out["status"] == "OK"
     return ok
 
@@ -274,10 +278,12 @@ def cpu_baseline(which, sample_snps, cores, repeats=1):
             best = dt if best is None else min(best, dt)
     os.remove(path)
     os.rmdir(tmp)
-    kind = ("numpy restatement of the OpenMx WLS fit (" +
-            ("oracle/marginals_oracle.py: every marginal statistic re-estimated per SNP, as OpenMx does; vectorised over people"
-             if which == "c3" else "oracle/fit_oracle.py; a per-SNP Python loop, interpreter-bound at this size") +
-            "), one process per core; model built through gwsem_b200.model.flatten")
+    kind = (("compiled (gcc -O3) restatement of the OpenMx WLS marginals fit, oracle/marginals_port.c: every marginal statistic "
+             "re-estimated per SNP, as OpenMx does (== oracle/marginals_oracle.py to 1e-6, tests/test_oracle_marginals_port.py; the "
+             "reference's vignettes call 1-2 s per SNP and process reasonable at this size)"
+             if which == "c3" else "numpy restatement of the OpenMx WLS cumulants fit, oracle/fit_oracle.py; a per-SNP Python loop, "
+             "interpreter-bound at this size") +
+            ", one process per core; model built through gwsem_b200.model.flatten")
     return sample_snps / best, f"{sample_snps} SNPs x {w['n_people']} people of the same synthetic cohort; {kind}"
 
 
