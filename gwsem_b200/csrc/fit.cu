@@ -39,11 +39,63 @@ __device__ double central_moment(const FitProgram& fp, const int* vars, int k, c
   return sum;
 }
 
+// The model description is a few KB of small tables that every step of the fit walks through (the moment index, RAM
+// cells, parameter lists).  Read from global memory their latency was most of the kernel's time (the lesson of
+// marg_fit_fast_kernel): every CTA copies them into shared memory first.
+template <typename T>
+__device__ const T* stage_fit_table(const T* src, int n, unsigned char* base, int& cursor) {
+  T* dst = reinterpret_cast<T*>(base + cursor);
+  if (src)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+  cursor += (n * (int)sizeof(T) + 7) & ~7;
+  return src ? dst : nullptr;
+}
+__host__ __device__ inline int fit_table_bytes(const FitProgram& fp) {
+  auto r8 = [](int b) { return (b + 7) & ~7; };
+  const int p1 = fp.p + 1;
+  return r8(8 * fp.nf) + r8(4 * p1 * p1 * p1 * p1) + 2 * r8(4 * fp.q) + 5 * r8(4 * fp.n_cells) + r8(8 * fp.n_cells) +
+         r8(4 * (fp.P + 1)) + 2 * r8(8 * fp.P);
+}
+
 template <int LANES>
 __global__ void __launch_bounds__(128)
-    fit_cumulants_kernel(FitProgram fp, int n_snps, const double* __restrict__ Rtab, const int32_t* __restrict__ n_rows,
-                         const double* __restrict__ maf_in, gwsem_result res) {
+    fit_cumulants_kernel(FitProgram fp_in, int n_snps, const double* __restrict__ Rtab, const int32_t* __restrict__ n_rows,
+                         const double* __restrict__ maf_in, gwsem_result res, int scratch_doubles) {
   extern __shared__ double smem_d[];
+  __shared__ __align__(16) unsigned char fp_raw[sizeof(FitProgram)];
+  // (one thread per SNP, LANES == 1: small models whose tables sit in L1 anyway; measured slower with the staging)
+  const FitProgram& fp = LANES == 1 ? fp_in : *reinterpret_cast<const FitProgram*>(fp_raw);
+  if (LANES > 1) {
+    FitProgram& fps = *reinterpret_cast<FitProgram*>(fp_raw);
+    unsigned char* tab = reinterpret_cast<unsigned char*>(smem_d + scratch_doubles);
+    int cur = 0;
+    const int p1 = fp_in.p + 1, nc = fp_in.n_cells, P = fp_in.P;
+    const double* tot = stage_fit_table(fp_in.tot, fp_in.nf, tab, cur);
+    const int32_t* idx4 = stage_fit_table(fp_in.idx4, p1 * p1 * p1 * p1, tab, cur);
+    const int32_t* stat_i = stage_fit_table(fp_in.stat_i, fp_in.q, tab, cur);
+    const int32_t* stat_j = stage_fit_table(fp_in.stat_j, fp_in.q, tab, cur);
+    const int32_t* cell_mat = stage_fit_table(fp_in.cell_mat, nc, tab, cur);
+    const int32_t* cell_row = stage_fit_table(fp_in.cell_row, nc, tab, cur);
+    const int32_t* cell_col = stage_fit_table(fp_in.cell_col, nc, tab, cur);
+    const int32_t* cell_par = stage_fit_table(fp_in.cell_par, nc, tab, cur);
+    const int32_t* par_cells;
+    {
+      int c2 = cur;   // every free cell is listed once: at most nc entries
+      par_cells = stage_fit_table(fp_in.par_cells, min(nc, fp_in.par_cell_ptr[P]), tab, c2);
+      cur += (4 * nc + 7) & ~7;
+    }
+    const double* cell_val = stage_fit_table(fp_in.cell_val, nc, tab, cur);
+    const int32_t* par_cell_ptr = stage_fit_table(fp_in.par_cell_ptr, P + 1, tab, cur);
+    const double* par_start = stage_fit_table(fp_in.par_start, P, tab, cur);
+    const double* par_lbound = stage_fit_table(fp_in.par_lbound, P, tab, cur);
+    if (threadIdx.x == 0) {
+      fps = fp_in;
+      fps.tot = tot; fps.idx4 = idx4; fps.stat_i = stat_i; fps.stat_j = stat_j; fps.cell_mat = cell_mat; fps.cell_row = cell_row;
+      fps.cell_col = cell_col; fps.cell_par = cell_par; fps.par_cells = par_cells; fps.cell_val = cell_val;
+      fps.par_cell_ptr = par_cell_ptr; fps.par_start = par_start; fps.par_lbound = par_lbound;
+    }
+    __syncthreads();
+  }
   const int group = threadIdx.x / LANES, lane = threadIdx.x % LANES;
   const int snp = blockIdx.x * (blockDim.x / LANES) + group;
   if (snp >= n_snps) return;
@@ -261,20 +313,25 @@ void launch_fit_cumulants(gwsem_engine* e, const FitProgram& fp, int n_snps, con
                           const double* d_maf, const gwsem_result& d_res) {
   if (n_snps <= 0) return;
   const size_t per_snp = fit_scratch_doubles(fp.p, fp.q, fp.nv, fp.P, fp.nf) * sizeof(double);
+  const size_t tables = (size_t)fit_table_bytes(fp) + 16;
   e->prof_begin(kFamFit);
   if (per_snp * 64 <= 96 * 1024) {
     // small model: one thread per SNP, each with its own shared-memory slab
     const int threads = 64;
-    const size_t smem = (per_snp + 8) * threads;
+    const size_t scratch = (per_snp + 8) * threads;
+    const size_t smem = scratch;   // (no staged tables in this variant: they would only cost occupancy)
     GW_CUDA(cudaFuncSetAttribute(fit_cumulants_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fit_cumulants_kernel<1><<<(n_snps + threads - 1) / threads, threads, smem, e->stream>>>(fp, n_snps, d_R, d_n, d_maf, d_res);
+    fit_cumulants_kernel<1><<<(n_snps + threads - 1) / threads, threads, smem, e->stream>>>(fp, n_snps, d_R, d_n, d_maf, d_res,
+                                                                                            (int)(scratch / sizeof(double)));
   } else {
     int warps = 4;
-    while (warps > 1 && per_snp * warps > 200 * 1024) warps >>= 1;
-    if (per_snp * warps > 227 * 1024) fail("model too large for the per-SNP fit kernel (%zu bytes of scratch)", per_snp);
-    const size_t smem = per_snp * warps;
+    while (warps > 1 && per_snp * warps + tables > 200 * 1024) warps >>= 1;
+    if (per_snp * warps + tables > 227 * 1024) fail("model too large for the per-SNP fit kernel (%zu bytes of scratch)", per_snp);
+    const size_t scratch = per_snp * warps;
+    const size_t smem = scratch + tables;
     GW_CUDA(cudaFuncSetAttribute(fit_cumulants_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fit_cumulants_kernel<32><<<(n_snps + warps - 1) / warps, warps * 32, smem, e->stream>>>(fp, n_snps, d_R, d_n, d_maf, d_res);
+    fit_cumulants_kernel<32><<<(n_snps + warps - 1) / warps, warps * 32, smem, e->stream>>>(fp, n_snps, d_R, d_n, d_maf, d_res,
+                                                                                             (int)(scratch / sizeof(double)));
   }
   GW_CUDA(cudaGetLastError());
   e->prof_end(kFamFit);
