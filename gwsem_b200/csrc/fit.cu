@@ -194,13 +194,13 @@ __global__ void __launch_bounds__(128)
   for (int k = lane; k < P; k += LANES) theta[k] = fp.par_start[k];
   gsync<LANES>();
   double F = objective(theta, r);
+  bool at_theta = true;   // Z and C in the scratch were last evaluated at theta: the Jacobian can use them as they are
   double lam = 1e-4;
   int status = GWSEM_STATUS_ITERATION_LIMIT;
   int it = 0;
   const int max_iter = 200;
   for (it = 1; it <= max_iter; ++it) {
-    // implied() for theta was the last evaluation at this point (Z, C valid)
-    ev.implied(theta, sig);
+    if (!at_theta) ev.implied(theta, sig);
     ev.jacobian(J);
     warp_forward_solve<LANES>(L, q, J, P, P, lane);  // J~ = L^-1 J
     for (int k = lane; k < P; k += LANES) {
@@ -247,6 +247,7 @@ __global__ void __launch_bounds__(128)
       }
       gsync<LANES>();
       Fc = objective(cand, sm + ws.rc);
+      at_theta = false;
       if (isfinite(Fc) && Fc <= F) { improved = true; break; }
       lam *= 10;
     }
@@ -264,13 +265,14 @@ __global__ void __launch_bounds__(128)
     for (int e = lane; e < q; e += LANES) r[e] = (sm + ws.rc)[e];
     gsync<LANES>();
     F = Fc;
+    at_theta = true;   // theta = cand, where the objective was just evaluated
     lam = fmax(lam / 10, 1e-12);
     if (step < 1e-10 || dF <= 1e-14 * (1 + F)) { status = GWSEM_STATUS_OK; break; }
   }
   if (it > max_iter) it = max_iter;
 
   // ---- O8: vcov = (J' W J)^-1 at the solution
-  ev.implied(theta, sig);
+  if (!at_theta) ev.implied(theta, sig);
   ev.jacobian(J);
   warp_forward_solve<LANES>(L, q, J, P, P, lane);
   for (int idx = lane; idx < P * P; idx += LANES) {
