@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(128)
   for (int k = lane; k < P; k += LANES) theta[k] = fp.par_start[k];
   gsync<LANES>();
   double F = objective(theta, r);
+  double dF_prev = 0.0;
   bool at_theta = true;   // Z and C in the scratch were last evaluated at theta: the Jacobian can use them as they are
   double lam = 1e-4;
   int status = GWSEM_STATUS_ITERATION_LIMIT;
@@ -267,7 +268,16 @@ __global__ void __launch_bounds__(128)
     F = Fc;
     at_theta = true;   // theta = cand, where the objective was just evaluated
     lam = fmax(lam / 10, 1e-12);
-    if (step < 1e-10 || dF <= 1e-14 * (1 + F)) { status = GWSEM_STATUS_OK; break; }
+    // F is on the chi-square scale: a decrease dF moved the estimate by about sqrt(2 dF) standard errors; with the
+    // contraction kappa = sqrt(dF / previous dF) seen so far, sqrt(2 dF) kappa / (1 - kappa) standard errors are left.
+    // Stop below 2e-6 (as marg_fit_fast_kernel does); slowly contracting fits run on to the oracle's own rule.
+    bool close_enough = false;
+    if (it >= 2 && dF_prev > 0.0 && dF >= 0.0) {
+      const double kappa = sqrt(dF / dF_prev);
+      close_enough = kappa < 0.5 && sqrt(2.0 * dF) * kappa / (1.0 - kappa) <= 2e-6;
+    }
+    dF_prev = dF;
+    if (step < 1e-10 || dF <= 1e-14 * (1 + F) || close_enough) { status = GWSEM_STATUS_OK; break; }
   }
   if (it > max_iter) it = max_iter;
 
