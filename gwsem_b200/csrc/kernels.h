@@ -82,7 +82,8 @@ void launch_assemble_moments(gwsem_engine* e, const FitProgram& fp, const People
                              int32_t* d_n, double* d_maf);
 // (ii) any genotype column (dosages, bgen): d_geno[snp][n_pad] doubles in file order, NaN = missing
 void launch_power_sums(gwsem_engine* e, const FitProgram& fp, const PeopleLayout& pl, int n_snps,
-                       const double* d_geno, const double* d_featT, int n_featm_pad, double* d_R, int32_t* d_n);
+                       const double* d_geno, const double* d_featT, int n_featm_pad, double* d_R, int32_t* d_n,
+                       int moment_order = 4);
 void launch_fit_cumulants(gwsem_engine* e, const FitProgram& fp, int n_snps, const double* d_R, const int32_t* d_n,
                           const double* d_maf, const gwsem_result& d_res);
 

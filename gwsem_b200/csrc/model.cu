@@ -476,7 +476,7 @@ void gwsem_model::fit_rows_device(const double* d_geno, const double* d_maf, int
     }
     d_R.ensure(5 * (size_t)nf * n);
     d_nrows.ensure(n);
-    launch_power_sums(engine, fp, layout, n, d_geno + (size_t)s0 * n_pad, d_featT, nfm_pad, d_R.p, d_nrows.p);
+    launch_power_sums(engine, fp, layout, n, d_geno + (size_t)s0 * n_pad, d_featT, nfm_pad, d_R.p, d_nrows.p, moment_order);
     gwsem_result r = d_res;
     r.est += (size_t)s0 * P; r.vcov += (size_t)s0 * P * P; r.fit += s0; r.maf += s0; r.n_used += s0;
     r.status += s0; r.catch_code += s0; r.catch_var += s0; r.iterations += s0;

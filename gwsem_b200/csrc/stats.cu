@@ -472,7 +472,8 @@ __global__ void __launch_bounds__(128)
 // sharing every feature load: lane = feature (NFG groups of 32), four people in flight per step.
 // Each warp owns a contiguous slice of people and sums it in order; the eight partial sums are then
 // added in warp order: deterministic.
-template <int S, int NFG>
+// NPOW: powers of the genotype kept (5: g^0..g^4 for the fourth-order moments of WLS cumulants; 3: ML reads up to g^2).
+template <int S, int NFG, int NPOW>
 __global__ void __launch_bounds__(256)
     power_sums_split_kernel(FitProgram fp, int n_snps, int n_src, int n_pad, const uint8_t* __restrict__ inc8,
                             const double* __restrict__ geno, const double* __restrict__ featT, int n_featm_pad,
@@ -482,13 +483,13 @@ __global__ void __launch_bounds__(256)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int snp0 = blockIdx.x * S, nf = fp.nf;
   const double nan = __longlong_as_double(0x7FF8000000000000ll);
-  double acc[S][NFG][5];
+  double acc[S][NFG][NPOW];
 #pragma unroll
   for (int s = 0; s < S; ++s)
 #pragma unroll
     for (int q = 0; q < NFG; ++q)
 #pragma unroll
-      for (int a = 0; a < 5; ++a) acc[s][q][a] = 0.0;
+      for (int a = 0; a < NPOW; ++a) acc[s][q][a] = 0.0;
   int cnt[S];
 #pragma unroll
   for (int s = 0; s < S; ++s) cnt[s] = 0;
@@ -531,8 +532,10 @@ __global__ void __launch_bounds__(256)
             acc[s][q][0] += hv;
             acc[s][q][1] = fma(g1, hv, acc[s][q][1]);
             acc[s][q][2] = fma(g2, hv, acc[s][q][2]);
-            acc[s][q][3] = fma(g3, hv, acc[s][q][3]);
-            acc[s][q][4] = fma(g4, hv, acc[s][q][4]);
+            if (NPOW > 3) {
+              acc[s][q][3] = fma(g3, hv, acc[s][q][3]);
+              acc[s][q][4] = fma(g4, hv, acc[s][q][4]);
+            }
           }
         }
       }
@@ -547,7 +550,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int q = 0; q < NFG; ++q)
 #pragma unroll
-      for (int a = 0; a < 5; ++a) red[((warp * NFG + q) * 32 + lane) * 5 + a] = acc[s][q][a];
+      for (int a = 0; a < 5; ++a) red[((warp * NFG + q) * 32 + lane) * 5 + a] = a < NPOW ? acc[s][q][a < NPOW ? a : 0] : 0.0;
     __syncthreads();
     if (snp0 + s < n_snps) {
       for (int e = tid; e < NFG * 32 * 5; e += 256) {
@@ -568,22 +571,29 @@ __global__ void __launch_bounds__(256)
 }
 
 void launch_power_sums(gwsem_engine* e, const FitProgram& fp, const PeopleLayout& pl, int n_snps,
-                       const double* d_geno, const double* d_featT, int n_featm_pad, double* d_R, int32_t* d_n) {
+                       const double* d_geno, const double* d_featT, int n_featm_pad, double* d_R, int32_t* d_n, int moment_order) {
   if (n_snps <= 0) return;
   if (fp.nf > 256) fail("too many features for the generic statistics kernel (%d > 256)", fp.nf);
   e->prof_begin(kFamClassSums);
   const int nfg = (fp.nf + 31) / 32;
-#define GW_PS(SS, NFG)                                                                                               \
+#define GW_PS(SS, NFG, NPOW)                                                                                         \
   {                                                                                                                  \
     const size_t smem = (size_t)8 * NFG * 32 * 5 * sizeof(double);                                                   \
-    GW_CUDA(cudaFuncSetAttribute(power_sums_split_kernel<SS, NFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    power_sums_split_kernel<SS, NFG><<<(n_snps + SS - 1) / SS, 256, smem, e->stream>>>(                              \
+    GW_CUDA(cudaFuncSetAttribute(power_sums_split_kernel<SS, NFG, NPOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    power_sums_split_kernel<SS, NFG, NPOW><<<(n_snps + SS - 1) / SS, 256, smem, e->stream>>>(                        \
         fp, n_snps, pl.n_src, pl.n_pad, pl.d_inc8, d_geno, d_featT, n_featm_pad, d_R, d_n);                          \
   }
-  if (nfg == 1) GW_PS(4, 1)
-  else if (nfg == 2) GW_PS(4, 2)
-  else if (nfg <= 4) GW_PS(2, 4)
-  else GW_PS(1, 8)
+  if (moment_order <= 2) {   // ML: second-order moments only -> g^0 .. g^2, more SNPs per CTA share every feature load
+    if (nfg == 1) GW_PS(8, 1, 3)
+    else if (nfg == 2) GW_PS(4, 2, 3)
+    else if (nfg <= 4) GW_PS(4, 4, 3)
+    else GW_PS(2, 8, 3)
+  } else {
+    if (nfg == 1) GW_PS(4, 1, 5)
+    else if (nfg == 2) GW_PS(4, 2, 5)
+    else if (nfg <= 4) GW_PS(2, 4, 5)
+    else GW_PS(1, 8, 5)
+  }
 #undef GW_PS
   GW_CUDA(cudaGetLastError());
   e->prof_end(kFamClassSums);
