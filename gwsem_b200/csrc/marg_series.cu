@@ -14,6 +14,7 @@
 // is accepted when the first neglected term of psi, rho^4 * rms over people of its coefficient, is below
 // tol * rms(psi at rho = 0) -- otherwise (causal SNPs, very rare alleles) marg_stats_kernel handles it as before.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <thread>
@@ -215,6 +216,9 @@ void build_series_features(MargProgram& mp, int n_src, int n_pad, const std::vec
   inv_scale.assign(nf, 0.0);
   tot.assign(nf, 0.0);
   const int q0p = mp.q0p, Kp = mp.Kp;
+  std::atomic<bool> heavy_tail(false);
+  int n_incl_people = 0;
+  for (int s = 0; s < n_src; ++s) n_incl_people += inc[s] ? 1 : 0;
   parallel_for(chunks, [&](int c) {
     const bool narrow = c >= wide_chunks;
     const int cf = narrow ? kTcNarrowFeatures : kTcWideFeatures;
@@ -264,8 +268,11 @@ void build_series_features(MargProgram& mp, int n_src, int n_pad, const std::vec
         }
         hv[s] = v;
       }
-      double mx = 0.0;
-      for (int s = 0; s < n_src; ++s) mx = std::max(mx, std::fabs(hv[s]));
+      double mx = 0.0, ss = 0.0;
+      for (int s = 0; s < n_src; ++s) { mx = std::max(mx, std::fabs(hv[s])); ss += hv[s] * hv[s]; }
+      // three digits resolve 2^-23 of the largest value: for a feature whose largest value is more than a thousand
+      // times its root mean square (an outlier in a covariate, say) that is no longer 1e-5 of a class sum's scale
+      if (narrow && ss > 0.0 && mx > 1000.0 * std::sqrt(ss / std::max(1, n_incl_people))) heavy_tail.store(true);
       int ex = 0;
       if (mx > 0) std::frexp(mx, &ex);
       const double sc = std::ldexp(1.0, grid_bits - ex);
@@ -280,6 +287,10 @@ void build_series_features(MargProgram& mp, int n_src, int n_pad, const std::vec
     }
     tc5_pack_chunk(q.data(), cf, n_pad, dst, narrow);
   });
+  if (heavy_tail.load()) {   // leave such models to the per-person kernel
+    mp.se_nf = mp.se_n_wide = mp.se_n_narrow = 0;
+    packed.clear();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ device: assembly

@@ -443,10 +443,12 @@ void gwsem_model::prepare_marginals(const std::vector<int>& dest_of) {
       std::vector<int8_t> packed;
       std::vector<double> inv, tot, err;
       build_series_features(mp, n_src, n_pad, inc, zz, cat, X, sc0, packed, inv, tot, err);
-      d_seq = up(pool, packed, st);
-      d_se_inv_scale = up(pool, inv, st);
-      mp.se_tot = up(pool, tot, st);
-      mp.se_err = up(pool, err, st);
+      if (mp.se_nf > 0) {   // (0: a feature too heavy-tailed for three digits; the per-person kernel serves the model)
+        d_seq = up(pool, packed, st);
+        d_se_inv_scale = up(pool, inv, st);
+        mp.se_tot = up(pool, tot, st);
+        mp.se_err = up(pool, err, st);
+      }
     }
   }
   mp.cat = up(pool, cat, st);
