@@ -6,7 +6,9 @@
 //   a continuous variable contributes sd * rho to a covariance
 //   model-implied vector: RAM moments conditional on the exogenous covariates, ordinal rows
 //   standardised by the implied sd; damped Gauss-Newton with the analytic Jacobian.
-// Mirrors oracle/marginals_oracle.py (fit_snp_marginals).
+// Mirrors oracle/marginals_oracle.py (fit_snp_marginals).  Two kernels (marg_fit_impl.cuh): marg_fit_kernel, the generic
+// one (full records of marg_exact, any model), and marg_fit_fast_kernel, the same estimator with the SNP-independent
+// algebra taken out of the loop for records assembled from the SNP-independent item side (series path / marg_stats).
 #include <algorithm>
 
 #include "common.h"

@@ -4,19 +4,18 @@
 // the features as four balanced base-256 digits [people x 4F], int8 x int8 -> int32 -- but issued as
 // tcgen05.mma kind::i8 with the one-hot A operand written straight to tensor memory:
 //
-//   thread t of the CTA = SNP snp0 + t = TMEM lane t.  Per pair of 32-person blocks it reads the 16 packed
-//   bytes of its SNP from the staged tile, expands them with PRMT (the packed word is the selector, see
-//   stats_imma.cu) into the het and the hom-ALT indicator rows -- 2 x 16 registers -- and stores them with
-//   tcgen05.st into its lane of the two A buffers (M = 128 SNPs, K = 32 people per MMA).  One thread then
-//   issues, per block, one MMA per class against the feature digits in shared memory (K-major canonical
-//   layout without swizzle, packed on the host) into the two accumulators D_het / D_hom [128 x N] in TMEM.
-//   The A buffers are double buffered; a tcgen05.commit -> mbarrier per buffer tells the CTA when the MMAs
-//   that read it are done.  The legacy mma.sync path spends 8.4 clk/SMSP per IMMA and overlaps only partly
-//   with the integer ALU work of the expansion (scripts/mma_rate.cu); here the tensor work is asynchronous
-//   and the expansion is the only thing the warps issue.
+//   SNP snp0 + t = TMEM lane t (M = 128 SNPs per CTA).  Expanding thread t reads, per pair of 32-person blocks, the 16
+//   packed bytes of its SNP from the staged tile, expands them with PRMT (the packed word is the selector, see
+//   stats_imma.cu) into the het and the hom-ALT indicator rows -- 2 x 16 registers -- and stores them with tcgen05.st
+//   into its lane of an A buffer of the ring (K = 32 people per MMA).  With a ring of four buffers two groups of four
+//   expanding warps take alternate stages.  Two more warps issue the MMAs, one per genotype class: per block one
+//   tcgen05.mma against the feature digits in shared memory (K-major canonical layout without swizzle, packed on the
+//   host) into the class's accumulator D_het / D_hom [128 x N] in TMEM, then a tcgen05.commit -> mbarrier that tells
+//   the expanding warps when the buffer is free again.  The tile's feature digits arrive by one cp.async.bulk (TMA)
+//   per tile, the packed rows by cp.async.  N = 16 / 64 digit columns for the cumulants and ML class sums, 128 / 144
+//   for the series path of the WLS marginals statistics (marg_series.cu).  What bounds it: DESIGN.md section 4.
 //
-// TMEM columns (32-bit): [0, N) D_het, [N, 2N) D_hom, then A[buffer][class] of 16 columns each (2 blocks x 8),
-// three buffers.
+// TMEM columns (32-bit): [0, N) D_het, [N, 2N) D_hom, then A[buffer][class] of 16 columns each (2 blocks x 8).
 #include "common.h"
 #include "kernels.h"
 
@@ -28,7 +27,7 @@ namespace gwsem {
 
 namespace {
 
-constexpr int kTcThreads = 128;   // expanding threads = SNPs per CTA = TMEM lanes; a fifth warp issues the MMAs
+constexpr int kTcThreads = 128;   // SNPs per CTA = TMEM lanes = threads of one expanding group
 constexpr int kTcGPad = 16;
 
 __device__ __forceinline__ unsigned prmt_raw(unsigned a, unsigned b, unsigned sel) {
