@@ -468,3 +468,44 @@ def test_series_path_and_structured_fit_match_the_per_person_kernels(engine, mon
     k = flat["par_names"].index("snp_to_F")
     z = res.est[:, k] / np.sqrt(res.vcov[:, k, k])
     assert abs(z[50]) > 8 and abs(z[51]) > 8                      # the causal SNPs are found
+
+
+def test_series_path_with_row_filter_and_missing_phenotypes(engine, monkeypatch):
+    """rowFilter (people skipped in the genotype file) and phenotype NAs (naAction = 'omit') under the class-sum
+    statistics path: excluded people carry zero features, the class counts come from the masked popcounts.  Against
+    the oracle on the retained people, and against the per-person kernels."""
+    import marginals_oracle as mo
+    from gwsem_b200.engine import Model
+    n_src = 9000
+    rng = np.random.default_rng(5)
+    rf = rng.random(n_src) < 0.2
+    n = int((~rf).sum())
+    ph = cohort(n, 41, 3, 2, [True, True, True])
+    ph.loc[ph.index[::29], "pc1"] = np.nan          # naAction = 'omit' on a covariate
+    ph["i2"] = ph["i2"].astype(object)
+    ph.loc[ph.index[5::31], "i2"] = np.nan          # ... and on an ordinal item
+    ph["i2"] = pd.Categorical(ph["i2"], ordered=True)
+    model = buildOneFac(ph, ["i1", "i2", "i3"], covariates=["pc1", "pc2"])
+    flat = flatten(model)
+    data, ncat = model_columns(model)
+    codes = synth.simulate_hardcalls(n_src, 24, seed=6, maf_range=(0.1, 0.5))
+    geno = np.array([0.0, 1.0, 2.0, np.nan])[codes[:, ~rf]]
+    want = [mo.fit_snp_marginals(flat, data, g, ncat) for g in geno[:6]]
+    gm = Model(engine, flat, data, ncat)
+    gm.set_row_filter(rf)
+    res = gm.fit_2bit(synth.pack_2bit(codes))
+    gm.close()
+    compare_first = type("R", (), {})()
+    for f in ("est", "vcov", "status", "catch_code", "n_used"):
+        setattr(compare_first, f, getattr(res, f)[:6])
+    compare(compare_first, want, flat["par_names"])
+    monkeypatch.setenv("GWSEM_NO_SERIES", "1")
+    monkeypatch.setenv("GWSEM_FIT_GENERIC", "1")
+    gm2 = Model(engine, flat, data, ncat)
+    gm2.set_row_filter(rf)
+    ref = gm2.fit_2bit(synth.pack_2bit(codes))
+    gm2.close()
+    assert np.array_equal(res.status, ref.status) and np.array_equal(res.n_used, ref.n_used)
+    se = np.sqrt(np.diagonal(ref.vcov, axis1=1, axis2=2))
+    assert np.max(np.abs(res.est - ref.est) / np.maximum(np.abs(ref.est), se)) < 2e-5
+    assert np.max(np.abs(np.sqrt(np.diagonal(res.vcov, axis1=1, axis2=2)) / se - 1)) < 1e-5
