@@ -509,3 +509,31 @@ def test_series_path_with_row_filter_and_missing_phenotypes(engine, monkeypatch)
     se = np.sqrt(np.diagonal(ref.vcov, axis1=1, axis2=2))
     assert np.max(np.abs(res.est - ref.est) / np.maximum(np.abs(ref.est), se)) < 2e-5
     assert np.max(np.abs(np.sqrt(np.diagonal(res.vcov, axis1=1, axis2=2)) / se - 1)) < 1e-5
+
+
+def test_series_path_binary_and_seven_level_items(engine, monkeypatch):
+    """Items with two, four and seven categories, no covariates: the class-sum path against the per-person kernels."""
+    from gwsem_b200.engine import Model
+    n = 15000
+    rng = np.random.default_rng(91)
+    F = rng.normal(size=n)
+    ph = pd.DataFrame()
+    for j, (lam, cuts) in enumerate([(.8, [0.2]), (.7, [-.67, 0, .67]), (.6, [-1.2, -.6, -.2, .2, .6, 1.2])]):
+        ph[f"i{j + 1}"] = pd.Categorical(np.searchsorted(cuts, lam * F + rng.normal(size=n)), ordered=True)
+    model = buildOneFac(ph, ["i1", "i2", "i3"])
+    flat = flatten(model)
+    data, ncat = model_columns(model)
+    assert ncat == {"i1": 2, "i2": 4, "i3": 7}
+    packed = synth.pack_2bit(synth.simulate_hardcalls(n, 64, seed=92, maf_range=(0.03, 0.5)))
+    gm = Model(engine, flat, data, ncat)
+    res = gm.fit_2bit(packed)
+    gm.close()
+    monkeypatch.setenv("GWSEM_NO_SERIES", "1")
+    monkeypatch.setenv("GWSEM_FIT_GENERIC", "1")
+    gm2 = Model(engine, flat, data, ncat)
+    ref = gm2.fit_2bit(packed)
+    gm2.close()
+    assert (ref.status == 0).all() and np.array_equal(res.status, ref.status)
+    se = np.sqrt(np.diagonal(ref.vcov, axis1=1, axis2=2))
+    assert np.max(np.abs(res.est - ref.est) / np.maximum(np.abs(ref.est), se)) < 2e-5
+    assert np.max(np.abs(np.sqrt(np.diagonal(res.vcov, axis1=1, axis2=2)) / se - 1)) < 1e-5
