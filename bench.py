@@ -553,6 +553,7 @@ def roofline(which, m, n_snps, steps, fp64_peak):
                 "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": src,
                 "launches_timed": n_k, "launches_per_step": n_k / steps, "kernel_ms_share": share,
                 "algorithmic_ops_per_launch": per_launch,
+                "peak_bf16_measured": peak / 2.0, "achieved_over_bf16_peak": achieved / (peak / 2.0) if achieved else None,
                 "fp64_equivalent": {"tflops": fp64_eq, "fp64_peak_tflops": fp64_peak, "ratio": fp64_eq / fp64_peak if fp64_peak else None,
                                     "note": "SURVEY.md section 8(d)'s 1,624 N FP64 flop per SNP (the per-person algorithm the reference "
                                             "runs) x SNPs / whole-step time, against the DFMA peak measured in this run: above 1 because "
