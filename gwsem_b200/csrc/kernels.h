@@ -59,7 +59,7 @@ constexpr int kTcWideFeatures = 32;     // features per wide chunk (4 digits eac
 constexpr int kTcNarrowFeatures = 48;   // features per narrow chunk (3 digits each: 144 digit columns)
 size_t tc5_wide_chunk_bytes(int n_pad);
 size_t tc5_narrow_chunk_bytes(int n_pad);
-void tc5_pack_chunk(const int64_t* q, int n_in_chunk, int n_pad, int8_t* chunk_base, bool narrow);
+void tc5_pack_chunk(const int64_t* q, int fi0, int n_in_chunk, int n_pad, int8_t* chunk_base, bool narrow);
 void launch_class_sums_tc5_wide(gwsem_engine* e, const uint8_t* d_packed, int64_t pitch, int n_snps, int plink1,
                                 const PeopleLayout& pl, const int8_t* d_featq, const double* d_inv_scale, int n_wide,
                                 int n_narrow, double* d_sums);

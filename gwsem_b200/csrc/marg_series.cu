@@ -219,10 +219,12 @@ void build_series_features(MargProgram& mp, int n_src, int n_pad, const std::vec
   std::atomic<bool> heavy_tail(false);
   int n_incl_people = 0;
   for (int s = 0; s < n_src; ++s) n_incl_people += inc[s] ? 1 : 0;
-  parallel_for(chunks, [&](int c) {
+  constexpr int kParts = 4;   // a chunk's features in four tasks: 92 tasks keep 16 host threads evenly busy
+  parallel_for(chunks * kParts, [&](int task) {
+    const int c = task / kParts, part = task % kParts;
     const bool narrow = c >= wide_chunks;
-    const int cf = narrow ? kTcNarrowFeatures : kTcWideFeatures;
-    const int first = narrow ? n_wide + (c - wide_chunks) * kTcNarrowFeatures : c * kTcWideFeatures;
+    const int cf_all = narrow ? kTcNarrowFeatures : kTcWideFeatures, cf = cf_all / kParts, fi_base = part * cf;
+    const int first = (narrow ? n_wide + (c - wide_chunks) * kTcNarrowFeatures : c * kTcWideFeatures) + fi_base;
     const int grid_bits = narrow ? 22 : 30;
     int8_t* dst = packed.data() + (narrow ? wide_bytes * wide_chunks + narrow_bytes * (size_t)(c - wide_chunks) : wide_bytes * (size_t)c);
     std::vector<double> h((size_t)cf * n_pad, 0.0);
@@ -285,7 +287,7 @@ void build_series_features(MargProgram& mp, int n_src, int n_pad, const std::vec
       }
       tot[first + fi] = (double)acc * inv_scale[first + fi];
     }
-    tc5_pack_chunk(q.data(), cf, n_pad, dst, narrow);
+    tc5_pack_chunk(q.data(), fi_base, cf, n_pad, dst, narrow);
   });
   if (heavy_tail.load()) {   // leave such models to the per-person kernel
     mp.se_nf = mp.se_n_wide = mp.se_n_narrow = 0;

@@ -565,11 +565,12 @@ void tc5_pack_features(const std::vector<std::vector<int64_t>>& q, int n_pad, co
 //   narrow kTcNarrowFeatures features x 3 digits, digit-major columns (48 d + f): 144 columns
 size_t tc5_wide_chunk_bytes(int n_pad) { return (size_t)((n_pad / 32 + 31) / 32 * 32) * (kTcWideFeatures * 4) * 32; }
 size_t tc5_narrow_chunk_bytes(int n_pad) { return (size_t)((n_pad / 32 + 31) / 32 * 32) * (kTcNarrowFeatures * 3) * 32; }
-void tc5_pack_chunk(const int64_t* q, int n_in_chunk, int n_pad, int8_t* chunk_base, bool narrow) {
+void tc5_pack_chunk(const int64_t* q, int fi0, int n_in_chunk, int n_pad, int8_t* chunk_base, bool narrow) {
+  // features fi0 .. fi0 + n_in_chunk - 1 of the chunk from q[feature - fi0][n_pad] (distinct features write distinct bytes)
   const int digits = narrow ? 3 : 4, ncol = narrow ? kTcNarrowFeatures * 3 : kTcWideFeatures * 4;
-  for (int fi = 0; fi < n_in_chunk; ++fi)
+  for (int fi = fi0; fi < fi0 + n_in_chunk; ++fi)
     for (int i = 0; i < n_pad; ++i) {
-      int64_t v = q[(size_t)fi * n_pad + i];
+      int64_t v = q[(size_t)(fi - fi0) * n_pad + i];
       if (v == 0) continue;
       for (int d = 0; d < digits; ++d) {
         const int64_t digit = ((v + 128) & 255) - 128;
