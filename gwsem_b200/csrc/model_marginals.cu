@@ -696,7 +696,9 @@ void gwsem_model::run_marginals(const uint8_t* d_packed, int64_t pitch, const do
   }
   d_summary.ensure((size_t)n * mp.sum_stride);
   mpl.cs_sums = nullptr;
-  if (!d_geno && mp.cs_nf > 0) {
+  // (with the series path on, the per-person kernel only sees the SNPs that path turned down, nearly all of them with a
+  // series root to start from: the six-product class sums for its iteration 0 are not worth a launch over the batch)
+  if (!d_geno && mp.cs_nf > 0 && mp.se_nf == 0) {
     d_cs_sums.ensure((size_t)n * 2 * mp.cs_nf);
     launch_class_sums_tc5(engine, d_packed, pitch, n, plink1, layout, d_csq, d_cs_inv_scale, mp.cs_nf, d_cs_sums.p, nullptr);
     mpl.cs_sums = d_cs_sums.p;
